@@ -1,0 +1,188 @@
+/*
+ * tmf.h -- C ABI of libtmf.so, the sm_100a (B200) matrix-factorization hot path
+ * that replaces the TensorFlow ops TeAMOFlow's `teamoflow.mf` calls.
+ *
+ * The reference has NO FFI/operator registry (it is pure Python over TensorFlow), so
+ * there is no existing native interface to mirror; every entry point below replaces
+ * the TensorFlow call sites cited beside it (paths relative to the reference repo,
+ * src/teamoflow/mf/...).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all buffers, including workspaces; the library allocates nothing
+ *     persistent and holds no global state (except a per-thread error string);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device unless its comment says so;
+ *   - return value: 0 = ok, negative = TMF_E_* (message via tmf_last_error());
+ *   - embedding matrices are row-major fp32 with a leading dimension `ld` (in floats),
+ *     `ld % 4 == 0` and 16-byte aligned base (rows are read with 128-bit loads);
+ *     columns [r, ld) must be zero;
+ *   - index arrays are int32 (nnz and n_users*n_samples must be < 2^31).
+ */
+#ifndef TMF_H_
+#define TMF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMF_ABI_VERSION 1
+
+enum {
+  TMF_OK = 0,
+  TMF_E_INVALID = -1,  /* bad argument (shape / alignment / range) */
+  TMF_E_CUDA = -2,     /* CUDA runtime error, see tmf_last_error() */
+  TMF_E_WORKSPACE = -3 /* workspace too small */
+};
+
+enum { TMF_LOSS_MSE = 0, TMF_LOSS_WMRB = 1 };
+
+typedef void* tmf_stream_t;
+
+#if defined(__GNUC__)
+#define TMF_API __attribute__((visibility("default")))
+#else
+#define TMF_API
+#endif
+
+TMF_API int tmf_abi_version(void);
+TMF_API const char* tmf_last_error(void); /* thread-local, valid until the next failing call on this thread */
+
+/* ------------------------------------------------------------------ setup (once per fit) */
+
+/* row_ptr[n_rows+1] from row-major-sorted COO row ids (tf_interactions.indices[:,0],
+ * loss_graphs.py:47 / utils.py:53-57). */
+TMF_API int tmf_rowptr_from_sorted(const int32_t* rows, int64_t nnz, int32_t n_rows, int32_t* row_ptr, tmf_stream_t stream);
+
+/* Stable counting transpose: perm = stable argsort(keys) (keys in [0, n_keys)), ptr[n_keys+1] =
+ * segment starts.  Builds the item-major (CSC) view of the interactions and of the sampled
+ * negatives (random_ind, matrix_factorization.py:72-73) and X^T for the embedding backward.
+ * Workspace size from tmf_transpose_ws_bytes(n). */
+TMF_API size_t tmf_transpose_ws_bytes(int64_t n);
+TMF_API int tmf_transpose_build(const int32_t* keys, int64_t n, int32_t n_keys, int32_t* ptr, int32_t* perm,
+                        void* ws, size_t ws_bytes, tmf_stream_t stream);
+
+/* item-major list of (user, coefficient slot): for e < nnz the user is coo_rows[perm[e]], otherwise
+ * (perm[e]-nnz)/n_samples (the flattened [n_users, n_samples] sample table follows the interactions). */
+TMF_API int tmf_tlist_users(const int32_t* perm, int64_t n, int64_t nnz, const int32_t* coo_rows, int32_t n_samples,
+                    int32_t* users_out, tmf_stream_t stream);
+
+/* Negatives without replacement: S distinct items per user (utils.py:20-22, np.random.choice
+ * replace=False) via a keyed bijection of [0, n_items); out is [n_users, S] int64 like random_ind. */
+TMF_API int tmf_sample_items(int32_t n_users, int32_t n_items, int32_t n_samples, uint64_t seed, int64_t* out,
+                     tmf_stream_t stream);
+
+/* Initializers (initializer_graphs.py:34,51): iid N(0,1) / U[0,1) then a GLOBAL l2 normalise
+ * x * rsqrt(max(sum x^2, 1e-12)).  w is [n_rows, ld], only columns < n_cols are filled.
+ * ws: >= tmf_reduce_ws_bytes() bytes. */
+TMF_API size_t tmf_reduce_ws_bytes(void);
+TMF_API int tmf_fill_normal(float* w, int64_t n_rows, int32_t n_cols, int32_t ld, uint64_t seed, tmf_stream_t stream);
+TMF_API int tmf_fill_uniform(float* w, int64_t n_rows, int32_t n_cols, int32_t ld, uint64_t seed, tmf_stream_t stream);
+TMF_API int tmf_l2_normalize_global(float* w, int64_t n, void* ws, tmf_stream_t stream);
+
+/* ------------------------------------------------------------------ training step */
+
+/* Generic deterministic segment-sum of scaled rows:
+ *     out[s, :] = sum_{e in [seg_ptr[s], seg_ptr[s+1])} c(e) * src[idx[e], :]
+ *     c(e) = coef[cpos ? cpos[e] : e]   (coef == NULL means c(e) = 1)
+ * Covers X.W (embedding_graphs.py:38,58,85), X^T.dE (its backward) and the item-major gradient
+ * dE_i = dP^T E_u (backward of matrix_factorization.py:149) without ever forming dP.
+ * Fixed chunking => bitwise reproducible.  ws: tmf_spmm_ws_bytes(n_entries, ld_out). */
+TMF_API size_t tmf_spmm_ws_bytes(int64_t n_entries, int32_t ld_out);
+TMF_API int tmf_spmm_seg(int32_t n_seg, const int32_t* seg_ptr, int64_t n_entries, const int32_t* idx,
+                 const int32_t* cpos, const float* coef, const float* src, int32_t ld_src, float* out,
+                 int32_t ld_out, int32_t n_cols, void* ws, size_t ws_bytes, tmf_stream_t stream);
+
+/* Fused user-major pass of one training step (replaces matrix_factorization.py:149-167 forward and
+ * the user half of :170): per user, sample scores <E_u, E_i[J_u]>, per-interaction scores, the loss
+ * (MSE loss_graphs.py:47-52 / WMRB :74-88), d(sum loss)/d(score) coefficients and dE_u.
+ *   loss_out[nnz]        per-interaction loss (0 where WMRB ignores a non-positive value)
+ *   coef_out[nnz + n_users*n_samples]   c_k, then G[u, j] (WMRB only)
+ *   dEu[n_users, ld]
+ *   order: optional heavy-first user permutation (NULL = natural), counter: one int32 work counter.
+ */
+TMF_API int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int64_t nnz, const int32_t* row_ptr, const int32_t* col_idx,
+                  const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
+                  const int32_t* samp, int32_t n_samples, const int32_t* order, int32_t* counter,
+                  float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream);
+
+/* p[k] = <Eu[rows[k]], Ei[cols[k]]>  (tf.gather_nd(predictions, indices), matrix_factorization.py:154,160) */
+TMF_API int tmf_pair_dots(int64_t nnz, const int32_t* rows, const int32_t* cols, const float* Eu, const float* Ei,
+                  int32_t ld, float* p, tmf_stream_t stream);
+
+/* KL loss (loss_graphs.py:111-122): scalar loss_out[0] and d loss / d p[k] in coef_out[nnz]. ws >= tmf_reduce_ws_bytes(). */
+TMF_API int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float* loss_out, float* coef_out, void* ws,
+                tmf_stream_t stream);
+
+/* Adam step t=1 from zero moments (a new tf.keras.optimizers.Adam each epoch, matrix_factorization.py:176). */
+TMF_API int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream);
+
+/* out[0] = sum(x[0..n)) accumulated in fp64, fixed order (reduce_mean numerator, :179). ws >= tmf_reduce_ws_bytes(). */
+TMF_API int tmf_reduce_sum(const float* x, int64_t n, float* out, void* ws, tmf_stream_t stream);
+
+/* ---- BiasedLinear / ReLU embedding pieces (embedding_graphs.py:52-58, :73-87) */
+TMF_API int tmf_bias_add(float* E, int64_t n_rows, int32_t n_cols, int32_t ld, const float* bias, int32_t relu, tmf_stream_t stream);
+TMF_API int tmf_col_sum(const float* dE, int64_t n_rows, int32_t n_cols, int32_t ld, float* out, void* ws, size_t ws_bytes,
+                tmf_stream_t stream); /* ws: 1024*ld floats */
+TMF_API int tmf_relu_mask(float* dH, const float* H, int64_t n, tmf_stream_t stream); /* dH *= (H > 0) */
+/* C[m,n] (ldc) = op(A) op(B), fp32 FMA chain; ta/tb: 0 = as stored, 1 = transposed. */
+TMF_API int tmf_gemm_f32(int32_t ta, int32_t tb, int32_t m, int32_t n, int32_t k, const float* A, int32_t lda,
+                 const float* B, int32_t ldb, float* C, int32_t ldc, tmf_stream_t stream);
+
+/* ---- unfused forward-only loss entry points behind LossGraph.get_loss (loss_graphs.py) */
+TMF_API int tmf_gather_rows2d(const float* in, int32_t n_rows, int64_t n_cols, const int64_t* index, int32_t k,
+                      float* out, tmf_stream_t stream); /* gather_matrix_indices, utils.py:94-105 */
+TMF_API int tmf_gather_nd2(const float* in, int64_t n_cols, const int64_t* indices2, int64_t n, float* out,
+                   tmf_stream_t stream); /* tf.gather_nd(params, indices[n,2]) */
+TMF_API int tmf_wmrb_forward(int64_t n_pos, const int32_t* pos_rows, const float* pos_pred, const float* sample_pred,
+                     int32_t n_samples, float scale, float* loss_out, tmf_stream_t stream);
+
+/* ------------------------------------------------------------------ scoring / top-k / metrics */
+
+/* fp32 [n, ld] -> bf16 [n_pad, k_pad] (zero padded) + per-row l2 norms; operands of the tcgen05 GEMM. */
+TMF_API int tmf_pack_bf16(const float* src, int64_t n, int32_t n_comp, int32_t ld, uint16_t* dst, int64_t n_pad,
+                  int32_t k_pad, float* norms, tmf_stream_t stream);
+
+/* U.V^T (matrix_factorization.py:195) + per-row top-k (tf.math.top_k, :245,:429) as ONE kernel:
+ * tcgen05 bf16 GEMM, accumulators in TMEM, fused threshold/candidate epilogue; then an fp32/fp64
+ * canonical rerank so indices are exact.  Scores are never written to HBM.
+ *   clamp != 0: scores <= 0 are +0.0 before ranking (recall_at_k path, :237).
+ *   item_offset: global index of this GPU's first item (item-sharded scoring).
+ *   out_idx[n_users, k] int32 (global ids), out_score[n_users, k] fp32 canonical scores.
+ * Workspace from tmf_score_topk_ws_bytes. */
+TMF_API size_t tmf_score_topk_ws_bytes(int64_t n_users, int64_t n_items, int32_t n_comp, int32_t k);
+TMF_API int tmf_score_topk(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                   int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
+                   size_t ws_bytes, tmf_stream_t stream);
+
+/* merge G per-shard top-k lists ([G, n_users, k]) -> [n_users, k], comparator (score desc, idx asc). */
+TMF_API int tmf_topk_merge(const int32_t* idx_in, const float* score_in, int32_t n_lists, int64_t n_users, int32_t k,
+                   int32_t* out_idx, float* out_score, tmf_stream_t stream);
+
+/* dense canonical scores P[n_users, n_items] (predict(), :195) -- small shapes only. */
+TMF_API int tmf_predict_dense(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                      float* P, tmf_stream_t stream);
+
+/* full descending ranking of every row of P (top_k(k = n_items), :336,:367,:432,:438), ties -> lower index. */
+TMF_API size_t tmf_rank_rows_ws_bytes(int64_t n_rows, int64_t n_cols);
+TMF_API int tmf_rank_rows(const float* P, int64_t n_rows, int64_t n_cols, int32_t clamp, int32_t* out_idx, void* ws,
+                  size_t ws_bytes, tmf_stream_t stream);
+
+/* hits[u] = #{i in topk[u] : A[u,i] != 0}, relevant[u] = #{i : A[u,i] > 0} for CSR A (:248-254). */
+TMF_API int tmf_metrics_hits(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
+                     const float* a_val, float* hits, float* relevant, tmf_stream_t stream);
+
+/* dcg[u] = sum_{q<k} (2^A[u,topk[u,q]] - 1) / log2(q+2)   (:339-351) */
+TMF_API int tmf_dcg(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
+            const float* a_val, float* dcg, tmf_stream_t stream);
+/* idcg[u]: gains of row u sorted descending (zeros between positives and negatives), first k (:370-384) */
+TMF_API int tmf_idcg(int64_t n_users, int64_t n_items, int32_t k, const int32_t* a_ptr, const float* a_val, float* idcg,
+             float* row_nnz, tmf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMF_H_ */

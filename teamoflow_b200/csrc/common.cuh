@@ -1,0 +1,77 @@
+// Shared device/host helpers for libtmf (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tmf.h"
+
+namespace tmf {
+
+void set_error(const char* fmt, ...);
+
+#define TMF_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      tmf::set_error(__VA_ARGS__);  \
+      return TMF_E_INVALID;         \
+    }                               \
+  } while (0)
+
+#define TMF_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      tmf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TMF_E_CUDA;                                                            \
+    }                                                                               \
+  } while (0)
+
+#define TMF_LAUNCH_CHECK() TMF_CUDA(cudaGetLastError())
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline cudaStream_t as_stream(tmf_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- sub-warp "row groups": LPR lanes (power of two) cooperate on one embedding row,
+//      each lane owning one float4 (128-bit) column slice.
+template <int LPR>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (LPR == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << LPR) - 1u) << (lane & ~(unsigned)(LPR - 1));
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, LPR);
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float c, const float4& r) {
+  acc.x = fmaf(c, r.x, acc.x);
+  acc.y = fmaf(c, r.y, acc.y);
+  acc.z = fmaf(c, r.z, acc.z);
+  acc.w = fmaf(c, r.w, acc.w);
+}
+
+__device__ __forceinline__ void add4(float4& acc, const float4& r) {
+  acc.x += r.x;
+  acc.y += r.y;
+  acc.z += r.z;
+  acc.w += r.w;
+}
+
+}  // namespace tmf

@@ -1,0 +1,271 @@
+// Scoring-side helpers: dense canonical scores, full row rankings, top-k list merge, metrics.
+// (The fused tcgen05 U.V^T + top-k kernel lives in score_topk.cu.)
+#include <cub/device/device_segmented_radix_sort.cuh>
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tmf {
+
+// canonical score: fp64 FMA chain in component order, rounded once to fp32
+__global__ void __launch_bounds__(256) predict_dense_kernel(const float* __restrict__ U, long long n_u, const float* __restrict__ V,
+                                                            long long n_i, int r, int ld, float* __restrict__ P) {
+  extern __shared__ float sm[];  // [16][r] users, [16][r] items
+  float* sU = sm;
+  float* sV = sm + 16 * r;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const long long u0 = (long long)blockIdx.y * 16, i0 = (long long)blockIdx.x * 16;
+  for (int t = threadIdx.x; t < 16 * r; t += 256) {
+    const int row = t / r, c = t % r;
+    sU[t] = (u0 + row < n_u) ? U[(u0 + row) * ld + c] : 0.f;
+    sV[t] = (i0 + row < n_i) ? V[(i0 + row) * ld + c] : 0.f;
+  }
+  __syncthreads();
+  if (u0 + ty >= n_u || i0 + tx >= n_i) return;
+  double acc = 0.0;
+  for (int c = 0; c < r; ++c) acc = fma((double)sU[ty * r + c], (double)sV[tx * r + c], acc);
+  P[(u0 + ty) * n_i + (i0 + tx)] = (float)acc;
+}
+
+__global__ void rank_prep_kernel(const float* __restrict__ P, long long n_rows, long long n_cols, int clamp,
+                                 float* __restrict__ keys, int* __restrict__ vals, int* __restrict__ offs) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_rows * n_cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = i; j <= n_rows; j += stride) offs[j] = (int)(j * n_cols);
+  for (; i < total; i += stride) {
+    float v = P[i];
+    if (clamp) v = v > 0.f ? v : 0.f;   // tf.where(p > 0, p, 0.0), matrix_factorization.py:237
+    keys[i] = v + 0.0f;                 // -0.0 -> +0.0 so equal scores share one radix key
+    vals[i] = (int)(i % n_cols);
+  }
+}
+
+// ---- top-k list merge: comparator (score desc, index asc); one warp per user, rank by counting
+constexpr int kMergeWarps = 4;
+__global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_kernel(const int* __restrict__ idx_in, const float* __restrict__ sc_in,
+                                                                      int G, long long n_users, int k, int* __restrict__ out_idx,
+                                                                      float* __restrict__ out_sc) {
+  extern __shared__ unsigned char smraw[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u = (long long)blockIdx.x * kMergeWarps + w;
+  if (u >= n_users) return;
+  const int n = G * k;
+  float* ss = reinterpret_cast<float*>(smraw) + (size_t)w * n;
+  int* si = reinterpret_cast<int*>(smraw + (size_t)kMergeWarps * n * sizeof(float)) + (size_t)w * n;
+  for (int t = lane; t < n; t += 32) {
+    const int g = t / k, q = t % k;
+    ss[t] = sc_in[((long long)g * n_users + u) * k + q];
+    si[t] = idx_in[((long long)g * n_users + u) * k + q];
+  }
+  __syncwarp();
+  for (int t = lane; t < n; t += 32) {
+    const float s = ss[t];
+    const int id = si[t];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) {
+      const float so = ss[o];
+      rank += (so > s) || (so == s && si[o] < id);
+    }
+    if (rank < k) {
+      out_idx[u * k + rank] = id;
+      out_sc[u * k + rank] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ float csr_lookup(const int* __restrict__ a_idx, const float* __restrict__ a_val, int lo, int hi, int item) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = a_idx[mid];
+    if (c == item) return a_val[mid];
+    if (c < item) lo = mid + 1; else hi = mid;
+  }
+  return 0.f;
+}
+
+// hits = #{q : A[u, topk[u,q]] != 0} (any sign, :248,:254); relevant = #{A[u,:] > 0} (:240,:251)
+__global__ void metrics_hits_kernel(const int* __restrict__ topk, long long n_users, int k, const int* __restrict__ a_ptr,
+                                    const int* __restrict__ a_idx, const float* __restrict__ a_val, float* __restrict__ hits,
+                                    float* __restrict__ relevant) {
+  const long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const int lo = a_ptr[u], hi = a_ptr[u + 1];
+  int h = 0, rel = 0;
+  for (int q = lane; q < k; q += 32) h += csr_lookup(a_idx, a_val, lo, hi, topk[u * k + q]) != 0.f;
+  for (int e = lo + lane; e < hi; e += 32) rel += a_val[e] > 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h += __shfl_xor_sync(0xffffffffu, h, o);
+    rel += __shfl_xor_sync(0xffffffffu, rel, o);
+  }
+  if (lane == 0) {
+    hits[u] = (float)h;
+    relevant[u] = (float)rel;
+  }
+}
+
+__device__ __forceinline__ float dcg_discount(int q) {  // rank q+1 -> log1p(q+1)/log(2), :342-346
+  return log1pf((float)(q + 1)) / logf(2.0f);
+}
+
+__global__ void dcg_kernel(const int* __restrict__ topk, long long n_users, int k, const int* __restrict__ a_ptr,
+                           const int* __restrict__ a_idx, const float* __restrict__ a_val, float* __restrict__ dcg) {
+  const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  const int lo = a_ptr[u], hi = a_ptr[u + 1];
+  float s = 0.f;
+  for (int q = 0; q < k; ++q) {
+    const float a = csr_lookup(a_idx, a_val, lo, hi, topk[u * k + q]);
+    s += (powf(2.0f, a) - 1.0f) / dcg_discount(q);  // :339,:348
+  }
+  dcg[u] = s;
+}
+
+// ideal DCG: gains 2^a - 1 of the row sorted descending -- positives, then the implicit zeros, then
+// negatives (:370-384).  One warp per user; q-th pick = next element in (gain desc, position asc) order.
+__global__ void idcg_kernel(long long n_users, long long n_items, int k, const int* __restrict__ a_ptr,
+                            const float* __restrict__ a_val, float* __restrict__ idcg, float* __restrict__ row_nnz) {
+  const long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (u >= n_users) return;
+  const int lo = a_ptr[u], hi = a_ptr[u + 1];
+  int n_pos = 0, n_neg = 0, n_nz = 0;
+  for (int e = lo + lane; e < hi; e += 32) {
+    const float g = powf(2.0f, a_val[e]) - 1.0f;
+    n_pos += g > 0.f;
+    n_neg += g < 0.f;
+    n_nz += a_val[e] != 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+    n_neg += __shfl_xor_sync(0xffffffffu, n_neg, o);
+    n_nz += __shfl_xor_sync(0xffffffffu, n_nz, o);
+  }
+  const long long n_zero = n_items - n_pos - n_neg;
+  float s = 0.f;
+  float prev_g = INFINITY;
+  int prev_e = -1;
+  for (int q = 0; q < k; ++q) {
+    bool want_pos;
+    if (q < n_pos) want_pos = true;
+    else if (q < n_pos + n_zero) continue;  // a zero gain contributes nothing
+    else want_pos = false;
+    if (q == n_pos + n_zero) { prev_g = INFINITY; prev_e = -1; }  // restart the scan for the negative tail
+    // next element after (prev_g, prev_e) in (gain desc, position asc) order with the wanted sign
+    float best_g = -INFINITY;
+    int best_e = 0x7fffffff;
+    for (int e = lo + lane; e < hi; e += 32) {
+      const float g = powf(2.0f, a_val[e]) - 1.0f;
+      if (want_pos ? !(g > 0.f) : !(g < 0.f)) continue;
+      const bool after_prev = (g < prev_g) || (g == prev_g && e > prev_e);
+      if (!after_prev) continue;
+      if (g > best_g || (g == best_g && e < best_e)) { best_g = g; best_e = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float og = __shfl_xor_sync(0xffffffffu, best_g, o);
+      const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
+      if (og > best_g || (og == best_g && oe < best_e)) { best_g = og; best_e = oe; }
+    }
+    prev_g = best_g;
+    prev_e = best_e;
+    s += best_g / dcg_discount(q);
+  }
+  if (lane == 0) {
+    idcg[u] = s;
+    row_nnz[u] = (float)n_nz;
+  }
+}
+
+}  // namespace tmf
+
+using namespace tmf;
+
+extern "C" int tmf_predict_dense(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                                 float* P, tmf_stream_t stream) {
+  TMF_REQUIRE(n_comp > 0 && n_comp <= ld && n_comp <= 1024, "tmf_predict_dense: bad n_components");
+  if (n_users == 0 || n_items == 0) return TMF_OK;
+  dim3 grid((unsigned)cdiv(n_items, 16), (unsigned)cdiv(n_users, 16));
+  TMF_REQUIRE(grid.y <= 65535, "tmf_predict_dense: too many users for the dense path (use tmf_score_topk)");
+  const size_t smem = (size_t)32 * n_comp * sizeof(float);
+  if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(predict_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  predict_dense_kernel<<<grid, 256, smem, as_stream(stream)>>>(U, n_users, V, n_items, n_comp, ld, P);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+static size_t seg_sort_temp_bytes(int64_t n, int64_t n_rows) {
+  size_t bytes = 0;
+  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, bytes, (const float*)nullptr, (float*)nullptr, (const int*)nullptr,
+                                                     (int*)nullptr, (int)n, (int)n_rows, (const int*)nullptr, (const int*)nullptr);
+  return bytes;
+}
+
+extern "C" size_t tmf_rank_rows_ws_bytes(int64_t n_rows, int64_t n_cols) {
+  const size_t n = (size_t)((n_rows * n_cols + 63) & ~63ll);
+  return seg_sort_temp_bytes(n_rows * n_cols, n_rows) + 3 * n * 4 + (size_t)((n_rows + 64) & ~63ll) * 4 + 1024;
+}
+
+extern "C" int tmf_rank_rows(const float* P, int64_t n_rows, int64_t n_cols, int32_t clamp, int32_t* out_idx, void* ws,
+                             size_t ws_bytes, tmf_stream_t stream) {
+  const long long total = n_rows * n_cols;
+  TMF_REQUIRE(total < (1ll << 31), "tmf_rank_rows: n_rows*n_cols must be < 2^31");
+  TMF_REQUIRE(ws_bytes >= tmf_rank_rows_ws_bytes(n_rows, n_cols), "tmf_rank_rows: workspace too small");
+  if (total == 0) return TMF_OK;
+  const size_t n = (size_t)((total + 63) & ~63ll);
+  float* keys = reinterpret_cast<float*>(ws);
+  float* keys_out = keys + n;
+  int* vals = reinterpret_cast<int*>(keys_out + n);
+  int* offs = vals + n;
+  void* temp = offs + ((n_rows + 64) & ~63ll);
+  size_t temp_bytes = seg_sort_temp_bytes(total, n_rows);
+  cudaStream_t st = as_stream(stream);
+  rank_prep_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 148 * 32), 256, 0, st>>>(P, n_rows, n_cols, clamp, keys, vals, offs);
+  TMF_LAUNCH_CHECK();
+  // stable LSD radix sort: equal keys keep ascending column order == tf.math.top_k tie order
+  TMF_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(temp, temp_bytes, (const float*)keys, keys_out, (const int*)vals, out_idx,
+                                                              (int)total, (int)n_rows, offs, offs + 1, 0, 32, st));
+  return TMF_OK;
+}
+
+extern "C" int tmf_topk_merge(const int32_t* idx_in, const float* score_in, int32_t n_lists, int64_t n_users, int32_t k,
+                              int32_t* out_idx, float* out_score, tmf_stream_t stream) {
+  TMF_REQUIRE(n_lists >= 1 && k >= 1, "tmf_topk_merge: bad sizes");
+  if (n_users == 0) return TMF_OK;
+  const size_t smem = (size_t)kMergeWarps * n_lists * k * 8;
+  TMF_REQUIRE(smem <= 200 * 1024, "tmf_topk_merge: n_lists*k too large");
+  if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  topk_merge_kernel<<<(unsigned)cdiv(n_users, kMergeWarps), kMergeWarps * 32, smem, as_stream(stream)>>>(
+      idx_in, score_in, n_lists, n_users, k, out_idx, out_score);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_metrics_hits(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
+                                const float* a_val, float* hits, float* relevant, tmf_stream_t stream) {
+  if (n_users == 0) return TMF_OK;
+  metrics_hits_kernel<<<(unsigned)cdiv(n_users * 32, 256), 256, 0, as_stream(stream)>>>(topk, n_users, k, a_ptr, a_idx, a_val, hits, relevant);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_dcg(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
+                       const float* a_val, float* dcg, tmf_stream_t stream) {
+  if (n_users == 0) return TMF_OK;
+  dcg_kernel<<<(unsigned)cdiv(n_users, 128), 128, 0, as_stream(stream)>>>(topk, n_users, k, a_ptr, a_idx, a_val, dcg);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_idcg(int64_t n_users, int64_t n_items, int32_t k, const int32_t* a_ptr, const float* a_val, float* idcg,
+                        float* row_nnz, tmf_stream_t stream) {
+  if (n_users == 0) return TMF_OK;
+  idcg_kernel<<<(unsigned)cdiv(n_users * 32, 256), 256, 0, as_stream(stream)>>>(n_users, n_items, k, a_ptr, a_val, idcg, row_nnz);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}

@@ -1,0 +1,879 @@
+// Training-step kernels of the matrix-factorization hot path (HBM/L2-bound gather/scatter work).
+//
+//   user_pass_kernel : fused score + loss + dL/dscore + dE_u for one user per CTA   (tmf_user_pass)
+//   spmm_seg_kernel  : deterministic segment-sum of scaled gathered rows            (tmf_spmm_seg)
+//   adam1 / reductions / KL statistics / bias, relu, small fp32 GEMM
+//
+// No float atomics anywhere: every sum has a fixed association order, so results are
+// bitwise reproducible run to run (north_star: "deterministic order").
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tmf {
+
+// =====================================================================================
+// fused user-major pass
+// =====================================================================================
+
+struct UserPassParams {
+  int n_users, n_items, ld, n_comp, n_samples, s_pad, cache_rows;
+  long long nnz;
+  const int* row_ptr;
+  const int* col_idx;
+  const float* val;
+  const float* Eu;
+  const float* Ei;
+  const int* samp;
+  const int* order;
+  int* counter;
+  float* loss_out;
+  float* coef_out;
+  float* dEu;
+  float scale;  // n_items / n_samples (python true division, loss_graphs.py:86)
+};
+
+template <int LPR, int VPL>
+__device__ __forceinline__ void load_row(const float* __restrict__ base, long long row, int ld, int nv, int lg,
+                                         float4 (&x)[VPL]) {
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) {
+    const int col = lg + LPR * v;
+    x[v] = (col < nv) ? ldg4(base + row * ld + 4 * col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int VPL>
+__device__ __forceinline__ float dotv(const float4 (&a)[VPL], const float4 (&b)[VPL]) {
+  float s = dot4(a[0], b[0]);
+#pragma unroll
+  for (int v = 1; v < VPL; ++v) s += dot4(a[v], b[v]);
+  return s;
+}
+
+constexpr int kUserPassThreads = 256;
+
+// JPL > 0 : each lane keeps JPL sample scores and JPL partial G sums in registers (S <= LPR*JPL)
+// JPL == 0: MSE (no samples)
+// JPL < 0 : generic WMRB, per-group G partials in shared memory
+template <int LPR, int VPL, int JPL, int LOSS>
+__global__ void __launch_bounds__(kUserPassThreads) user_pass_kernel(const UserPassParams p) {
+  constexpr int NT = kUserPassThreads;
+  constexpr int NG = NT / LPR;
+  constexpr int JR = JPL > 0 ? JPL : 1;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ int s_next;
+  const int tid = threadIdx.x;
+  const int g = tid / LPR;
+  const int lg = tid % LPR;
+  const unsigned gm = group_mask<LPR>();
+  const int ld = p.ld;
+  const int nv = ld >> 2;
+  const int S = p.n_samples;
+  float* sS = smem;                     // [s_pad]  sample scores, later final G_j
+  float* sG = sS + p.s_pad;             // [NG][s_pad] per-group partial G
+  float* sAcc = sG + (LOSS == TMF_LOSS_WMRB ? NG * p.s_pad : 0);  // [NG][ld]
+  float* sRows = sAcc + NG * ld;        // [S][ld] optional cache of the sampled item rows
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_next = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int t_user = s_next;
+    if (t_user >= p.n_users) break;
+    const int u = p.order ? p.order[t_user] : t_user;
+    const int a = p.row_ptr[u];
+    const int b = p.row_ptr[u + 1];
+
+    if (a == b) {  // no interactions: all gradients of this user are zero
+      if (LOSS == TMF_LOSS_WMRB)
+        for (int j = tid; j < S; j += NT) p.coef_out[p.nnz + (long long)u * S + j] = 0.f;
+      for (int c = tid; c < ld; c += NT) p.dEu[(long long)u * ld + c] = 0.f;
+      continue;
+    }
+
+    float4 eu[VPL];
+    load_row<LPR, VPL>(p.Eu, u, ld, nv, lg, eu);
+
+    float sj[JR];
+    float gj[JR];
+    if constexpr (LOSS == TMF_LOSS_WMRB) {
+      const int* su = p.samp + (long long)u * S;
+#pragma unroll 4
+      for (int j = g; j < S; j += NG) {
+        float4 row[VPL];
+        load_row<LPR, VPL>(p.Ei, su[j], ld, nv, lg, row);
+        const float s = group_sum<LPR>(dotv<VPL>(eu, row), gm);
+        if (lg == 0) sS[j] = s;
+        if (p.cache_rows) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int col = lg + LPR * v;
+            if (col < nv) reinterpret_cast<float4*>(sRows + (long long)j * ld)[col] = row[v];
+          }
+        }
+      }
+      if constexpr (JPL < 0) {
+        for (int j = lg; j < S; j += LPR) sG[g * p.s_pad + j] = 0.f;
+      }
+      __syncthreads();
+      if constexpr (JPL > 0) {
+#pragma unroll
+        for (int t = 0; t < JPL; ++t) {
+          const int j = lg + LPR * t;
+          sj[t] = (j < S) ? sS[j] : -INFINITY;
+          gj[t] = 0.f;
+        }
+      }
+    }
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- interactions of this user, strided over the NG row groups, next row prefetched
+    int k = a + g;
+    float4 row_n[VPL];
+    float v_n = 0.f;
+    if (k < b) {
+      v_n = p.val[k];
+      load_row<LPR, VPL>(p.Ei, p.col_idx[k], ld, nv, lg, row_n);
+    }
+    for (; k < b; k += NG) {
+      float4 row[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) row[v] = row_n[v];
+      const float a_k = v_n;
+      const int kn = k + NG;
+      if (kn < b) {
+        v_n = p.val[kn];
+        load_row<LPR, VPL>(p.Ei, p.col_idx[kn], ld, nv, lg, row_n);
+      }
+      const float pk = group_sum<LPR>(dotv<VPL>(eu, row), gm);
+      float c = 0.f, l = 0.f;
+      if constexpr (LOSS == TMF_LOSS_MSE) {
+        const float d = a_k - pk;  // loss_graphs.py:52
+        l = d * d;
+        c = -2.0f * d;
+      } else {
+        if (a_k > 0.f) {  // loss_graphs.py:74
+          const float base = __fsub_rn(1.0f, pk);
+          float sum = 0.f, cnt = 0.f;
+          if constexpr (JPL > 0) {
+            unsigned ind = 0;
+#pragma unroll
+            for (int t = 0; t < JPL; ++t) {
+              const float h = __fadd_rn(base, sj[t]);  // (1 - p) + s, loss_graphs.py:84
+              if (h >= 0.f) {                           // TF maximum(x, 0): gradient to x when x >= 0
+                ind |= 1u << t;
+                sum += h;
+                cnt += 1.f;
+              }
+            }
+            sum = group_sum<LPR>(sum, gm);
+            cnt = group_sum<LPR>(cnt, gm);
+            const float m = p.scale * sum;                 // :86
+            l = logf(__fadd_rn(1.0f, m));                  // :88
+            const float w = p.scale / __fadd_rn(1.0f, m);
+            c = -w * cnt;
+#pragma unroll
+            for (int t = 0; t < JPL; ++t)
+              if (ind & (1u << t)) gj[t] += w;
+          } else {
+            for (int j = lg; j < S; j += LPR) {
+              const float h = __fadd_rn(base, sS[j]);
+              if (h >= 0.f) {
+                sum += h;
+                cnt += 1.f;
+              }
+            }
+            sum = group_sum<LPR>(sum, gm);
+            cnt = group_sum<LPR>(cnt, gm);
+            const float m = p.scale * sum;
+            l = logf(__fadd_rn(1.0f, m));
+            const float w = p.scale / __fadd_rn(1.0f, m);
+            c = -w * cnt;
+            for (int j = lg; j < S; j += LPR) {
+              const float h = __fadd_rn(base, sS[j]);
+              if (h >= 0.f) sG[g * p.s_pad + j] += w;
+            }
+          }
+        }
+      }
+      if (lg == 0) {
+        p.loss_out[k] = l;
+        p.coef_out[k] = c;
+      }
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) fma4(acc[v], c, row[v]);
+    }
+
+    if constexpr (LOSS == TMF_LOSS_WMRB) {
+      if constexpr (JPL > 0) {
+#pragma unroll
+        for (int t = 0; t < JPL; ++t) {
+          const int j = lg + LPR * t;
+          if (j < S) sG[g * p.s_pad + j] = gj[t];
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < S; j += NT) {  // fixed group order => deterministic
+        float G = sG[j];
+        for (int gg = 1; gg < NG; ++gg) G += sG[gg * p.s_pad + j];
+        p.coef_out[p.nnz + (long long)u * S + j] = G;
+        sS[j] = G;
+      }
+      __syncthreads();
+      const int* su = p.samp + (long long)u * S;
+#pragma unroll 4
+      for (int j = g; j < S; j += NG) {
+        const float G = sS[j];
+        float4 row[VPL];
+        if (p.cache_rows) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            const int col = lg + LPR * v;
+            row[v] = (col < nv) ? reinterpret_cast<const float4*>(sRows + (long long)j * ld)[col]
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          load_row<LPR, VPL>(p.Ei, su[j], ld, nv, lg, row);
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) fma4(acc[v], G, row[v]);
+      }
+    }
+
+    // ---- dE_u[u] = sum over groups (fixed order)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int col = lg + LPR * v;
+      if (col < nv) reinterpret_cast<float4*>(sAcc + g * ld)[col] = acc[v];
+    }
+    __syncthreads();
+    for (int c = tid; c < ld; c += NT) {
+      float s = sAcc[c];
+      for (int gg = 1; gg < NG; ++gg) s += sAcc[gg * ld + c];
+      p.dEu[(long long)u * ld + c] = s;
+    }
+  }
+}
+
+template <int LPR, int VPL, int JPL, int LOSS>
+static int launch_user_pass(const UserPassParams& p, cudaStream_t st) {
+  constexpr int NG = kUserPassThreads / LPR;
+  auto kern = user_pass_kernel<LPR, VPL, JPL, LOSS>;
+  size_t base = (size_t)NG * p.ld * sizeof(float);
+  if (LOSS == TMF_LOSS_WMRB) base += (size_t)(1 + NG) * p.s_pad * sizeof(float);
+  UserPassParams q = p;
+  size_t rows = (LOSS == TMF_LOSS_WMRB) ? (size_t)p.n_samples * p.ld * sizeof(float) : 0;
+  q.cache_rows = (LOSS == TMF_LOSS_WMRB) && (base + rows <= 56 * 1024);
+  size_t smem = base + (q.cache_rows ? rows : 0);
+  TMF_REQUIRE(smem <= 200 * 1024, "tmf_user_pass: n_samples=%d too large for shared memory (%zu B)", p.n_samples, smem);
+  if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  TMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kUserPassThreads, smem));
+  if (occ < 1) occ = 1;
+  long long grid = (long long)kNumSMs * occ;
+  if (grid > p.n_users) grid = p.n_users;
+  TMF_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(int), st));
+  kern<<<(unsigned)grid, kUserPassThreads, smem, st>>>(q);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+template <int LPR, int VPL>
+static int dispatch_user_pass_j(const UserPassParams& p, int loss, cudaStream_t st) {
+  if (loss == TMF_LOSS_MSE) return launch_user_pass<LPR, VPL, 0, TMF_LOSS_MSE>(p, st);
+  const int jpl = (p.n_samples + LPR - 1) / LPR;
+  if (jpl <= 4) return launch_user_pass<LPR, VPL, 4, TMF_LOSS_WMRB>(p, st);
+  if (jpl <= 8) return launch_user_pass<LPR, VPL, 8, TMF_LOSS_WMRB>(p, st);
+  if (jpl <= 16) return launch_user_pass<LPR, VPL, 16, TMF_LOSS_WMRB>(p, st);
+  return launch_user_pass<LPR, VPL, -1, TMF_LOSS_WMRB>(p, st);
+}
+
+// =====================================================================================
+// deterministic segment-sum of scaled gathered rows
+// =====================================================================================
+
+constexpr int kSpmmThreads = 256;
+
+struct SpmmParams {
+  int n_seg, ld_src, ld_out, nv, chunk;
+  long long n_entries;
+  const int* seg_ptr;
+  const int* idx;
+  const int* cpos;
+  const float* coef;
+  const float* src;
+  float* out;
+  float* part_first;  // [n_chunks][ld_out]
+  float* part_carry;  // [n_chunks][ld_out]
+};
+
+// group `gid` owns entries [gid*chunk, (gid+1)*chunk); walks the segments that intersect it.
+template <int LPR>
+__global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(const SpmmParams p) {
+  const int lg = threadIdx.x % LPR;
+  const unsigned gm = group_mask<LPR>();
+  const long long gid = ((long long)blockIdx.x * kSpmmThreads + threadIdx.x) / LPR;
+  const long long cs = gid * p.chunk;
+  if (cs >= p.n_entries) return;
+  const long long ce = min(cs + (long long)p.chunk, p.n_entries);
+  const int col = blockIdx.y * LPR + lg;  // float4 column
+  const bool active = col < p.nv;
+
+  // last segment s with seg_ptr[s] <= cs  (upper_bound - 1)
+  int lo = 0, hi = p.n_seg;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)p.seg_ptr[mid] <= cs) lo = mid; else hi = mid - 1;
+  }
+  int s = lo;
+  long long e = cs;
+  while (e < ce) {
+    long long sb = p.seg_ptr[s + 1];
+    while (sb <= e) { ++s; sb = p.seg_ptr[s + 1]; }  // skip empty segments
+    const long long sa = p.seg_ptr[s];
+    const long long pe = min(sb, ce);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    while (e < pe) {
+      const int nb = (int)min((long long)LPR, pe - e);
+      int my_i = 0;
+      float my_c = 0.f;
+      if (lg < nb) {
+        my_i = p.idx[e + lg];
+        my_c = p.coef ? p.coef[p.cpos ? p.cpos[e + lg] : (e + lg)] : 1.0f;
+      }
+      int t = 0;
+      for (; t + 4 <= nb; t += 4) {  // 4 independent row loads in flight, FMAs in entry order
+        const int i0 = __shfl_sync(gm, my_i, t + 0, LPR), i1 = __shfl_sync(gm, my_i, t + 1, LPR);
+        const int i2 = __shfl_sync(gm, my_i, t + 2, LPR), i3 = __shfl_sync(gm, my_i, t + 3, LPR);
+        const float c0 = __shfl_sync(gm, my_c, t + 0, LPR), c1 = __shfl_sync(gm, my_c, t + 1, LPR);
+        const float c2 = __shfl_sync(gm, my_c, t + 2, LPR), c3 = __shfl_sync(gm, my_c, t + 3, LPR);
+        if (active) {
+          const float4 r0 = ldg4(p.src + (long long)i0 * p.ld_src + 4 * col);
+          const float4 r1 = ldg4(p.src + (long long)i1 * p.ld_src + 4 * col);
+          const float4 r2 = ldg4(p.src + (long long)i2 * p.ld_src + 4 * col);
+          const float4 r3 = ldg4(p.src + (long long)i3 * p.ld_src + 4 * col);
+          fma4(acc, c0, r0);
+          fma4(acc, c1, r1);
+          fma4(acc, c2, r2);
+          fma4(acc, c3, r3);
+        }
+      }
+      for (; t < nb; ++t) {
+        const int i0 = __shfl_sync(gm, my_i, t, LPR);
+        const float c0 = __shfl_sync(gm, my_c, t, LPR);
+        if (active) fma4(acc, c0, ldg4(p.src + (long long)i0 * p.ld_src + 4 * col));
+      }
+      e += nb;
+    }
+    if (active) {
+      float* dst;
+      if (sa >= cs && sb <= ce) dst = p.out + (long long)s * p.ld_out;
+      else if (sa < cs) dst = p.part_first + gid * p.ld_out;
+      else dst = p.part_carry + gid * p.ld_out;
+      reinterpret_cast<float4*>(dst)[col] = acc;
+    }
+    ++s;
+  }
+}
+
+// one group per segment: zero-fill empty segments, combine the partials of chunk-spanning ones
+template <int LPR>
+__global__ void __launch_bounds__(kSpmmThreads) spmm_fixup_kernel(const SpmmParams p) {
+  const int lg = threadIdx.x % LPR;
+  const long long s = ((long long)blockIdx.x * kSpmmThreads + threadIdx.x) / LPR;
+  if (s >= p.n_seg) return;
+  const int col = blockIdx.y * LPR + lg;
+  if (col >= p.nv) return;
+  const long long a = p.seg_ptr[s], b = p.seg_ptr[s + 1];
+  float4* dst = reinterpret_cast<float4*>(p.out + s * p.ld_out) + col;
+  if (a == b) {
+    *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const long long c0 = a / p.chunk, c1 = (b - 1) / p.chunk;
+  if (c0 == c1) return;
+  float4 acc = reinterpret_cast<const float4*>(p.part_carry + c0 * p.ld_out)[col];
+  for (long long c = c0 + 1; c <= c1; ++c) add4(acc, reinterpret_cast<const float4*>(p.part_first + c * p.ld_out)[col]);
+  *dst = acc;
+}
+
+static int spmm_chunk_for(long long n_entries) {
+  // enough groups to fill the machine (~148 SMs x 2048 threads / 16 lanes), bounded partial buffers
+  long long c = n_entries / 32768;
+  int chunk = 32;
+  while (chunk < c && chunk < 256) chunk <<= 1;
+  return chunk;
+}
+
+template <int LPR>
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+  const long long n_chunks = cdiv(p.n_entries, p.chunk);
+  const int gpb = kSpmmThreads / LPR;
+  dim3 grid_y((unsigned)1, (unsigned)cdiv(p.nv, LPR));
+  if (n_chunks > 0) {
+    dim3 grid((unsigned)cdiv(n_chunks, gpb), grid_y.y);
+    spmm_seg_kernel<LPR><<<grid, kSpmmThreads, 0, st>>>(p);
+    TMF_LAUNCH_CHECK();
+  }
+  if (p.n_seg > 0) {
+    dim3 grid((unsigned)cdiv(p.n_seg, gpb), grid_y.y);
+    spmm_fixup_kernel<LPR><<<grid, kSpmmThreads, 0, st>>>(p);
+    TMF_LAUNCH_CHECK();
+  }
+  return TMF_OK;
+}
+
+// =====================================================================================
+// elementwise / reductions
+// =====================================================================================
+
+__global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g, long long n, float lr) {
+  // Keras Adam, step 1 from zero moments, un-simplified m/v/alpha form in fp32
+  const float one_m_b1 = 1.0f - 0.9f;
+  const float one_m_b2 = 1.0f - 0.999f;
+  const float alpha = lr * sqrtf(one_m_b2) / one_m_b1;
+  const float eps = 1e-7f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gi = g[i];
+    const float m = gi * one_m_b1;
+    const float v = (gi * gi) * one_m_b2;
+    w[i] = w[i] - __fdiv_rn(alpha * m, sqrtf(v) + eps);
+  }
+}
+
+__global__ void pair_dots_kernel(long long nnz, const int* __restrict__ rows, const int* __restrict__ cols,
+                                 const float* __restrict__ Eu, const float* __restrict__ Ei, int ld, float* __restrict__ p) {
+  // 8 lanes per pair, float4 strided over the row
+  const int lg = threadIdx.x & 7;
+  const unsigned gm = group_mask<8>();
+  const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (k >= nnz) return;
+  const float* a = Eu + (long long)rows[k] * ld;
+  const float* b = Ei + (long long)cols[k] * ld;
+  float s = 0.f;
+  for (int c = lg; c < (ld >> 2); c += 8) s += dot4(ldg4(a + 4 * c), ldg4(b + 4 * c));
+  s = group_sum<8>(s, gm);
+  if (lg == 0) p[k] = s;
+}
+
+constexpr int kRedBlocks = 1024;
+constexpr int kRedThreads = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out) {
+  __shared__ double sm[NV][kRedThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[i][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double x = 0.0;
+      for (int j = 0; j < kRedThreads / 32; ++j) x += sm[i][j];
+      out[i] = x;
+    }
+  }
+}
+
+// MODE 0: sum(x)            MODE 1: sum(x^2)
+// MODE 2: KL first moments  {cnt+, sum+, cnt-, sum-}
+// MODE 3: KL second moments {ssd+, ssd-} around stats[0]=mu+, stats[1]=mu-
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads) reduce_partial_kernel(const float* __restrict__ x, const float* __restrict__ val,
+                                                                    long long n, const double* __restrict__ stats,
+                                                                    double* __restrict__ partial) {
+  constexpr int NV = MODE == 2 ? 4 : (MODE == 3 ? 2 : 1);
+  double v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.0;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = min(lo + per, n);
+  for (long long i = lo + threadIdx.x; i < hi; i += kRedThreads) {
+    const double xi = x[i];
+    if (MODE == 0) v[0] += xi;
+    if (MODE == 1) v[0] += xi * xi;
+    if (MODE == 2) {
+      if (val[i] > 0.f) { v[0] += 1.0; v[1] += xi; } else { v[2] += 1.0; v[3] += xi; }
+    }
+    if (MODE == 3) {
+      if (val[i] > 0.f) { const double d = xi - stats[0]; v[0] += d * d; } else { const double d = xi - stats[1]; v[1] += d * d; }
+    }
+  }
+  block_reduce_store<NV>(v, partial + (long long)blockIdx.x * NV);
+}
+
+// FIN 0: out_f[0] = sum                      FIN 1: scale = rsqrt(max(sum, 1e-12)) -> stats[0]
+// FIN 2: KL means -> stats[0..3] = {mu+, mu-, n+, n-}
+// FIN 3: KL finish: stats[4..] = {s, z, phi}; out_f[0] = loss
+template <int FIN>
+__global__ void __launch_bounds__(kRedThreads) reduce_final_kernel(const double* __restrict__ partial, int n_blocks,
+                                                                  double* __restrict__ stats, float* __restrict__ out_f) {
+  constexpr int NV = FIN == 2 ? 4 : (FIN == 3 ? 2 : 1);
+  double v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.0;
+  for (int b = threadIdx.x; b < n_blocks; b += kRedThreads)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += partial[(long long)b * NV + i];
+  __shared__ double res[4];
+  block_reduce_store<NV>(v, res);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (FIN == 0) out_f[0] = (float)res[0];
+    if (FIN == 1) stats[0] = 1.0 / sqrt(fmax(res[0], 1e-12));
+    if (FIN == 2) {
+      stats[0] = (double)(float)(res[1] / res[0]);  // mu+ rounded to fp32 like tf.nn.moments
+      stats[1] = (double)(float)(res[3] / res[2]);
+      stats[2] = res[0];
+      stats[3] = res[2];
+    }
+    if (FIN == 3) {
+      const float vp = (float)(res[0] / stats[2]);  // population variance
+      const float vn = (float)(res[1] / stats[3]);
+      const float s = sqrtf(vp + vn);
+      const float z = ((float)stats[0] - (float)stats[1]) / s;
+      const float phi = expf(-0.5f * z * z) * 0.3989422804014327f;
+      stats[4] = s;
+      stats[5] = z;
+      stats[6] = phi;
+      out_f[0] = 1.0f - 0.5f * erfcf(-z * 0.7071067811865476f);  // 1 - ndtr(z), loss_graphs.py:120-122
+    }
+  }
+}
+
+__global__ void kl_coef_kernel(long long nnz, const float* __restrict__ p, const float* __restrict__ val,
+                               const double* __restrict__ stats, float* __restrict__ coef) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const float mp = (float)stats[0], mn = (float)stats[1];
+  const float np_ = (float)stats[2], nn_ = (float)stats[3];
+  const float s = (float)stats[4], z = (float)stats[5], phi = (float)stats[6];
+  if (val[k] > 0.f) coef[k] = -phi / (s * np_) * (1.0f - z * (p[k] - mp) / s);
+  else coef[k] = -phi / (s * nn_) * (-1.0f - z * (p[k] - mn) / s);
+}
+
+__global__ void scale_kernel(float* __restrict__ w, long long n, const double* __restrict__ stats) {
+  const float sc = (float)stats[0];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) w[i] *= sc;
+}
+
+__global__ void bias_add_kernel(float* __restrict__ E, long long n_rows, int n_cols, int ld, const float* __restrict__ bias, int relu) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n_rows * ld;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const int c = (int)(i % ld);
+    if (c < n_cols) {
+      float v = E[i] + bias[c];
+      if (relu) v = v > 0.f ? v : 0.f;  // tf.nn.relu
+      E[i] = v;
+    }
+  }
+}
+
+__global__ void relu_mask_kernel(float* __restrict__ dH, const float* __restrict__ H, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride)
+    if (!(H[i] > 0.f)) dH[i] = 0.f;  // H > 0 <=> pre-activation > 0 (strict, tf.nn.relu gradient)
+}
+
+// column sums in two fixed-order levels
+__global__ void col_sum_partial_kernel(const float* __restrict__ dE, long long n_rows, int ld, float* __restrict__ partial) {
+  const long long per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const long long lo = per * blockIdx.x, hi = min(lo + per, n_rows);
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = lo; r < hi; ++r) s += dE[r * ld + c];
+    partial[(long long)blockIdx.x * ld + c] = s;
+  }
+}
+__global__ void col_sum_final_kernel(const float* __restrict__ partial, int n_blocks, int n_cols, int ld, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  float s = 0.f;
+  for (int b = 0; b < n_blocks; ++b) s += partial[(long long)b * ld + c];
+  out[c] = s;
+}
+
+// small fp32 GEMM (ReLU embedding second stage and its backward): 64x64 tile, 4x4 per thread
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(int m, int n, int k, const float* __restrict__ A, int lda,
+                                                       const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc) {
+  __shared__ float sA[16][64 + 1];
+  __shared__ float sB[16][64 + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < k; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i / 64, mm = i % 64;
+      const int gm_ = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm_ < m && gk < k) v = TA ? A[(long long)gk * lda + gm_] : A[(long long)gm_ * lda + gk];
+      sA[kk][mm] = v;
+      const int gn = n0 + mm;
+      float w = 0.f;
+      if (gn < n && gk < k) w = TB ? B[(long long)gn * ldb + gk] : B[(long long)gk * ldb + gn];
+      sB[kk][mm] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm_ = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm_ < m && gn < n) C[(long long)gm_ * ldc + gn] = acc[i][j];
+    }
+}
+
+__global__ void gather_rows2d_kernel(const float* __restrict__ in, int n_rows, long long n_cols, const long long* __restrict__ index,
+                                     int k, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_rows * k) return;
+  const long long r = i / k;
+  out[i] = in[r * n_cols + index[i]];
+}
+
+__global__ void gather_nd2_kernel(const float* __restrict__ in, long long n_cols, const long long* __restrict__ ind, long long n,
+                                  float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = in[ind[2 * i] * n_cols + ind[2 * i + 1]];
+}
+
+// one warp per positive interaction: loss_graphs.py:80-88
+__global__ void wmrb_forward_kernel(long long n_pos, const int* __restrict__ pos_rows, const float* __restrict__ pos_pred,
+                                    const float* __restrict__ sample_pred, int S, float scale, float* __restrict__ loss) {
+  const long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (k >= n_pos) return;
+  const float base = __fsub_rn(1.0f, pos_pred[k]);
+  const float* sp = sample_pred + (long long)pos_rows[k] * S;
+  float sum = 0.f;
+  for (int j = lane; j < S; j += 32) sum += fmaxf(__fadd_rn(base, sp[j]), 0.f);
+  sum = group_sum<32>(sum, 0xffffffffu);
+  if (lane == 0) loss[k] = logf(__fadd_rn(1.0f, scale * sum));
+}
+
+}  // namespace tmf
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+using namespace tmf;
+
+extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int64_t nnz, const int32_t* row_ptr, const int32_t* col_idx,
+                             const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
+                             const int32_t* samp, int32_t n_samples, const int32_t* order, int32_t* counter,
+                             float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream) {
+  TMF_REQUIRE(loss == TMF_LOSS_MSE || loss == TMF_LOSS_WMRB, "tmf_user_pass: unknown loss %d", loss);
+  TMF_REQUIRE(n_users >= 0 && n_items > 0 && ld > 0 && ld % 4 == 0 && n_comp <= ld, "tmf_user_pass: bad shape");
+  TMF_REQUIRE(ld <= 256, "tmf_user_pass: n_components up to 256 supported (ld=%d)", ld);
+  TMF_REQUIRE(aligned16(Eu) && aligned16(Ei) && aligned16(dEu), "tmf_user_pass: embeddings must be 16-byte aligned");
+  TMF_REQUIRE(row_ptr && col_idx && val && counter && loss_out && coef_out, "tmf_user_pass: null pointer");
+  if (loss == TMF_LOSS_WMRB) TMF_REQUIRE(samp && n_samples > 0, "tmf_user_pass: WMRB needs samples (random_ind)");
+  if (n_users == 0) return TMF_OK;
+  UserPassParams p{};
+  p.n_users = n_users; p.n_items = n_items; p.ld = ld; p.n_comp = n_comp;
+  p.n_samples = loss == TMF_LOSS_WMRB ? n_samples : 0;
+  p.s_pad = (p.n_samples + 3) & ~3;
+  p.row_ptr = row_ptr; p.col_idx = col_idx; p.val = val; p.Eu = Eu; p.Ei = Ei; p.samp = samp; p.order = order;
+  p.counter = counter; p.loss_out = loss_out; p.coef_out = coef_out; p.dEu = dEu;
+  p.scale = loss == TMF_LOSS_WMRB ? (float)((double)n_items / (double)n_samples) : 0.f;
+  cudaStream_t st = as_stream(stream);
+  p.nnz = nnz;  // the G block of coef_out starts at nnz
+  const int nv = ld / 4;
+  int lpr = 4;
+  while (lpr < nv && lpr < 32) lpr <<= 1;
+  if (loss == TMF_LOSS_WMRB)
+    while (lpr < 32 && (n_samples + lpr - 1) / lpr > 16) lpr <<= 1;
+  if (nv > 32) return dispatch_user_pass_j<32, 2>(p, loss, st);
+  switch (lpr) {
+    case 4: return dispatch_user_pass_j<4, 1>(p, loss, st);
+    case 8: return dispatch_user_pass_j<8, 1>(p, loss, st);
+    case 16: return dispatch_user_pass_j<16, 1>(p, loss, st);
+    default: return dispatch_user_pass_j<32, 1>(p, loss, st);
+  }
+}
+
+extern "C" size_t tmf_spmm_ws_bytes(int64_t n_entries, int32_t ld_out) {
+  const int chunk = spmm_chunk_for(n_entries);
+  return (size_t)2 * (size_t)cdiv(n_entries > 0 ? n_entries : 1, chunk) * (size_t)ld_out * sizeof(float) + 256;
+}
+
+extern "C" int tmf_spmm_seg(int32_t n_seg, const int32_t* seg_ptr, int64_t n_entries, const int32_t* idx,
+                            const int32_t* cpos, const float* coef, const float* src, int32_t ld_src, float* out,
+                            int32_t ld_out, int32_t n_cols, void* ws, size_t ws_bytes, tmf_stream_t stream) {
+  TMF_REQUIRE(n_seg >= 0 && n_entries >= 0 && n_entries < (1ll << 31), "tmf_spmm_seg: bad sizes");
+  TMF_REQUIRE(ld_src % 4 == 0 && ld_out % 4 == 0 && n_cols <= ld_src && n_cols <= ld_out, "tmf_spmm_seg: bad leading dims");
+  TMF_REQUIRE(aligned16(src) && aligned16(out) && aligned16(ws), "tmf_spmm_seg: 16-byte alignment required");
+  TMF_REQUIRE(ws_bytes >= tmf_spmm_ws_bytes(n_entries, ld_out), "tmf_spmm_seg: workspace too small");
+  if (n_seg == 0) return TMF_OK;
+  SpmmParams p{};
+  p.n_seg = n_seg; p.ld_src = ld_src; p.ld_out = ld_out; p.nv = (n_cols + 3) / 4; p.chunk = spmm_chunk_for(n_entries);
+  p.n_entries = n_entries; p.seg_ptr = seg_ptr; p.idx = idx; p.cpos = cpos; p.coef = coef; p.src = src; p.out = out;
+  const long long n_chunks = cdiv(n_entries > 0 ? n_entries : 1, p.chunk);
+  p.part_first = reinterpret_cast<float*>(ws);
+  p.part_carry = p.part_first + n_chunks * ld_out;
+  cudaStream_t st = as_stream(stream);
+  if (p.nv <= 4) return launch_spmm<4>(p, st);
+  if (p.nv <= 8) return launch_spmm<8>(p, st);
+  if (p.nv <= 16) return launch_spmm<16>(p, st);
+  return launch_spmm<32>(p, st);
+}
+
+extern "C" int tmf_pair_dots(int64_t nnz, const int32_t* rows, const int32_t* cols, const float* Eu, const float* Ei,
+                             int32_t ld, float* p, tmf_stream_t stream) {
+  TMF_REQUIRE(ld % 4 == 0 && aligned16(Eu) && aligned16(Ei), "tmf_pair_dots: alignment");
+  if (nnz == 0) return TMF_OK;
+  pair_dots_kernel<<<(unsigned)cdiv(nnz * 8, 256), 256, 0, as_stream(stream)>>>(nnz, rows, cols, Eu, Ei, ld, p);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" size_t tmf_reduce_ws_bytes(void) { return (size_t)(kRedBlocks * 4 + 16) * sizeof(double); }
+
+static int red_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>(kRedBlocks, cdiv(n, 4096))); }
+
+extern "C" int tmf_reduce_sum(const float* x, int64_t n, float* out, void* ws, tmf_stream_t stream) {
+  TMF_REQUIRE(ws && out, "tmf_reduce_sum: null");
+  double* partial = reinterpret_cast<double*>(ws) + 16;
+  const int nb = red_blocks(n);
+  cudaStream_t st = as_stream(stream);
+  reduce_partial_kernel<0><<<nb, kRedThreads, 0, st>>>(x, nullptr, n, nullptr, partial);
+  reduce_final_kernel<0><<<1, kRedThreads, 0, st>>>(partial, nb, reinterpret_cast<double*>(ws), out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_l2_normalize_global(float* w, int64_t n, void* ws, tmf_stream_t stream) {
+  TMF_REQUIRE(ws && w, "tmf_l2_normalize_global: null");
+  double* stats = reinterpret_cast<double*>(ws);
+  double* partial = stats + 16;
+  const int nb = red_blocks(n);
+  cudaStream_t st = as_stream(stream);
+  reduce_partial_kernel<1><<<nb, kRedThreads, 0, st>>>(w, nullptr, n, nullptr, partial);
+  reduce_final_kernel<1><<<1, kRedThreads, 0, st>>>(partial, nb, stats, nullptr);
+  scale_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 16), 256, 0, st>>>(w, n, stats);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float* loss_out, float* coef_out, void* ws,
+                           tmf_stream_t stream) {
+  TMF_REQUIRE(ws && p && val && loss_out && coef_out, "tmf_kl_coef: null");
+  double* stats = reinterpret_cast<double*>(ws);
+  double* partial = stats + 16;
+  const int nb = red_blocks(nnz);
+  cudaStream_t st = as_stream(stream);
+  reduce_partial_kernel<2><<<nb, kRedThreads, 0, st>>>(p, val, nnz, nullptr, partial);
+  reduce_final_kernel<2><<<1, kRedThreads, 0, st>>>(partial, nb, stats, nullptr);
+  reduce_partial_kernel<3><<<nb, kRedThreads, 0, st>>>(p, val, nnz, stats, partial);
+  reduce_final_kernel<3><<<1, kRedThreads, 0, st>>>(partial, nb, stats, loss_out);
+  if (nnz > 0) kl_coef_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, st>>>(nnz, p, val, stats, coef_out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream) {
+  if (n == 0) return TMF_OK;
+  adam1_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, as_stream(stream)>>>(w, g, n, lr);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_bias_add(float* E, int64_t n_rows, int32_t n_cols, int32_t ld, const float* bias, int32_t relu,
+                            tmf_stream_t stream) {
+  if (n_rows == 0) return TMF_OK;
+  bias_add_kernel<<<(unsigned)std::min<long long>(cdiv(n_rows * ld, 256), 148 * 32), 256, 0, as_stream(stream)>>>(
+      E, n_rows, n_cols, ld, bias, relu);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_relu_mask(float* dH, const float* H, int64_t n, tmf_stream_t stream) {
+  if (n == 0) return TMF_OK;
+  relu_mask_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, as_stream(stream)>>>(dH, H, n);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_col_sum(const float* dE, int64_t n_rows, int32_t n_cols, int32_t ld, float* out, void* ws,
+                           size_t ws_bytes, tmf_stream_t stream) {
+  TMF_REQUIRE(ws_bytes >= (size_t)1024 * ld * sizeof(float), "tmf_col_sum: workspace too small");
+  const int nb = (int)std::max<long long>(1, std::min<long long>(1024, cdiv(n_rows, 64)));
+  cudaStream_t st = as_stream(stream);
+  col_sum_partial_kernel<<<nb, 256, 0, st>>>(dE, n_rows, ld, reinterpret_cast<float*>(ws));
+  col_sum_final_kernel<<<(unsigned)cdiv(n_cols, 128), 128, 0, st>>>(reinterpret_cast<float*>(ws), nb, n_cols, ld, out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_gemm_f32(int32_t ta, int32_t tb, int32_t m, int32_t n, int32_t k, const float* A, int32_t lda,
+                            const float* B, int32_t ldb, float* C, int32_t ldc, tmf_stream_t stream) {
+  if (m == 0 || n == 0) return TMF_OK;
+  dim3 grid((unsigned)cdiv(n, 64), (unsigned)cdiv(m, 64));
+  cudaStream_t st = as_stream(stream);
+  if (!ta && !tb) gemm_f32_kernel<0, 0><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc);
+  else if (ta && !tb) gemm_f32_kernel<1, 0><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc);
+  else if (!ta && tb) gemm_f32_kernel<0, 1><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc);
+  else gemm_f32_kernel<1, 1><<<grid, 256, 0, st>>>(m, n, k, A, lda, B, ldb, C, ldc);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_gather_rows2d(const float* in, int32_t n_rows, int64_t n_cols, const int64_t* index, int32_t k,
+                                 float* out, tmf_stream_t stream) {
+  const long long n = (long long)n_rows * k;
+  if (n == 0) return TMF_OK;
+  gather_rows2d_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(in, n_rows, n_cols,
+                                                                           reinterpret_cast<const long long*>(index), k, out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_gather_nd2(const float* in, int64_t n_cols, const int64_t* indices2, int64_t n, float* out,
+                              tmf_stream_t stream) {
+  if (n == 0) return TMF_OK;
+  gather_nd2_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(in, n_cols, reinterpret_cast<const long long*>(indices2), n, out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_wmrb_forward(int64_t n_pos, const int32_t* pos_rows, const float* pos_pred, const float* sample_pred,
+                                int32_t n_samples, float scale, float* loss_out, tmf_stream_t stream) {
+  if (n_pos == 0) return TMF_OK;
+  wmrb_forward_kernel<<<(unsigned)cdiv(n_pos * 32, 256), 256, 0, as_stream(stream)>>>(n_pos, pos_rows, pos_pred, sample_pred,
+                                                                                   n_samples, scale, loss_out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}

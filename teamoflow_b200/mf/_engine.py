@@ -1,0 +1,295 @@
+"""Host-side orchestration of the CUDA training step (one process per GPU).
+
+``TrainPlan`` owns every device buffer of a ``MatrixFactorization.fit`` call and issues, per epoch,
+the kernel sequence that replaces ``matrix_factorization.py:130-176``:
+
+    embed fwd (spmm / alias)  ->  fused user pass (scores, loss, dL/dscore, dE_u)
+    ->  item-major segment-sum (dE_i)  ->  [all-reduce dE_i over NCCL when user-sharded]
+    ->  embed bwd  ->  Adam step-1 on every trainable
+
+Embedding matrices live in padded storage ``[n, ld]`` (``ld = ceil4(r)``, pad columns zero) so rows
+are 16-byte aligned for 128-bit loads; the public tensors are the ``[:, :r]`` views.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _abi
+from ._tensors import FeatureMatrix, SparseInteractions, build_transpose, device, pad4, to_device
+
+LINEAR, BIASED, RELU = "linear", "biased", "relu"
+MSE, WMRB, KL = "mse", "wmrb", "kl"
+_LOSS_CODE = {MSE: 0, WMRB: 1}
+
+
+# ----------------------------------------------------------------------------- storage helpers
+
+
+def new_storage(n, r, fill=None):
+    st = torch.zeros(int(n), pad4(r), dtype=torch.float32, device=device())
+    if fill is not None:
+        st[:, :r] = fill
+    return st
+
+
+def storage_of(W):
+    """Padded ``[n, ld]`` storage behind a public ``[n, r]`` weight (copying when ``W`` is not one of ours)."""
+    if isinstance(W, torch.Tensor) and W.is_cuda and W.dtype == torch.float32 and W.dim() == 2:
+        base = W._base if W._base is not None else W
+        n, r = W.shape
+        if (base.dim() == 2 and base.is_contiguous() and base.shape == (n, pad4(r)) and base.data_ptr() == W.data_ptr()
+                and W.stride() == (pad4(r), 1) and base.data_ptr() % 16 == 0):
+            return base
+    Wt = to_device(W.detach() if isinstance(W, torch.Tensor) else W, torch.float32)
+    if Wt.dim() != 2:
+        raise ValueError("weights must be 2-D")
+    return new_storage(Wt.shape[0], Wt.shape[1], Wt)
+
+
+def _ws(nbytes):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device())
+
+
+def reduce_ws():
+    return _ws(_abi.query("tmf_reduce_ws_bytes"))
+
+
+def spmm(n_seg, seg_ptr, n_entries, idx, cpos, coef, src, n_cols, out=None, ws=None):
+    """``out[s] = sum_e c(e) * src[idx[e]]`` -- see ``tmf_spmm_seg``."""
+    ld_out = pad4(n_cols)
+    if out is None:
+        out = torch.empty(n_seg, ld_out, dtype=torch.float32, device=src.device)
+        if ld_out != n_cols:
+            out.zero_()
+    need = _abi.query("tmf_spmm_ws_bytes", n_entries, out.shape[1])
+    if ws is None or ws.numel() < need:
+        ws = _ws(need)
+    _abi.call("tmf_spmm_seg", n_seg, _abi.ptr(seg_ptr), n_entries, _abi.ptr(idx), _abi.ptr(cpos), _abi.ptr(coef),
+              _abi.ptr(src), src.shape[1], _abi.ptr(out), out.shape[1], n_cols, _abi.ptr(ws), ws.numel())
+    return out
+
+
+def gemm(ta, tb, m, n, k, A, B, out=None):
+    if out is None:
+        out = torch.zeros(m, pad4(n), dtype=torch.float32, device=A.device)
+    _abi.call("tmf_gemm_f32", int(ta), int(tb), m, n, k, _abi.ptr(A), A.shape[1], _abi.ptr(B), B.shape[1],
+              _abi.ptr(out), out.shape[1])
+    return out
+
+
+def col_sum(dE, n_cols):
+    out = torch.zeros(1, pad4(n_cols), dtype=torch.float32, device=dE.device)
+    ws = _ws(1024 * dE.shape[1] * 4)
+    _abi.call("tmf_col_sum", _abi.ptr(dE), dE.shape[0], n_cols, dE.shape[1], _abi.ptr(out), _abi.ptr(ws), ws.numel())
+    return out
+
+
+def adam1(w, g, lr):
+    _abi.call("tmf_adam1", _abi.ptr(w), _abi.ptr(g), w.numel(), float(lr))
+
+
+# ----------------------------------------------------------------------------- one embedding tower
+
+
+class Tower:
+    """One side (user or item) of the model: features, trainables, embedding and its backward.
+
+    kind/params follow ``embedding_graphs.py``: Linear ``X W`` (:38); BiasedLinear ``X W + b`` (:58);
+    ReLU ``relu(X W_r + b_r) W`` with hidden width ``5 r`` (:73-87).
+    """
+
+    def __init__(self, kind, X: FeatureMatrix, r, W, b=None, Wr=None, br=None):
+        self.kind, self.X, self.r = kind, X, int(r)
+        self.n = X.shape[0]
+        self.W = W            # storage [F or 5r, ld]
+        self.b = b            # storage [1, ld]
+        self.Wr, self.br = Wr, br  # [F, ld5], [1, ld5]
+        self.aux = 5 * self.r
+        self.H = None
+        alias = (kind == LINEAR and X.identity)
+        self.E = W if alias else torch.zeros(self.n, pad4(r), dtype=torch.float32, device=W.device)
+        self.dE = torch.zeros(self.n, pad4(r), dtype=torch.float32, device=W.device)
+        self.grads = {}
+        self._ws = None
+
+    # -- helpers
+    def _x_times(self, M, n_cols, out=None):
+        X = self.X
+        if X.identity:
+            if out is None:
+                return M
+            out.copy_(M)
+            return out
+        return spmm(self.n, X.ptr, X.nnz, X.idx, None, X.val, M, n_cols, out=out)
+
+    def _xt_times(self, D, n_cols):
+        X = self.X
+        if X.identity:
+            return D
+        ptr_t, rows_t, perm_t = X.transpose()
+        return spmm(X.shape[1], ptr_t, X.nnz, rows_t, perm_t, X.val, D, n_cols)
+
+    def forward(self):
+        r = self.r
+        if self.kind == LINEAR:
+            if not self.X.identity:
+                self._x_times(self.W, r, out=self.E)
+        elif self.kind == BIASED:
+            self._x_times(self.W, r, out=self.E)
+            _abi.call("tmf_bias_add", _abi.ptr(self.E), self.n, r, self.E.shape[1], _abi.ptr(self.b), 0)
+        else:
+            if self.H is None:
+                self.H = torch.zeros(self.n, pad4(self.aux), dtype=torch.float32, device=self.W.device)
+            self._x_times(self.Wr, self.aux, out=self.H)
+            _abi.call("tmf_bias_add", _abi.ptr(self.H), self.n, self.aux, self.H.shape[1], _abi.ptr(self.br), 1)
+            gemm(0, 0, self.n, r, self.aux, self.H, self.W, out=self.E)
+        return self.E
+
+    def backward(self):
+        """Gradients of every trainable from ``self.dE``."""
+        r, dE = self.r, self.dE
+        if self.kind == LINEAR:
+            self.grads = {"W": self._xt_times(dE, r)}
+        elif self.kind == BIASED:
+            self.grads = {"W": self._xt_times(dE, r), "b": col_sum(dE, r)}
+        else:
+            dW = gemm(1, 0, self.aux, r, self.n, self.H, dE)          # H^T dE
+            dH = gemm(0, 1, self.n, self.aux, r, dE, self.W)          # dE W^T
+            _abi.call("tmf_relu_mask", _abi.ptr(dH), _abi.ptr(self.H), dH.numel())
+            self.grads = {"W": dW, "Wr": self._xt_times(dH, self.aux), "br": col_sum(dH, self.aux)}
+        return self.grads
+
+    def trainables(self):
+        """Storage tensors in the order ``get_repr`` returns them."""
+        if self.kind == LINEAR:
+            return {"W": self.W}
+        if self.kind == BIASED:
+            return {"W": self.W, "b": self.b}
+        return {"W": self.W, "Wr": self.Wr, "br": self.br}
+
+    def update(self, lr):
+        for k, w in self.trainables().items():
+            adam1(w, self.grads[k], lr)
+
+
+# ----------------------------------------------------------------------------- interaction structure
+
+
+class InteractionPlan:
+    """Everything derived from the (fixed) interactions and (fixed) negatives, built once per fit:
+    CSR by user, the item-major list of (user, coefficient slot) over interactions ++ samples,
+    heavy-first user order, coefficient / loss buffers."""
+
+    def __init__(self, inter: SparseInteractions, loss, random_ind=None):
+        self.inter, self.loss = inter, loss
+        self.n_users, self.n_items = inter.dense_shape
+        self.row_ptr, self.col_idx, self.vals, self.coo_rows, self.perm = inter.csr()
+        dev = self.vals.device
+        self.nnz = inter.nnz
+        self.S = 0
+        self.samp = None
+        keys = self.col_idx
+        if loss == WMRB:
+            if random_ind is None:
+                raise ValueError("WMRBLoss needs sampled items: construct the model with n_users, n_items and "
+                                 "generate_sample=True (or set model.random_ind)")
+            ri = to_device(random_ind, torch.int64)
+            if ri.dim() != 2 or ri.shape[0] != self.n_users:
+                raise ValueError(f"random_ind must be [n_users={self.n_users}, n_samples], got {tuple(ri.shape)}")
+            if ri.numel() and (int(ri.min()) < 0 or int(ri.max()) >= self.n_items):
+                raise ValueError("random_ind holds item ids outside [0, n_items)")
+            self.S = int(ri.shape[1])
+            if self.n_users * self.S + self.nnz >= 2 ** 31:
+                raise ValueError("nnz + n_users*n_samples must be < 2^31")
+            self.samp = ri.to(torch.int32).contiguous()
+            keys = torch.cat([self.col_idx, self.samp.reshape(-1)])
+        self.T = int(keys.numel())
+        self.t_ptr, self.t_src = build_transpose(keys, self.n_items)
+        self.t_user = torch.empty(max(self.T, 1), dtype=torch.int32, device=dev)
+        _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
+                  _abi.ptr(self.t_user))
+        lens = (self.row_ptr[1:] - self.row_ptr[:-1])
+        self.order = torch.argsort(lens, descending=True, stable=True).to(torch.int32).contiguous()
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = torch.zeros(max(self.nnz + self.n_users * self.S, 1), dtype=torch.float32, device=dev)
+        self.loss_k = torch.zeros(max(self.nnz, 1), dtype=torch.float32, device=dev)
+        self.p = torch.zeros(max(self.nnz, 1), dtype=torch.float32, device=dev) if loss == KL else None
+        self.kl_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.red_ws = reduce_ws()
+        self.red_out = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.spmm_ws = None
+        self.n_pos = int((self.vals > 0).sum()) if loss == WMRB else self.nnz
+
+    def user_pass(self, Eu, Ei, r, dEu):
+        """scores + loss + coefficients + dE_u."""
+        if self.loss in (MSE, WMRB):
+            _abi.call("tmf_user_pass", _LOSS_CODE[self.loss], self.n_users, self.n_items, self.nnz,
+                      _abi.ptr(self.row_ptr), _abi.ptr(self.col_idx), _abi.ptr(self.vals), _abi.ptr(Eu), _abi.ptr(Ei),
+                      Eu.shape[1], r, _abi.ptr(self.samp), self.S, _abi.ptr(self.order), _abi.ptr(self.counter),
+                      _abi.ptr(self.loss_k), _abi.ptr(self.coef), _abi.ptr(dEu))
+        else:
+            _abi.call("tmf_pair_dots", self.nnz, _abi.ptr(self.coo_rows), _abi.ptr(self.col_idx), _abi.ptr(Eu),
+                      _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.p))
+            _abi.call("tmf_kl_coef", self.nnz, _abi.ptr(self.p), _abi.ptr(self.vals), _abi.ptr(self.kl_loss),
+                      _abi.ptr(self.coef), _abi.ptr(self.red_ws))
+            self.spmm_ws = self._spmm_ws(dEu.shape[1])
+            spmm(self.n_users, self.row_ptr, self.nnz, self.col_idx, None, self.coef, Ei, r, out=dEu, ws=self.spmm_ws)
+
+    def _spmm_ws(self, ld):
+        need = max(_abi.query("tmf_spmm_ws_bytes", self.T, ld), _abi.query("tmf_spmm_ws_bytes", self.nnz, ld))
+        if self.spmm_ws is None or self.spmm_ws.numel() < need:
+            self.spmm_ws = _ws(need)
+        return self.spmm_ws
+
+    def item_pass(self, Eu, r, dEi):
+        """dE_i[i] = sum over the item-major list of coef * E_u[user]  (deterministic)."""
+        ws = self._spmm_ws(dEi.shape[1])
+        spmm(self.n_items, self.t_ptr, self.T, self.t_user, self.t_src, self.coef, Eu, r, out=dEi, ws=ws)
+
+    # -- loss reporting (matrix_factorization.py:165-167, :179)
+    def loss_vector(self):
+        """The reference's ``loss_fn`` tensor in stored order."""
+        if self.loss == KL:
+            return self.kl_loss.reshape(())
+        lk = self.loss_k[:self.nnz]
+        vals = self.vals
+        if self.perm is not None:  # back to the caller's stored order
+            out = torch.empty_like(lk)
+            out[self.perm] = lk
+            v = torch.empty_like(vals)
+            v[self.perm] = vals
+            lk, vals = out, v
+        return lk[vals > 0] if self.loss == WMRB else lk
+
+    def mean_loss(self):
+        """``tf.reduce_mean(loss_fn)`` (:179); fixed-order fp64 accumulation on the device."""
+        if self.loss == KL:
+            return float(self.kl_loss.item())
+        if self.n_pos == 0:
+            return float("nan")
+        _abi.call("tmf_reduce_sum", _abi.ptr(self.loss_k), self.nnz, _abi.ptr(self.red_out), _abi.ptr(self.red_ws))
+        return float(self.red_out.item()) / self.n_pos
+
+
+class TrainPlan:
+    def __init__(self, user_tower: Tower, item_tower: Tower, inter_plan: InteractionPlan, r, comm=None):
+        self.u, self.i, self.ip, self.r = user_tower, item_tower, inter_plan, int(r)
+        self.comm = comm  # optional teamoflow_b200.mf.dist.GradientSync
+
+    def forward_backward(self):
+        Eu = self.u.forward()
+        Ei = self.i.forward()
+        self.ip.user_pass(Eu, Ei, self.r, self.u.dE)
+        self.ip.item_pass(Eu, self.r, self.i.dE)
+        if self.comm is not None:
+            self.comm.sync_item_grad(self.i.dE)
+        self.u.backward()
+        self.i.backward()
+        if self.comm is not None:
+            self.comm.sync_shared_grads(self.u, self.i)
+
+    def step(self, lr):
+        self.forward_backward()
+        self.u.update(lr)
+        self.i.update(lr)
