@@ -158,6 +158,12 @@ TMF_API int tmf_score_topk(const float* U, int64_t n_users, const float* V, int6
                    int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
                    size_t ws_bytes, tmf_stream_t stream);
 
+/* The raw tensor-core scores of the same kernel, written densely (P[n_users, n_items], small shapes only):
+ * used to test the bf16 error bound |s~ - s| <= 2^-8 * 1.05 * |u| * |v| that the exactness argument rests on.
+ * Workspace as for tmf_score_topk with k = 1. */
+TMF_API int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                         float* P, void* ws, size_t ws_bytes, tmf_stream_t stream);
+
 /* merge G per-shard top-k lists ([G, n_users, k]) -> [n_users, k], comparator (score desc, idx asc). */
 TMF_API int tmf_topk_merge(const int32_t* idx_in, const float* score_in, int32_t n_lists, int64_t n_users, int32_t k,
                    int32_t* out_idx, float* out_score, tmf_stream_t stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tmf_pack_bf16": (_i32, [_p, _i64, _i32, _i32, _p, _i64, _i32, _p, _p]),
     "tmf_score_topk_ws_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "tmf_score_topk": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tmf_score_dense_bf16": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "tmf_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "tmf_predict_dense": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p]),
     "tmf_rank_rows_ws_bytes": (_sz, [_i64, _i64]),
@@ -57,8 +58,12 @@ SIGNATURES = {
 }
 
 _lib = None
-# count of libtmf kernel-launching calls (bench.py's "gpu_launches" claim is derived from it)
+# libtmf calls / kernels launched so far (bench.py's "gpu_launches" claim is derived from these)
 call_count = 0
+launch_count = 0
+# kernels per ABI call where it is not 1 (memsets are not counted)
+KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5,
+                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 5}
 
 
 class TmfError(RuntimeError):
@@ -102,11 +107,12 @@ def ptr(t):
 
 def call(name, *args):
     """Invoke ``tmf_<name>`` on the current torch stream and raise on a non-zero return code."""
-    global call_count
+    global call_count, launch_count
     require_cuda()
     h = lib()
     rc = getattr(h, name)(*args, stream())
     call_count += 1
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise TmfError(f"{name} failed ({rc}): {h.tmf_last_error().decode()}")
 

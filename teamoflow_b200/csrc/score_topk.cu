@@ -57,7 +57,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
@@ -173,6 +173,8 @@ struct TopkParams {
   int* cnt;                     // [n_users_pad] candidates per row, -1 = overflow (exact path)
   int* ovf_count;               // [1]
   int* ovf_rows;                // [n_users_pad]
+  float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
+  long long dump_ld;
 };
 
 // keep rule shared by the in-kernel compaction and the final selection
@@ -332,6 +334,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j >= p.n_items) r[j] = 0xff800000u;  // -inf: padded items never qualify
+          }
+          if (p.dump != nullptr && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
           }
           float mx = __uint_as_float(r[0]);
 #pragma unroll
@@ -636,9 +643,9 @@ extern "C" size_t tmf_score_topk_ws_bytes(int64_t n_users, int64_t n_items, int3
   return topk_layout(n_users, n_items, n_comp).total;
 }
 
-extern "C" int tmf_score_topk(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
-                              int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
-                              size_t ws_bytes, tmf_stream_t stream) {
+static int score_topk_impl(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                           int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
+                           size_t ws_bytes, tmf_stream_t stream, float* dump) {
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && n_comp > 0 && n_comp <= ld, "tmf_score_topk: bad shape");
   TMF_REQUIRE(n_comp <= MAX_KB * BK, "tmf_score_topk: n_components up to %d supported", MAX_KB * BK);
   TMF_REQUIRE(k >= 1 && k <= 128 && k <= n_items, "tmf_score_topk: need 1 <= k <= min(128, n_items) (k=%d)", k);
@@ -677,12 +684,14 @@ extern "C" int tmf_score_topk(const float* U, int64_t n_users, const float* V, i
   p.k = k; p.clamp = clamp ? 1 : 0; p.item_offset = item_offset;
   p.unorm = unorm; p.vmax = reinterpret_cast<const float*>(vmax_bits);
   p.cand = cand; p.cnt = cnt; p.ovf_count = ovfc; p.ovf_rows = ovfr;
+  p.dump = dump; p.dump_ld = n_items;
 
   const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 + 4 * 256 * sizeof(int);
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(kNumSMs, p.n_ublocks);
   score_topk_kernel<<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
   TMF_LAUNCH_CHECK();
+  if (dump != nullptr) return TMF_OK;
 
   RerankParams q{};
   q.n_users = n_users; q.n_items = n_items; q.k = k; q.clamp = p.clamp; q.item_offset = item_offset; q.r = n_comp; q.ld = ld;
@@ -694,4 +703,16 @@ extern "C" int tmf_score_topk(const float* U, int64_t n_users, const float* V, i
   exact_rows_kernel<<<L.scratch_rows, 256, 0, st>>>(q, ovfc, ovfr, scratch);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
+}
+
+extern "C" int tmf_score_topk(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                              int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
+                              size_t ws_bytes, tmf_stream_t stream) {
+  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, k, clamp, item_offset, out_idx, out_score, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                                    float* P, void* ws, size_t ws_bytes, tmf_stream_t stream) {
+  TMF_REQUIRE(P != nullptr, "tmf_score_dense_bf16: null output");
+  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, 1, 0, 0, nullptr, nullptr, ws, ws_bytes, stream, P);
 }

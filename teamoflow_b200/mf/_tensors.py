@@ -119,7 +119,7 @@ def as_interactions(x, shape=None):
     if isinstance(x, torch.Tensor) and x.layout != torch.strided:
         c = x.coalesce() if x.layout == torch.sparse_coo else x.to_sparse_coo().coalesce()
         return SparseInteractions(c.indices().t().contiguous(), c.values(), tuple(c.shape))
-    if isinstance(x, (tuple, list)) and len(x) == 3 and not np.isscalar(x[0]) and np.ndim(x[0]) == 2:
+    if isinstance(x, (tuple, list)) and len(x) == 3 and getattr(x[0], "ndim", 0) == 2 and len(x[2]) == 2:
         return SparseInteractions(x[0], x[1], x[2])
     # dense array-like: nonzeros in row-major order (convert_np_to_tf_sparse, input_utils.py:133-153)
     A = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float32))

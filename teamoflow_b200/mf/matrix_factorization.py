@@ -168,6 +168,8 @@ class MatrixFactorization:
         ``comm`` (extension): a ``teamoflow_b200.mf.dist.GradientSync`` for user-sharded data parallelism.
         """
         plan = self._prepare(user_features, item_features, tf_interactions, comm=comm)
+        if comm is not None:
+            comm.broadcast_params(plan.u, plan.i)
         cumulative_time = 0
         self.loss_history = []
         for epoch in range(epochs):

@@ -1,0 +1,213 @@
+"""GPU parity tests of scoring / top-k / metrics.  Indices must be BIT-EXACT against the oracle's
+canonical score + stable descending order (ties -> lower item id), as north_star requires."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mf_oracle as o
+
+pytestmark = pytest.mark.gpu
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def model_with(U, V):
+    from teamoflow_b200.mf.matrix_factorization import MatrixFactorization
+    from teamoflow_b200.mf._engine import new_storage
+    m = MatrixFactorization(U.shape[1])
+    r = U.shape[1]
+    m.user_embedding = new_storage(U.shape[0], r, torch.as_tensor(U, device="cuda"))[:, :r]
+    m.item_embedding = new_storage(V.shape[0], r, torch.as_tensor(V, device="cuda"))[:, :r]
+    return m
+
+
+def fused_topk(U, V, k, clamp, item_offset=0):
+    from teamoflow_b200.mf._engine import new_storage
+    from teamoflow_b200.mf.matrix_factorization import score_topk
+    r = U.shape[1]
+    Us = new_storage(U.shape[0], r, torch.as_tensor(U, device="cuda"))
+    Vs = new_storage(V.shape[0], r, torch.as_tensor(V, device="cuda"))
+    idx, sc = score_topk(Us, Vs, r, k, clamp, item_offset)
+    torch.cuda.synchronize()
+    return cpu(idx), cpu(sc)
+
+
+def oracle_topk(U, V, k, clamp):
+    P = o.canonical_scores(U, V)
+    if clamp:
+        P = np.where(P > 0, P, np.float32(0))
+    idx = o.topk_stable(P, k)
+    return idx, np.take_along_axis(P, idx.astype(np.int64), 1)
+
+
+def test_predict_dense_is_canonical_bit_exact():
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((70, 37)).astype(np.float32)
+    V = rng.standard_normal((90, 37)).astype(np.float32)
+    m = model_with(U, V)
+    P = cpu(m.predict())
+    assert np.array_equal(P, o.canonical_scores(U, V))
+    from teamoflow_b200.mf.predict_graphs import DotProductPrediction
+    assert np.array_equal(cpu(DotProductPrediction().get_prediction(m.user_embedding, m.item_embedding)), P)
+    A = (rng.random((70, 90)) < 0.1).astype(np.float32)
+    allp, unobs = m.predict(torch.as_tensor(A))
+    assert np.array_equal(cpu(unobs), P[A == 0])
+    ranks = cpu(m.predict_ranks(torch.as_tensor(A)))
+    assert np.array_equal(ranks, o.topk_stable(P[A == 0], int((A == 0).sum())))
+
+
+@pytest.mark.parametrize("n_u,n_i,r,k", [(300, 5000, 32, 10), (129, 257, 128, 100), (64, 1000, 10, 1), (500, 3000, 64, 128),
+                                         (130, 700, 200, 17), (10, 40, 5, 40)])
+@pytest.mark.parametrize("clamp", [False, True])
+def test_fused_topk_random_bit_exact(n_u, n_i, r, k, clamp):
+    rng = np.random.default_rng(n_u + n_i + r)
+    U = (rng.standard_normal((n_u, r)) / np.sqrt(r)).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) / np.sqrt(r)).astype(np.float32)
+    if clamp:
+        U[3] = -np.abs(U[3]); V[:] = np.where(rng.random((n_i, 1)) < 0.5, np.abs(V), V)  # rows with few positive scores
+        U[5] = 0.0
+    idx, sc = fused_topk(U, V, k, clamp)
+    widx, wsc = oracle_topk(U, V, k, clamp)
+    assert np.array_equal(idx, widx)
+    assert np.array_equal(sc, wsc)
+
+
+def test_fused_topk_grid_golden_ties():
+    c = G["grid_topk"]
+    U = np.array(c["U_int"], np.float32) / c["scale"]
+    V = np.array(c["V_int"], np.float32) / c["scale"]
+    idx, _ = fused_topk(U, V, c["k"], False)
+    assert idx.tolist() == c["raw"]
+    idx, _ = fused_topk(U, V, c["k"], True)
+    assert idx.tolist() == c["clamped"]
+
+
+def test_fused_topk_massive_ties_take_exact_path():
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal((40, 16)).astype(np.float32)
+    V = np.tile(rng.standard_normal((1, 16)).astype(np.float32), (3000, 1))  # every item identical
+    V[1234] *= 2.0
+    for clamp in (False, True):
+        idx, sc = fused_topk(U, V, 20, clamp)
+        widx, wsc = oracle_topk(U, V, 20, clamp)
+        assert np.array_equal(idx, widx) and np.array_equal(sc, wsc)
+
+
+def test_fused_topk_adversarial_increasing_scores():
+    # scores increase with the item id: every item beats the running threshold (worst case for the filter)
+    n_i, r = 6000, 8
+    U = np.ones((33, r), np.float32)
+    V = np.tile(np.linspace(-1, 1, n_i, dtype=np.float32)[:, None], (1, r))
+    idx, _ = fused_topk(U, V, 50, False)
+    widx, _ = oracle_topk(U, V, 50, False)
+    assert np.array_equal(idx, widx)
+
+
+def test_item_sharded_topk_merge_equals_single_shot():
+    from teamoflow_b200 import _abi
+    rng = np.random.default_rng(2)
+    n_u, n_i, r, k = 200, 4000, 48, 25
+    U = (rng.standard_normal((n_u, r)) / 7).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) / 7).astype(np.float32)
+    V[100] = V[3900]  # a tie across shards
+    bounds = [0, 1300, 2600, 4000]
+    idxs, scs = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        i, s = fused_topk(U, V[a:b], k, True, item_offset=a)
+        idxs.append(i); scs.append(s)
+    idx_in = torch.as_tensor(np.stack(idxs), device="cuda").contiguous()
+    sc_in = torch.as_tensor(np.stack(scs), device="cuda").contiguous()
+    out_i = torch.empty(n_u, k, dtype=torch.int32, device="cuda")
+    out_s = torch.empty(n_u, k, dtype=torch.float32, device="cuda")
+    _abi.call("tmf_topk_merge", _abi.ptr(idx_in), _abi.ptr(sc_in), 3, n_u, k, _abi.ptr(out_i), _abi.ptr(out_s))
+    widx, wsc = oracle_topk(U, V, k, True)
+    assert np.array_equal(cpu(out_i), widx) and np.array_equal(cpu(out_s), wsc)
+
+
+def test_metrics_golden_and_quirks():
+    c = G["metrics_4x5"]
+    P, A, k = np.array(c["P"], np.float32), np.array(c["A"], np.float32), c["k"]
+    m = model_with(P, np.eye(5, dtype=np.float32))  # U = P, V = I  =>  scores == P exactly
+    At = torch.as_tensor(A)
+    assert cpu(m._topk(k, clamp=True)).tolist() == c["topk_clamped"]
+    np.testing.assert_array_equal(cpu(m.recall_at_k(At, k)), np.array(c["recall_drop"], np.float32))
+    keep = [np.inf if x == "inf" else x for x in c["recall_keep"]]
+    np.testing.assert_array_equal(cpu(m.recall_at_k(At, k, preserve_rows=True)), np.array(keep, np.float32))
+    np.testing.assert_array_equal(cpu(m.precision_at_k(At, k)), np.array(c["precision_drop"], np.float32))
+    np.testing.assert_array_equal(cpu(m.precision_at_k(At, k, preserve_rows=True)), np.array(c["precision_keep"], np.float32))
+    assert float(m.f1_at_k(At, k)) == float(o.f1_at_k(P, A, k))
+
+
+@pytest.mark.parametrize("k", [1, 10, 30])
+def test_metrics_random_vs_oracle(k):
+    rng = np.random.default_rng(k)
+    n_u, n_i, r = 150, 400, 16
+    U = (rng.standard_normal((n_u, r)) / 4).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) / 4).astype(np.float32)
+    A = np.where(rng.random((n_u, n_i)) < 0.05, rng.choice([-2.0, 1.0, 3.0, 5.0], (n_u, n_i)), 0.0).astype(np.float32)
+    A[7] = 0.0
+    m = model_with(U, V)
+    P = o.canonical_scores(U, V)
+    At = torch.as_tensor(A)
+    from scipy import sparse
+    for Ain in (At, sparse.csr_matrix(A)):  # dense like the reference, or sparse (extension)
+        np.testing.assert_array_equal(cpu(m.recall_at_k(Ain, k)), o.recall_at_k(P, A, k))
+        np.testing.assert_array_equal(cpu(m.recall_at_k(Ain, k, True)), o.recall_at_k(P, A, k, True))
+        np.testing.assert_array_equal(cpu(m.precision_at_k(Ain, k)), o.precision_at_k(P, A, k))
+    np.testing.assert_allclose(float(m.f1_at_k(At, k)), float(o.f1_at_k(P, A, k)), rtol=1e-6)
+    np.testing.assert_allclose(cpu(m.dcg_at_k(At, k)), o.dcg_at_k(P, A, k), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(cpu(m.idcg_at_k(At, k)), o.idcg_at_k(P, A, k), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(cpu(m.ndcg_at_k(At, k)), o.ndcg_at_k(P, A, k), rtol=5e-6, atol=1e-6)
+    np.testing.assert_allclose(cpu(m.ndcg_at_k(At, k, True)), o.ndcg_at_k(P, A, k, True), rtol=5e-6, atol=1e-6)
+
+
+def test_idcg_uses_negative_gains_when_k_exceeds_nonnegative_count():
+    U = np.ones((2, 2), np.float32); V = np.array([[1, 0], [0.5, 0], [0.2, 0], [0.1, 0]], np.float32)
+    A = np.array([[2.0, -1.0, -3.0, 1.0], [-1.0, -1.0, -2.0, -4.0]], np.float32)
+    m = model_with(U, V)
+    P = o.canonical_scores(U, V)
+    np.testing.assert_allclose(cpu(m.idcg_at_k(torch.as_tensor(A), 4)), o.idcg_at_k(P, A, 4), rtol=2e-6)
+    np.testing.assert_allclose(cpu(m.dcg_at_k(torch.as_tensor(A), 4)), o.dcg_at_k(P, A, 4), rtol=2e-6)
+
+
+def test_retrieve_user_recs_all_modes():
+    rng = np.random.default_rng(4)
+    U = rng.standard_normal((30, 6)).astype(np.float32)
+    V = rng.standard_normal((200, 6)).astype(np.float32)
+    V[50] = V[10]
+    m = model_with(U, V)
+    P = o.canonical_scores(U, V)
+    for user, k in ((None, 5), (3, None), (3, 7), (None, None)):
+        got = m.retrieve_user_recs(user=user, k=k)
+        assert got.dtype == np.int32
+        assert np.array_equal(got, o.retrieve_user_recs(P, user=user, k=k))
+
+
+@pytest.mark.parametrize("n_u,n_i,r", [(128, 256, 64), (200, 700, 128), (130, 300, 10), (64, 513, 200)])
+def test_tensor_core_scores_within_stated_error_bound(n_u, n_i, r):
+    """The raw tcgen05 bf16 GEMM scores obey |s~ - s| <= 2^-8 * 1.05 * |u| * |v| (the premise of the exact top-k)."""
+    from teamoflow_b200 import _abi
+    from teamoflow_b200.mf._engine import new_storage
+    rng = np.random.default_rng(r)
+    U = (rng.standard_normal((n_u, r)) * rng.uniform(0.1, 3.0, (n_u, 1))).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) * rng.uniform(0.1, 3.0, (n_i, 1))).astype(np.float32)
+    Us = new_storage(n_u, r, torch.as_tensor(U, device="cuda")); Vs = new_storage(n_i, r, torch.as_tensor(V, device="cuda"))
+    P = torch.full((n_u, n_i), float("nan"), device="cuda")
+    ws_bytes = _abi.query("tmf_score_topk_ws_bytes", n_u, n_i, r, 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    _abi.call("tmf_score_dense_bf16", _abi.ptr(Us), n_u, _abi.ptr(Vs), n_i, r, Us.shape[1], _abi.ptr(P), _abi.ptr(ws), ws_bytes)
+    torch.cuda.synchronize()
+    got = cpu(P).astype(np.float64)
+    exact = U.astype(np.float64) @ V.astype(np.float64).T
+    bound = (1.05 / 256) * np.linalg.norm(U.astype(np.float64), axis=1)[:, None] * np.linalg.norm(V.astype(np.float64), axis=1)[None, :]
+    assert np.isfinite(got).all()
+    err = np.abs(got - exact)
+    assert (err <= bound + 1e-30).all(), f"max err/bound = {(err / bound).max():.3f}"
+    # and it really is a bf16-operand product, not something sloppier: typical error well inside the bound
+    assert np.median(err / bound) < 0.2
