@@ -244,9 +244,11 @@ class MatrixFactorization:
     def precision_at_k(self, A, k=10, preserve_rows=False):
         """ref:271-304."""
         hits, relevant = self._hits_relevant(A, k)
+        kk = torch.full_like(hits, float(k))  # tensor / tensor is a true IEEE division (tensor / scalar multiplies by 1/k)
         if not preserve_rows:
-            return hits[relevant != 0.0] / k
-        return hits / k
+            m = relevant != 0.0
+            return hits[m] / kk[m]
+        return hits / kk
 
     def f1_at_k(self, A, k=10, beta=1.0):
         """ref:306-318 (formula kept as written)."""
