@@ -18,15 +18,16 @@
 namespace tmf {
 
 constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
-constexpr int BN = 256;        // items per accumulator tile (TMEM columns)
+constexpr int BN = 128;        // items per accumulator tile (TMEM columns); two CTAs share an SM
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NSTAGES = 4;     // B-operand ring
+constexpr int NSTAGES = 4;     // B-operand ring (16 KB stages)
+constexpr int TMEM_COLS = 2 * BN;  // two accumulators per CTA, double-buffered against the epilogue
 constexpr int CAP = 512;       // candidate slots per row
 constexpr int CPL = CAP / 32;  // candidates per lane in warp-cooperative passes
 constexpr int TOPK_THREADS = 256;
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2; // 32 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
 constexpr float ERR_FACTOR = 1.05f / 256.0f;
 
@@ -91,6 +92,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait that also pins the loaded registers behind it (consumers cannot be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -213,8 +224,52 @@ __device__ void warp_compact(float2* buf, int n, int k, float E, int clamp, int 
   thr_out = thr;
 }
 
+// Filter one 32-column slice of a row's accumulator against its running threshold.  The fast path is a
+// 3-input max tree (FMNMX3) and one compare; 8-column groups that contain a survivor are rescanned.
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, bool tail_tile, bool valid, float thr, int& cnt,
+                                               float2* buf, long long row, const TopkParams& p) {
+  if (tail_tile) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= p.n_items) r[j] = 0xff800000u;  // -inf: padded items never qualify
+  }
+  if (p.dump != nullptr && valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < p.n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
+  }
+  float m8[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float a = fmaxf(fmaxf(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+    const float b = fmaxf(fmaxf(a, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
+    const float c = fmaxf(fmaxf(b, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
+    m8[g] = fmaxf(c, __uint_as_float(r[8 * g + 7]));
+  }
+  const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  const bool filler = p.clamp && col0 < p.k;  // clamp mode: the k lowest item ids of the slab are always kept
+  if (!__any_sync(0xffffffffu, valid && (mx >= thr || filler))) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const bool gh = valid && (m8[g] >= thr || (filler && col0 + 8 * g < p.k));
+    if (__any_sync(0xffffffffu, gh)) {
+      if (gh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = __uint_as_float(r[8 * g + j]);
+          const int col = col0 + 8 * g + j;
+          if (col < p.n_items && (v >= thr || (filler && col < p.k))) {
+            buf[cnt] = make_float2(v, __int_as_float(p.item_offset + col));
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ the fused kernel
-__global__ void __launch_bounds__(TOPK_THREADS, 1)
+__global__ void __launch_bounds__(TOPK_THREADS, 2)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve (1024-byte aligned operand tiles first)
@@ -244,8 +299,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {  // TMEM: all 512 columns (two 128x256 fp32 accumulators)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+  if (warp == 2) {  // TMEM: 256 columns = two 128x128 fp32 accumulators (the SM's other CTA takes the other half)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -324,66 +379,48 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         tcgen05_fence_after();
         const bool tail_tile = (long long)(nt + 1) * BN > p.n_items;
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-          tmem_ld_wait();
-          const int col0 = nt * BN + ch * 32;  // local item index of r[0]
-          if (tail_tile) {
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_base, ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j >= p.n_items) r[j] = 0xff800000u;  // -inf: padded items never qualify
-          }
-          if (p.dump != nullptr && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
-          }
-          float mx = __uint_as_float(r[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          const bool filler = p.clamp && col0 < p.k;  // clamp mode: the k lowest item ids are always kept
-          if (valid && (mx >= thr || filler)) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]);
-              const int col = col0 + j;
-              if (col < p.n_items && (v >= thr || (filler && col < p.k))) {
-                buf[cnt] = make_float2(v, __int_as_float(p.item_offset + col));
-                ++cnt;
-              }
-            }
-          }
-          // make room before the next 32 columns (warp-uniform)
-          unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
-          while (need) {
-            const int owner = __ffs(need) - 1;
-            need &= need - 1;
-            const int n_o = __shfl_sync(0xffffffffu, cnt, owner);
-            const float E_o = __shfl_sync(0xffffffffu, E, owner);
-            float2* buf_o = p.cand + ((long long)ub * BM + q * 32 + owner) * CAP;
-            __syncwarp();
-            int n_new;
-            float thr_new;
-            warp_compact(buf_o, n_o, p.k, E_o, p.clamp, p.item_offset, hist, n_new, thr_new);
-            if (lane == owner) {
-              if (n_new > CAP - 32) {  // cannot shrink (massive ties): hand the row to the exact path
-                const int slot = atomicAdd(p.ovf_count, 1);
-                p.ovf_rows[slot] = (int)row;
-                thr = INFINITY;
-                cnt = -1;
-              } else {
-                thr = thr_new;
-                cnt = n_new;
-              }
-            }
-          }
+        for (int ch = 0; ch < BN / 32; ch += 2) {
+          // chunk ch is in ra; chunk ch+1 is fetched into rb while ra is filtered (and vice versa)
+          tmem_ld_wait_for(ra);
+          tmem_ld32(t_base + (uint32_t)((ch + 1) * 32), rb);
+          epilogue_chunk(ra, nt * BN + ch * 32, tail_tile, valid, thr, cnt, buf, row, p);
+          tmem_ld_wait_for(rb);
+          if (ch + 2 < BN / 32) tmem_ld32(t_base + (uint32_t)((ch + 2) * 32), ra);
+          epilogue_chunk(rb, nt * BN + (ch + 1) * 32, tail_tile, valid, thr, cnt, buf, row, p);
         }
+        // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&tempty[acc]));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+        // make room for the next tile's (at most BN) appends -- warp-uniform
+        unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - BN);
+        while (need) {
+          const int owner = __ffs(need) - 1;
+          need &= need - 1;
+          const int n_o = __shfl_sync(0xffffffffu, cnt, owner);
+          const float E_o = __shfl_sync(0xffffffffu, E, owner);
+          float2* buf_o = p.cand + ((long long)ub * BM + q * 32 + owner) * CAP;
+          __syncwarp();
+          int n_new;
+          float thr_new;
+          warp_compact(buf_o, n_o, p.k, E_o, p.clamp, p.item_offset, hist, n_new, thr_new);
+          if (lane == owner) {
+            if (n_new > CAP - BN) {  // cannot shrink (massive ties): hand the row to the exact path
+              const int slot = atomicAdd(p.ovf_count, 1);
+              p.ovf_rows[slot] = (int)row;
+              thr = INFINITY;
+              cnt = -1;
+            } else {
+              thr = thr_new;
+              cnt = n_new;
+            }
+          }
+        }
       }
       p.cnt[row] = valid ? cnt : 0;
     }
@@ -391,7 +428,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
 
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -688,7 +725,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 + 4 * 256 * sizeof(int);
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(kNumSMs, p.n_ublocks);
+  const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
   score_topk_kernel<<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
   TMF_LAUNCH_CHECK();
   if (dump != nullptr) return TMF_OK;

@@ -59,7 +59,8 @@ constexpr int kUserPassThreads = 256;
 // JPL == 0: MSE (no samples)
 // JPL < 0 : generic WMRB, per-group G partials in shared memory
 template <int LPR, int VPL, int JPL, int LOSS>
-__global__ void __launch_bounds__(kUserPassThreads) user_pass_kernel(const UserPassParams p) {
+__global__ void __launch_bounds__(kUserPassThreads, (JPL >= 0 && JPL <= 8 && VPL == 1) ? 4 : 2)
+user_pass_kernel(const UserPassParams p) {
   constexpr int NT = kUserPassThreads;
   constexpr int NG = NT / LPR;
   constexpr int JR = JPL > 0 ? JPL : 1;
@@ -101,17 +102,26 @@ __global__ void __launch_bounds__(kUserPassThreads) user_pass_kernel(const UserP
     float gj[JR];
     if constexpr (LOSS == TMF_LOSS_WMRB) {
       const int* su = p.samp + (long long)u * S;
-#pragma unroll 4
-      for (int j = g; j < S; j += NG) {
-        float4 row[VPL];
-        load_row<LPR, VPL>(p.Ei, su[j], ld, nv, lg, row);
-        const float s = group_sum<LPR>(dotv<VPL>(eu, row), gm);
-        if (lg == 0) sS[j] = s;
-        if (p.cache_rows) {
+      for (int j0 = g * 4; j0 < S; j0 += NG * 4) {  // 4 independent row gathers in flight per group
+        int it[4];
+        float4 row[4][VPL];
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const int col = lg + LPR * v;
-            if (col < nv) reinterpret_cast<float4*>(sRows + (long long)j * ld)[col] = row[v];
+        for (int q = 0; q < 4; ++q) it[q] = (j0 + q < S) ? su[j0 + q] : 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) load_row<LPR, VPL>(p.Ei, it[q], ld, nv, lg, row[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + q;
+          const float s = group_sum<LPR>(dotv<VPL>(eu, row[q]), gm);
+          if (j < S) {
+            if (lg == 0) sS[j] = s;
+            if (p.cache_rows) {
+#pragma unroll
+              for (int v = 0; v < VPL; ++v) {
+                const int col = lg + LPR * v;
+                if (col < nv) reinterpret_cast<float4*>(sRows + (long long)j * ld)[col] = row[q][v];
+              }
+            }
           }
         }
       }
@@ -165,18 +175,16 @@ __global__ void __launch_bounds__(kUserPassThreads) user_pass_kernel(const UserP
             unsigned ind = 0;
 #pragma unroll
             for (int t = 0; t < JPL; ++t) {
-              const float h = __fadd_rn(base, sj[t]);  // (1 - p) + s, loss_graphs.py:84
-              if (h >= 0.f) {                           // TF maximum(x, 0): gradient to x when x >= 0
-                ind |= 1u << t;
-                sum += h;
-                cnt += 1.f;
-              }
+              const float h = __fadd_rn(base, sj[t]);   // (1 - p) + s, loss_graphs.py:84
+              sum += fmaxf(h, 0.f);                      // tf.maximum(h, 0)
+              ind |= (h >= 0.f) ? (1u << t) : 0u;        // its gradient goes to h when h >= 0
             }
             sum = group_sum<LPR>(sum, gm);
-            cnt = group_sum<LPR>(cnt, gm);
+            cnt = group_sum<LPR>((float)__popc(ind), gm);
             const float m = p.scale * sum;                 // :86
-            l = logf(__fadd_rn(1.0f, m));                  // :88
-            const float w = p.scale / __fadd_rn(1.0f, m);
+            const float d = __fadd_rn(1.0f, m);
+            l = logf(d);                                   // :88
+            const float w = __fdividef(p.scale, d);
             c = -w * cnt;
 #pragma unroll
             for (int t = 0; t < JPL; ++t)

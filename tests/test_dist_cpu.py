@@ -1,0 +1,142 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU plumbing: shard bounds, the all-reduce hooks of
+user-sharded training and the all-gather + merge of item-sharded top-k.  The compute legs are played by the
+oracle (test infrastructure) so that only the host-side sharding / collective logic is under test."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import mf_oracle as o
+from teamoflow_b200.mf import dist as tdist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _spawn(fn, world=2):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    assert tdist.shard_bounds(10, 3) == [0, 4, 7, 10]
+    assert tdist.shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    b = tdist.balanced_user_bounds([100, 1, 1, 1, 100, 1, 1, 95], 2)
+    assert b[0] == 0 and b[-1] == 8 and 1 <= b[1] <= 5
+    lens = np.random.default_rng(0).integers(0, 50, 1000)
+    b = tdist.balanced_user_bounds(lens, 4)
+    per = [lens[b[i]:b[i + 1]].sum() for i in range(4)]
+    assert max(per) - min(per) <= 2 * lens.max()
+
+
+class _FakeTower:
+    def __init__(self, kind, grads, params):
+        self.kind, self.grads, self._p = kind, grads, params
+
+    def trainables(self):
+        return self._p
+
+
+def _problem():
+    rng = np.random.default_rng(3)
+    n_u, n_i, r, S = 40, 30, 6, 5
+    (rows, cols, vals), _ = o.generate_random_interaction(n_u, n_i, density=0.2, random_state=4)
+    U = o.uniform_initializer(n_u, r, rng).astype(np.float64)
+    V = o.uniform_initializer(n_i, r, rng).astype(np.float64)
+    samp = np.stack([rng.choice(n_i, S, replace=False) for _ in range(n_u)])
+    return n_u, n_i, r, S, rows, cols, vals.astype(np.float64), U, V, samp
+
+
+def _dp_training(rank, world):
+    n_u, n_i, r, S, rows, cols, vals, U, V, samp = _problem()
+    full = o.train_step_sparse("wmrb", np.eye(n_u), np.eye(n_i), "linear", "linear", {"W": U}, {"W": V}, rows, cols, vals,
+                               samp, n_i, S, update=False)
+    lens = np.bincount(rows, minlength=n_u)
+    b = tdist.balanced_user_bounds(lens, world)
+    lo, hi = b[rank], b[rank + 1]
+    m = (rows >= lo) & (rows < hi)
+    local = o.train_step_sparse("wmrb", np.eye(hi - lo), np.eye(n_i), "linear", "linear", {"W": U[lo:hi]}, {"W": V},
+                                rows[m] - lo, cols[m], vals[m], samp[lo:hi], n_i, S, update=False)
+    comm = tdist.GradientSync()
+    dEi = torch.from_numpy(local[2]["W"].copy())
+    comm.sync_item_grad(dEi)  # one all-reduce per epoch: the summed item gradient
+    np.testing.assert_allclose(dEi.numpy(), full[2]["W"], rtol=1e-12, atol=1e-14)
+    # the user rows are owned by the shard: no communication, identical to the corresponding rows of the full run
+    np.testing.assert_allclose(local[1]["W"], full[1]["W"][lo:hi], rtol=1e-12, atol=1e-14)
+    assert comm.bytes_reduced == dEi.numel() * 8
+
+    # shared user-side parameters (side-feature rows, bias) are reduced; rank-local identity rows are not
+    g = {"W": torch.full((7, 2), float(rank + 1)), "b": torch.full((1, 2), float(rank + 1))}
+    tower = _FakeTower("biased", g, {"W": torch.zeros(7, 2), "b": torch.zeros(1, 2)})
+    tdist.GradientSync(shared_user_rows=5).sync_shared_grads(tower, None)
+    assert torch.all(g["W"][:5] == rank + 1) and torch.all(g["W"][5:] == 3.0) and torch.all(g["b"] == 3.0)
+
+    # replicated parameters start identical (rank 0 wins)
+    pu = {"W": torch.full((7, 2), float(rank)), "b": torch.full((1, 2), float(rank))}
+    pi = {"W": torch.full((4, 2), float(rank + 10))}
+    tdist.GradientSync(shared_user_rows=5).broadcast_params(_FakeTower("biased", {}, pu), _FakeTower("linear", {}, pi))
+    assert torch.all(pi["W"] == 10.0) and torch.all(pu["W"][5:] == 0.0) and torch.all(pu["W"][:5] == rank) and torch.all(pu["b"] == 0)
+
+
+def test_user_sharded_training_allreduce():
+    _spawn(_dp_training)
+
+
+def _sharded_topk(rank, world):
+    rng = np.random.default_rng(9)
+    n_u, n_i, r, k = 25, 90, 8, 7
+    U = rng.integers(-4, 5, (n_u, r)).astype(np.float32) / 8
+    V = rng.integers(-4, 5, (n_i, r)).astype(np.float32) / 8  # grid values: many exact ties across shards
+    P = o.canonical_scores(U, V)
+    want = o.topk_stable(P, k)
+    b = tdist.shard_bounds(n_i, world)
+    lo, hi = b[rank], b[rank + 1]
+    loc = o.topk_stable(P[:, lo:hi], k)
+    loc_idx = torch.from_numpy((loc + lo).astype(np.int32))
+    loc_sc = torch.from_numpy(np.take_along_axis(P[:, lo:hi], loc.astype(np.int64), 1))
+    all_idx = [torch.empty_like(loc_idx) for _ in range(world)]
+    all_sc = [torch.empty_like(loc_sc) for _ in range(world)]
+    dist.all_gather(all_idx, loc_idx)
+    dist.all_gather(all_sc, loc_sc)
+    idx, sc = tdist.merge_topk_lists([t.numpy() for t in all_idx], [t.numpy() for t in all_sc], k)
+    assert np.array_equal(idx, want)  # a global top-k member is always in its slab's local top-k
+    assert np.array_equal(sc, np.take_along_axis(P, want.astype(np.int64), 1))
+
+
+def test_item_sharded_topk_merge():
+    _spawn(_sharded_topk)
+
+
+def _mean_loss(rank, world):
+    class IP:
+        loss = "wmrb"
+        n_pos = 3 + rank
+        vals = torch.zeros(1)
+
+        def mean_loss(self):
+            return 2.0 + rank
+    got = tdist.GradientSync().mean_loss(IP())
+    assert abs(got - (3 * 2.0 + 4 * 3.0) / 7) < 1e-12
+
+
+def test_mean_loss_is_weighted_over_ranks():
+    _spawn(_mean_loss)
