@@ -369,6 +369,7 @@ def main():
     ap.add_argument("--topk", default="1000000x1000000x128x100", help="users x items x rank x k of the secondary top-k bench; 'none' skips")
     ap.add_argument("--topk-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--topk-only", action="store_true", help="run only the secondary top-k bench (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -398,6 +399,13 @@ def main():
     from teamoflow_b200.mf import dist as tdist
     dev = torch.device("cuda", local)
     hbm_peak, tf_peak, peak_src = peaks()
+
+    if args.topk_only:
+        tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
+        res = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak)
+        if rank == 0:
+            print(json.dumps(res))
+        return
 
     wl = Workload(args.workload, rank, world)
     comm = None

@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -21,10 +22,15 @@ constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
 constexpr int BN = 128;        // items per accumulator tile (TMEM columns); two CTAs share an SM
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NSTAGES = 4;     // B-operand ring (16 KB stages)
+constexpr int NSTAGES = 3;     // B-operand ring (16 KB stages)
 constexpr int TMEM_COLS = 2 * BN;  // two accumulators per CTA, double-buffered against the epilogue
-constexpr int CAP = 512;       // candidate slots per row
-constexpr int CPL = CAP / 32;  // candidates per lane in warp-cooperative passes
+constexpr int CAP = 2048;      // candidate slots per row (appended, never compacted; saturation -> exact path)
+constexpr int INIT_N = 512;    // a row's threshold state is initialised from its first <= INIT_N entries
+constexpr int CPL = INIT_N / 32;  // entries per lane in the warp-cooperative initial selection
+constexpr int NBINS = 48;      // per-row score histogram bins (16-bit counts, two per word)
+constexpr int QCAP = 16;       // per-row survivor queue slots in shared memory (drained warp-wide)
+constexpr int HSTRIDE = NBINS / 2 + 1;  // words per row, padded against bank conflicts
+constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 4 GB
 constexpr int TOPK_THREADS = 256;
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
@@ -125,7 +131,12 @@ __device__ __forceinline__ float key2f(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// k-th largest of the n (<= CAP) values spread 16-per-lane (element e = lane + 32 t); hist: 256 ints of smem
+// shared-space reduction (a generic-address atomicAdd compiles to the slow generic ATOM path)
+__device__ __forceinline__ void smem_inc(int* p) {
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+
+// k-th largest of the n (<= INIT_N) values spread 16-per-lane (element e = lane + 32 t); hist: 256 ints of smem
 __device__ float warp_kth_largest(const float (&sc)[CPL], int n, int k, int* hist) {
   const int lane = threadIdx.x & 31;
   uint32_t prefix = 0, mask = 0;
@@ -138,7 +149,7 @@ __device__ float warp_kth_largest(const float (&sc)[CPL], int n, int k, int* his
 #pragma unroll
     for (int t = 0; t < CPL; ++t) {
       const uint32_t key = f2key(sc[t]);
-      if (lane + 32 * t < n && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      if (lane + 32 * t < n && (key & mask) == prefix) smem_inc(&hist[(key >> shift) & 255u]);
     }
     __syncwarp();
     int c[8];
@@ -176,68 +187,126 @@ __device__ float warp_kth_largest(const float (&sc)[CPL], int n, int k, int* his
 
 struct TopkParams {
   long long n_users, n_items;   // real sizes
-  int n_ublocks, n_tiles, kb;   // padded tiling: user blocks of 128, item tiles of 256, k-blocks of 64
+  int ub0, n_ublocks;           // this launch covers user blocks [ub0, ub0 + n_ublocks)
+  int n_tiles, kb;              // item tiles of BN, k-blocks of BK
   int k, clamp, item_offset;
-  const float* unorm;           // [n_users_pad] l2 norm of each user row
+  const float* unorm;           // [n_users_pad] l2 norm of each user row (global row index)
   const float* vmax;            // [1] max item-row norm
-  float2* cand;                 // [n_users_pad][CAP] (approx score, item id bits)
-  int* cnt;                     // [n_users_pad] candidates per row, -1 = overflow (exact path)
+  float2* cand;                 // [batch rows][CAP] (approx score, item id bits), batch-local row index
+  int* cnt;                     // [batch rows] candidates per row, -1 = overflow (exact path)
+  float* thr_out;               // [batch rows] final keep-threshold of the row
   int* ovf_count;               // [1]
-  int* ovf_rows;                // [n_users_pad]
+  int* ovf_rows;                // [n_users_pad] global rows handed to the exact path
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
+  unsigned long long* prof;     // optional [8] cycle counters (env TMF_TOPK_PROF=1): where the warps wait
+  int dbg;                      // profiling aid (env TMF_TOPK_DEBUG): 1 = no appends, 2 = no filtering, 3 = no TMEM reads
 };
 
-// keep rule shared by the in-kernel compaction and the final selection
-__device__ __forceinline__ float new_threshold(float kth, float E, int clamp) {
+// Keep-threshold from a lower bound `kth` of the row's k-th largest approximate score.
+//   raw scores   : every top-k member has s~ >= kth - 2E
+//   clamped (>0) : every top-k member outside the k lowest item ids has s~ >= max(kth - E, 0) - E
+__device__ __forceinline__ float keep_threshold(float kth, float E, int clamp) {
   return clamp ? fmaxf(kth - E, 0.f) - E : kth - 2.f * E;
 }
 
-// compact one row's candidate list in place; returns the new count and threshold (all lanes)
-__device__ void warp_compact(float2* buf, int n, int k, float E, int clamp, int item_offset, int* hist, int& n_out, float& thr_out) {
-  const int lane = threadIdx.x & 31;
-  float sc[CPL];
-  int ix[CPL];
+// ---- per-row running threshold: a lane-private 48-bin histogram of the appended scores (16-bit counts, two
+// bins per shared-memory word).  bthr = the highest bin whose "at or above" count A is still >= k, so the lower
+// edge of bin bthr is a valid lower bound of the k-th largest score seen so far; it only ever rises.
+//
+// ---- SIMD list maintenance.  A lane that finds a survivor only pushes (score, item) onto its own small
+// shared-memory queue (3 instructions, no dependent loads).  When a queue is about to fill, the WHOLE warp
+// drains: iteration s handles entry s of every lane at once, each lane appending to its own row's list and
+// updating its own histogram -- the ~40-instruction append runs once per queue slot for 32 rows instead of
+// once per survivor with 1-3 active lanes (measured: 400-600 cycles per survivor in the divergent versions).
+struct RowState {
+  float thr;      // current keep-threshold (+inf for padded rows)
+  float lo, w, inv_w, E;
+  int cnt;        // list length; > CAP = saturated (-> exact path)
+  int cq;         // entries waiting in the lane's queue
+  int bthr, A;    // threshold bin and # entries with bin >= bthr
+};
+
+__device__ __forceinline__ int hist_get(const uint32_t* hrow, int b) { return (int)((hrow[b >> 1] >> ((b & 1) * 16)) & 0xffffu); }
+// explicit shared-space accesses: through generic pointers these compile to the slower ST.E/LD.E with 64-bit addressing
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ int hist_get_s(uint32_t hrow, int b) { return (int)((lds_u32(hrow + 4u * (uint32_t)(b >> 1)) >> ((b & 1) * 16)) & 0xffffu); }
+
+__device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, float E, int clamp) {
+  const float edge = lo + (float)bthr * w;
+  const float slack = 4e-7f * (fabsf(lo) + (float)NBINS * w);  // rounding of the bin arithmetic
+  return keep_threshold(edge - slack, E, clamp);
+}
+
+// warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane)
+__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
+  int maxq = st.cq;
 #pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const int e = lane + 32 * t;
-    float2 x = make_float2(-INFINITY, 0.f);
-    if (e < n) x = buf[e];
-    sc[t] = x.x;
-    ix[t] = __float_as_int(x.y);
+  for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
+#pragma unroll 1
+  for (int s = 0; s < maxq; ++s) {
+    if (s < st.cq) {
+      const float2 e = lds_f2(queue + 8u * (uint32_t)s);
+      if (e.x >= st.thr) {  // the threshold may have risen since the entry was queued
+        if (st.cnt < CAP) __stcg(buf + st.cnt, e);
+        ++st.cnt;           // > CAP marks saturation
+        if (e.x >= st.lo) {
+          const int b = (int)fminf((e.x - st.lo) * st.inv_w, (float)(NBINS - 1));
+          const uint32_t wa = hrow + 4u * (uint32_t)(b >> 1);
+          sts_u32(wa, lds_u32(wa) + (1u << ((b & 1) * 16)));
+          if (b >= st.bthr) {
+            ++st.A;
+            bool moved = false;
+            while (st.bthr < NBINS - 1) {
+              const int hb = hist_get_s(hrow, st.bthr);
+              if (st.A - hb < k) break;
+              st.A -= hb;
+              ++st.bthr;
+              moved = true;
+            }
+            if (moved) st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, clamp);
+          }
+        }
+      }
+    }
   }
-  const float kth = warp_kth_largest(sc, n, k, hist);
-  const float thr = new_threshold(kth, E, clamp);
+  st.cq = 0;
   __syncwarp();
-  int base = 0;
-  const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const int e = lane + 32 * t;
-    const bool keep = e < n && (sc[t] >= thr || (clamp && ix[t] - item_offset < k));
-    const unsigned b = __ballot_sync(0xffffffffu, keep);
-    if (keep) buf[base + __popc(b & lt)] = make_float2(sc[t], __int_as_float(ix[t]));
-    base += __popc(b);
-  }
-  __syncwarp();
-  n_out = base;
-  thr_out = thr;
 }
 
 // Filter one 32-column slice of a row's accumulator against its running threshold.  The fast path is a
-// 3-input max tree (FMNMX3) and one compare; 8-column groups that contain a survivor are rescanned.
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, bool tail_tile, bool valid, float thr, int& cnt,
-                                               float2* buf, long long row, const TopkParams& p) {
-  if (tail_tile) {
+// 3-input max tree (FMNMX3) and one compare; 8-column groups that contain a survivor are rescanned and the
+// survivors queued.  Before a row's threshold exists (first 3 tiles) every column is appended directly.
+// (Clamp-mode "filler" items -- the k <= 128 lowest ids -- therefore need no special case here.)
+template <bool DUMP>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int n_items, bool tail_tile, bool valid, bool warp_inited,
+                                               RowState& st, uint32_t queue, float2* buf, uint32_t hrow, long long row,
+                                               const TopkParams& p) {
+  if (DUMP) {
+    if (valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j >= p.n_items) r[j] = 0xff800000u;  // -inf: padded items never qualify
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
+    }
+    return;
   }
-  if (p.dump != nullptr && valid) {
+  if (p.dbg == 2 || p.dbg == 3) return;
+  const int id0 = p.item_offset + col0;
+  if (!warp_inited) {  // warp-uniform: no threshold yet, keep everything (coalesced per lane, no queue)
+    if (valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < p.n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < n_items) {
+          __stcg(buf + st.cnt, make_float2(__uint_as_float(r[j]), __int_as_float(id0 + j)));
+          ++st.cnt;
+        }
+      }
+    }
+    return;
   }
+  // (padded item columns of the last tile hold NaN scores -- see pack_bf16_kernel -- and never qualify)
   float m8[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -247,35 +316,153 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, bool
     m8[g] = fmaxf(c, __uint_as_float(r[8 * g + 7]));
   }
   const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-  const bool filler = p.clamp && col0 < p.k;  // clamp mode: the k lowest item ids of the slab are always kept
-  if (!__any_sync(0xffffffffu, valid && (mx >= thr || filler))) return;
+  if (p.dbg == 1) {  // keep the max tree alive without ever appending
+    if (mx == 123456.0f) buf[0] = make_float2(mx, 0.f);
+    return;
+  }
+  const float thr = st.thr;  // invalid rows carry thr = +inf
+  if (!__any_sync(0xffffffffu, mx >= thr)) return;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const bool gh = valid && (m8[g] >= thr || (filler && col0 + 8 * g < p.k));
+    const bool gh = m8[g] >= thr;
     if (__any_sync(0xffffffffu, gh)) {
+      if (__any_sync(0xffffffffu, gh && st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
       if (gh) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float v = __uint_as_float(r[8 * g + j]);
-          const int col = col0 + 8 * g + j;
-          if (col < p.n_items && (v >= thr || (filler && col < p.k))) {
-            buf[cnt] = make_float2(v, __int_as_float(p.item_offset + col));
-            ++cnt;
-          }
+          // predicated push onto the lane's queue (no branch: 8 sites per group stay convergent)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
+                       ::"f"(v), "f"(thr), "r"(queue + 8u * (uint32_t)st.cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
+          st.cq += (v >= thr) ? 1 : 0;
         }
       }
     }
   }
 }
 
+// exact k-th largest approximate score of a row's list (n entries in global memory, streamed through L2) by an
+// 8-bit-per-pass radix select; also returns the list maximum.  radix: 256 ints of shared-memory scratch.
+__device__ __noinline__ float warp_select_kth(const float2* buf, int n, int k, int* radix, float& mx_out) {
+  const int lane = threadIdx.x & 31;
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) radix[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const float sc = __ldcg(&buf[e].x);
+      mx = fmaxf(mx, sc);
+      const uint32_t key = f2key(sc);
+      if ((key & mask) == prefix) smem_inc(&radix[(key >> shift) & 255u]);
+    }
+    __syncwarp();
+    int c[8];
+    int lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // lane L owns bins 255-8L .. 248-8L, visited in descending order
+      c[i] = radix[255 - 8 * lane - i];
+      lsum += c[i];
+    }
+    int incl = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= krem);
+    const int F = reach ? __ffs(reach) - 1 : 31;  // reach != 0 whenever n >= k
+    int bin = 0, knew = 0;
+    if (lane == F) {
+      int cum = incl - lsum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cum + c[i] >= krem) { bin = 255 - 8 * lane - i; knew = krem - cum; break; }
+        cum += c[i];
+      }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, F);
+    krem = __shfl_sync(0xffffffffu, knew, F);
+    prefix |= (uint32_t)bin << shift;
+    mask |= 255u << shift;
+    __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  mx_out = mx;
+  return key2f(prefix);
+}
+
+// Warp-cooperative (re)build of one row's threshold state from its list of n (<= CAP) entries, streamed from L2:
+// exact k-th largest by radix select, histogram re-centred on [kth, kth + 4 (max - kth)), list compacted in place
+// against the new threshold (clamp mode also keeps the k lowest item ids).  Used once when a row has seen its first
+// 3 tiles and again whenever its list is about to saturate, so a badly placed histogram range heals itself.
+// Results in out[0..5] (shared memory): lo, w, inv_w, bthr, A, n_new.
+__device__ __noinline__ void warp_rebuild_row(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
+                                              int* radix, float* out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  float mx;
+  const float kth = warp_select_kth(buf, n, k, radix, mx);
+  float W = 4.0f * (mx - kth);
+  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(kth), 1.0f) * 1e-3f;
+  const float lo = kth;
+  const float w = W / (float)NBINS;
+  const float inv_w = (float)NBINS / W;
+  const float thr = keep_threshold(kth, E, clamp);  // exact k-th: the tightest valid threshold
+  // ---- compact in place against thr and rebuild the histogram from the kept entries >= lo
+  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
+  __syncwarp();
+  int base = 0;
+  for (int b0 = 0; b0 < n; b0 += 32 * 8) {
+    float2 x[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+    }
+    __syncwarp();  // every read of this batch precedes its writes (writes land at or below b0)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      const bool keep = e < n && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        __stcg(buf + base + __popc(bal & lt), x[t]);
+        if (x[t].x >= lo) {
+          const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
+        }
+      }
+      base += __popc(bal);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    // highest bin with at least k entries at or above it (bin 0 qualifies: >= k entries are >= kth)
+    int A = 0, bthr = 0;
+    for (int b = NBINS - 1; b >= 0; --b) {
+      A += hist_get(hrow, b);
+      if (A >= k) { bthr = b; break; }
+    }
+    out[0] = lo; out[1] = w; out[2] = inv_w; out[3] = __int_as_float(bthr); out[4] = __int_as_float(A);
+    out[5] = __int_as_float(base);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------ the fused kernel
+template <bool DUMP>
 __global__ void __launch_bounds__(TOPK_THREADS, 2)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve (1024-byte aligned operand tiles first)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] bf16
-  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // NSTAGES x [256][64] bf16
+  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // NSTAGES x [BN][64] bf16
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGES * B_STAGE_BYTES);
   uint64_t* full_bar = bars;                  // [NSTAGES]
   uint64_t* empty_bar = bars + NSTAGES;       // [NSTAGES]
@@ -284,7 +471,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   uint64_t* tfull = a_empty + 1;              // [2]
   uint64_t* tempty = tfull + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  int* hist_all = reinterpret_cast<int*>(tmem_slot + 4);  // 4 warps x 256
+  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(tmem_slot + 4);             // [BM][HSTRIDE] per-row score histograms
+  float2* queues = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(hist_rows + BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [BM][QCAP]
+  float* init_out = reinterpret_cast<float*>(queues + BM * QCAP);  // [4 warps][8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -314,18 +503,24 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+        long long t0 = clock64();
         mbar_wait(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
+        long long w_empty = 0, w_aempty = clock64() - t0;
         mbar_expect_tx(smem_u32(a_full), p.kb * A_SUB_BYTES);
-        for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, ub * BM, smem_u32(a_full));
+        for (int kb = 0; kb < p.kb; ++kb)
+          tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
         a_phase ^= 1;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.kb; ++kb) {
+            t0 = clock64();
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            w_empty += clock64() - t0;
             mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + stage * B_STAGE_BYTES), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
             if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
+        if (p.prof) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
       }
     }
   } else if (warp == 1) {
@@ -336,12 +531,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
         mbar_wait(smem_u32(a_full), a_phase);
         a_phase ^= 1;
+        long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
+          long long t0 = clock64();
           mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
+          w_tempty += clock64() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
+            t0 = clock64();
             mbar_wait(smem_u32(&full_bar[stage]), phase);
+            w_full += clock64() - t0;
             tcgen05_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
             const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
@@ -358,71 +558,110 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           if (acc == 0) acc_phase ^= 1;
         }
         tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
+        if (p.prof) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: threshold filter + candidate append =====================
+    // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
     const int q = warp - 4;  // TMEM lane quarter == warp % 4
-    int* hist = hist_all + q * 256;
+    int* radix = reinterpret_cast<int*>(queues + q * 32 * QCAP);  // radix-select scratch aliases the warp's (empty) queues
+    const uint32_t hrow = smem_u32(hist_rows + (q * 32 + lane) * HSTRIDE);
+    const uint32_t queue = smem_u32(queues + (q * 32 + lane) * QCAP);
+    float* iout = init_out + q * 8;
+    const int n_items = (int)p.n_items;
     int acc = 0;
     uint32_t acc_phase = 0;
     const float vmax = *p.vmax;
     for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-      const long long row = (long long)ub * BM + q * 32 + lane;
+      const long long lrow = (long long)ub * BM + q * 32 + lane;       // batch-local row (candidate buffers)
+      const long long row = (long long)p.ub0 * BM + lrow;              // global row
       const bool valid = row < p.n_users;
-      const float E = ERR_FACTOR * p.unorm[row] * vmax + 1e-30f;
-      float thr = valid ? -INFINITY : INFINITY;
-      int cnt = 0;
-      float2* buf = p.cand + row * CAP;
+      RowState st;
+      st.thr = valid ? -INFINITY : INFINITY;
+      st.lo = 0.f; st.w = 0.f; st.inv_w = 0.f;
+      st.E = ERR_FACTOR * p.unorm[row] * vmax + 1e-30f;
+      st.cnt = 0; st.cq = 0; st.bthr = 0; st.A = 0;
+      bool warp_inited = false;
+      float2* buf = p.cand + lrow * CAP;
+      long long w_tfull = 0, w_work = 0, w_init = 0;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
+        long long t0 = clock64();
         mbar_wait(smem_u32(&tfull[acc]), acc_phase);
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
+        long long t1 = clock64();
+        w_tfull += t1 - t0;
         tcgen05_fence_after();
-        const bool tail_tile = (long long)(nt + 1) * BN > p.n_items;
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const bool tail_tile = (nt + 1) * BN > n_items;
         uint32_t ra[32], rb[32];
-        tmem_ld32(t_base, ra);
-#pragma unroll
-        for (int ch = 0; ch < BN / 32; ch += 2) {
-          // chunk ch is in ra; chunk ch+1 is fetched into rb while ra is filtered (and vice versa)
-          tmem_ld_wait_for(ra);
-          tmem_ld32(t_base + (uint32_t)((ch + 1) * 32), rb);
-          epilogue_chunk(ra, nt * BN + ch * 32, tail_tile, valid, thr, cnt, buf, row, p);
-          tmem_ld_wait_for(rb);
-          if (ch + 2 < BN / 32) tmem_ld32(t_base + (uint32_t)((ch + 2) * 32), ra);
-          epilogue_chunk(rb, nt * BN + (ch + 1) * 32, tail_tile, valid, thr, cnt, buf, row, p);
+        if (p.dbg < 3) {
+          tmem_ld32(t_base, ra);
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ch += 2) {
+            // chunk ch is in ra; chunk ch+1 is fetched into rb while ra is filtered (and vice versa)
+            tmem_ld_wait_for(ra);
+            tmem_ld32(t_base + (uint32_t)((ch + 1) * 32), rb);
+            epilogue_chunk<DUMP>(ra, nt * BN + ch * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
+            tmem_ld_wait_for(rb);
+            if (ch + 2 < BN / 32) tmem_ld32(t_base + (uint32_t)((ch + 2) * 32), ra);
+            epilogue_chunk<DUMP>(rb, nt * BN + (ch + 1) * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
+          }
         }
         // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&tempty[acc]));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        // make room for the next tile's (at most BN) appends -- warp-uniform
-        unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - BN);
-        while (need) {
-          const int owner = __ffs(need) - 1;
-          need &= need - 1;
-          const int n_o = __shfl_sync(0xffffffffu, cnt, owner);
-          const float E_o = __shfl_sync(0xffffffffu, E, owner);
-          float2* buf_o = p.cand + ((long long)ub * BM + q * 32 + owner) * CAP;
-          __syncwarp();
-          int n_new;
-          float thr_new;
-          warp_compact(buf_o, n_o, p.k, E_o, p.clamp, p.item_offset, hist, n_new, thr_new);
-          if (lane == owner) {
-            if (n_new > CAP - BN) {  // cannot shrink (massive ties): hand the row to the exact path
-              const int slot = atomicAdd(p.ovf_count, 1);
-              p.ovf_rows[slot] = (int)row;
-              thr = INFINITY;
-              cnt = -1;
-            } else {
-              thr = thr_new;
-              cnt = n_new;
-            }
+        long long t2 = clock64();
+        w_work += t2 - t1;
+        if (!DUMP) {
+          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+          // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
+          // the same tile because everything is appended until then), later whenever a list is about to saturate
+          const bool first = !warp_inited && __any_sync(0xffffffffu, valid && st.cnt >= INIT_N - BN);
+          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
+          if (need) {  // the radix scratch aliases the queues: empty them first (lengths may grow a little)
+            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
           }
+          while (need) {
+            const int owner = __ffs(need) - 1;
+            need &= need - 1;
+            const int n_o = __shfl_sync(0xffffffffu, st.cnt, owner);
+            const float E_o = __shfl_sync(0xffffffffu, st.E, owner);
+            __syncwarp();
+            warp_rebuild_row(p.cand + ((long long)ub * BM + q * 32 + owner) * CAP, n_o, p.k, p.clamp, p.item_offset, E_o,
+                             hist_rows + (q * 32 + owner) * HSTRIDE, radix, iout);
+            if (lane == owner) {
+              st.lo = iout[0]; st.w = iout[1]; st.inv_w = iout[2];
+              st.bthr = __float_as_int(iout[3]); st.A = __float_as_int(iout[4]);
+              st.cnt = __float_as_int(iout[5]);
+              st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp);
+              if (st.cnt > CAP - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
+                st.cnt = CAP + 1;
+                st.thr = INFINITY;
+              }
+            }
+            __syncwarp();
+          }
+          if (first) warp_inited = true;
         }
+        w_init += clock64() - t2;
       }
-      p.cnt[row] = valid ? cnt : 0;
+      if (!DUMP) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+      if (p.prof && lane == 0) {
+        atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
+        atomicAdd(p.prof + 6, (unsigned long long)w_init); atomicAdd(p.prof + 7, 1ull);
+      }
+      const bool ovf = st.cnt > CAP;
+      if (valid && ovf) {
+        const int slot = atomicAdd(p.ovf_count, 1);
+        p.ovf_rows[slot] = (int)row;
+        if (p.prof) atomicAdd(p.prof + 8, 1ull);
+      }
+      p.cnt[lrow] = valid ? (ovf ? -1 : st.cnt) : 0;
+      p.thr_out[lrow] = st.thr;
+      __syncwarp();
     }
   }
 
@@ -433,10 +672,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
 }
 
 // ------------------------------------------------------------------ final selection + canonical rerank
-constexpr int RR_WARPS = 4;
+constexpr int RR_WARPS = 8;
+constexpr int SEL_CAP = 512;   // survivors per row the rerank can rank; more -> exact path
+constexpr int RR_CHAINS = 4;   // independent fp64 FMA chains per lane
 
 struct RerankParams {
-  long long n_users, n_items;
+  long long n_users, n_items, row0;  // rows [row0, row0 + n_rows) are batch-local rows [0, n_rows)
+  long long n_rows;
   int k, clamp, item_offset, r, ld;
   const float* U;
   const float* V;
@@ -444,6 +686,10 @@ struct RerankParams {
   const float* vmax;
   const float2* cand;
   const int* cnt;
+  const float* thr;
+  int* ovf_count;
+  int* ovf_rows;
+  unsigned long long* prof;
   int* out_idx;
   float* out_score;
 };
@@ -451,66 +697,95 @@ struct RerankParams {
 __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParams p) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rp = p.r + 1;  // padded row stride: conflict-free per-lane row walks
-  const size_t per_warp = (size_t)(32 * rp + p.r) * sizeof(float) + CAP * 8 + 256 * sizeof(int);
+  const size_t per_warp = (size_t)p.ld * sizeof(double) + SEL_CAP * 8;
   unsigned char* base = rr_smem + (size_t)w * per_warp;
-  float* tile = reinterpret_cast<float*>(base);      // [32][r+1] gathered item rows
-  float* su = tile + 32 * rp;                        // [r] this user's row
-  float* ex = su + p.r;                              // [CAP] exact scores
-  int* id = reinterpret_cast<int*>(ex + CAP);        // [CAP] item ids
-  int* hist = id + CAP;                              // [256]
+  double* ud = reinterpret_cast<double*>(base);            // [ld] this user's row, widened once
+  float* ex = reinterpret_cast<float*>(ud + p.ld);          // [SEL_CAP] canonical scores
+  int* id = reinterpret_cast<int*>(ex + SEL_CAP);           // [SEL_CAP] item ids
+  int* radix = id;                                          // radix-select scratch (256 ints) before id[] is filled
 
-  const long long row = (long long)blockIdx.x * RR_WARPS + w;
-  if (row >= p.n_users) return;
-  const int n = p.cnt[row];
-  if (n < 0) return;  // overflowed row: exact_rows_kernel owns it
-  const float2* buf = p.cand + row * CAP;
-  float sc[CPL];
-  int ix[CPL];
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const int e = lane + 32 * t;
-    float2 x = make_float2(-INFINITY, 0.f);
-    if (e < n) x = buf[e];
-    sc[t] = x.x;
-    ix[t] = __float_as_int(x.y);
-  }
+  const long long lrow = (long long)blockIdx.x * RR_WARPS + w;
+  if (lrow >= p.n_rows) return;
+  const long long row = p.row0 + lrow;
+  const int n = p.cnt[lrow];
+  if (n < 0) return;  // overflowed in the main kernel: exact_rows_kernel owns it
+  const float2* buf = p.cand + lrow * CAP;
   const int k = p.k;
-  const float E = ERR_FACTOR * p.unorm[row] * (*p.vmax) + 1e-30f;
-  const float kth = warp_kth_largest(sc, n, k, hist);
-  const float thr = new_threshold(kth, E, p.clamp);
+  // final keep-threshold from the exact k-th largest approximate score of the list (tighter than the running
+  // histogram edge the main kernel stopped at: fewer canonical scores to evaluate)
+  float thr = p.thr[lrow];
+  if (n > k) {
+    float mx;
+    const float kth = warp_select_kth(buf, n, k, radix, mx);
+    thr = fmaxf(thr, keep_threshold(kth, ERR_FACTOR * p.unorm[row] * (*p.vmax) + 1e-30f, p.clamp));
+  }
+  // ---- pass 1: stream the list once, keep what the final threshold (or the clamp-mode filler rule) keeps
   int m = 0;
   const unsigned lt = (1u << lane) - 1u;
+  for (int b0 = 0; b0 < n; b0 += 128) {
+    float2 x[4];
 #pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const int e = lane + 32 * t;
-    const bool keep = e < n && (sc[t] >= thr || (p.clamp && ix[t] - p.item_offset < k));
-    const unsigned b = __ballot_sync(0xffffffffu, keep);
-    if (keep) id[m + __popc(b & lt)] = ix[t];
-    m += __popc(b);
+    for (int t = 0; t < 4; ++t) {
+      const int e = b0 + 32 * t + lane;
+      x[t] = (e < n) ? buf[e] : make_float2(-INFINITY, 0.f);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = b0 + 32 * t + lane;
+      const int item = __float_as_int(x[t].y);
+      const bool keep = e < n && (x[t].x >= thr || (p.clamp && item - p.item_offset < k));
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      const int pos = m + __popc(bal & lt);
+      if (keep && pos < SEL_CAP) id[pos] = item;
+      m += __popc(bal);
+    }
   }
-  for (int c = lane; c < p.r; c += 32) su[c] = p.U[row * p.ld + c];
+  if (m > SEL_CAP) {  // too many near-ties to rank here
+    if (lane == 0) {
+      if (p.prof) atomicAdd(p.prof + 9, 1ull);
+      const int slot = atomicAdd(p.ovf_count, 1);
+      p.ovf_rows[slot] = (int)row;
+    }
+    return;
+  }
+  for (int c = lane; c < p.ld; c += 32) ud[c] = (double)p.U[row * p.ld + c];
   __syncwarp();
-  // canonical scores, 32 candidates at a time: coalesced row gathers into smem, then one fp64 FMA
-  // chain per lane in component order (bit-identical to oracle.canonical_scores)
-  for (int b0 = 0; b0 < m; b0 += 32) {
-    const int nb = min(32, m - b0);
-    for (int j = 0; j < nb; ++j) {
-      const float* vrow = p.V + (long long)(id[b0 + j] - p.item_offset) * p.ld;
-      for (int c = lane; c < p.r; c += 32) tile[j * rp + c] = vrow[c];
+  // ---- canonical scores: one fp64 FMA chain per candidate in component order (bit-identical to
+  // oracle.canonical_scores; zero pad columns add +0.0), RR_CHAINS independent chains per lane for ILP
+  for (int t0 = lane; t0 < m; t0 += 32 * RR_CHAINS) {
+    const float* vr[RR_CHAINS];
+    double acc[RR_CHAINS];
+#pragma unroll
+    for (int q = 0; q < RR_CHAINS; ++q) {
+      const int t = t0 + 32 * q;
+      vr[q] = p.V + (long long)((t < m ? id[t] : id[t0]) - p.item_offset) * p.ld;
+      acc[q] = 0.0;
     }
-    __syncwarp();
-    if (lane < nb) {
-      double acc = 0.0;
-      const float* tr = tile + lane * rp;
-      for (int c = 0; c < p.r; ++c) acc = fma((double)su[c], (double)tr[c], acc);
-      float s = (float)acc;
-      if (p.clamp) s = s > 0.f ? s : 0.f;  // tf.where(p > 0, p, 0.0)
-      ex[b0 + lane] = s + 0.0f;
+    for (int c = 0; c < p.ld; c += 4) {
+      float4 x[RR_CHAINS];
+#pragma unroll
+      for (int q = 0; q < RR_CHAINS; ++q) x[q] = ldg4(vr[q] + c);
+      const double u0 = ud[c], u1 = ud[c + 1], u2 = ud[c + 2], u3 = ud[c + 3];
+#pragma unroll
+      for (int q = 0; q < RR_CHAINS; ++q) {
+        acc[q] = fma(u0, (double)x[q].x, acc[q]);
+        acc[q] = fma(u1, (double)x[q].y, acc[q]);
+        acc[q] = fma(u2, (double)x[q].z, acc[q]);
+        acc[q] = fma(u3, (double)x[q].w, acc[q]);
+      }
     }
-    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < RR_CHAINS; ++q) {
+      const int t = t0 + 32 * q;
+      if (t < m) {
+        float s = (float)acc[q];
+        if (p.clamp) s = s > 0.f ? s : 0.f;  // tf.where(p > 0, p, 0.0)
+        ex[t] = s + 0.0f;
+      }
+    }
   }
-  // rank by counting with comparator (score desc, item id asc); ids are distinct so ranks are too
+  __syncwarp();
+  // ---- rank by counting with comparator (score desc, item id asc); ids are distinct so ranks are too
   for (int t = lane; t < m; t += 32) {
     const float s = ex[t];
     const int my = id[t];
@@ -523,64 +798,107 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   }
 }
 
-// exact path for rows whose candidate list overflowed (huge tie groups): all canonical scores of the
-// row into scratch, then k rounds of block-wide arg-max in (score desc, id asc) order.
+// exact path for rows whose candidate list overflowed (huge tie groups, adversarially ordered scores): all
+// canonical scores of the row go to scratch; a block-wide radix select finds the k-th largest score T; entries > T
+// plus the lowest-indexed entries == T are collected (k in total) and ranked by (score desc, id asc).
 __global__ void __launch_bounds__(256) exact_rows_kernel(const RerankParams p, const int* __restrict__ ovf_count,
                                                          const int* __restrict__ ovf_rows, float* __restrict__ scratch) {
-  __shared__ float s_best[8];
-  __shared__ int s_besti[8];
-  __shared__ float s_prev;
-  __shared__ int s_previ;
+  __shared__ int hist[256];
+  __shared__ int s_bin, s_krem, s_cnt_gt, s_cnt_eq, s_warp_tot[8];
+  __shared__ float sel_s[128];
+  __shared__ int sel_i[128];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n_ovf = *ovf_count;
+  const int n = (int)p.n_items;
+  const int k = p.k;
   float* sc = scratch + (long long)blockIdx.x * p.n_items;
   for (int o = blockIdx.x; o < n_ovf; o += gridDim.x) {
     const long long row = ovf_rows[o];
     const float* u = p.U + row * p.ld;
-    for (long long i = threadIdx.x; i < p.n_items; i += 256) {
-      const float* v = p.V + i * p.ld;
+    for (int i = tid; i < n; i += 256) {
+      const float* v = p.V + (long long)i * p.ld;
       double acc = 0.0;
       for (int c = 0; c < p.r; ++c) acc = fma((double)u[c], (double)v[c], acc);
       float s = (float)acc;
       if (p.clamp) s = s > 0.f ? s : 0.f;
       sc[i] = s + 0.0f;
     }
-    if (threadIdx.x == 0) { s_prev = INFINITY; s_previ = -1; }
     __syncthreads();
-    for (int q = 0; q < p.k; ++q) {
-      const float ps = s_prev;
-      const int pi = s_previ;
-      float best = -INFINITY;
-      int besti = 0x7fffffff;
-      for (long long i = threadIdx.x; i < p.n_items; i += 256) {
-        const float s = sc[i];
-        const bool after = (s < ps) || (s == ps && (int)i > pi);
-        if (after && (s > best || (s == best && (int)i < besti))) { best = s; besti = (int)i; }
-      }
-#pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o2);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o2);
-        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-      }
-      if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_besti[threadIdx.x >> 5] = besti; }
+    // ---- k-th largest key, 8 bits per pass
+    uint32_t prefix = 0, mask = 0;
+    int krem = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0;
       __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int w2 = 1; w2 < 8; ++w2)
-          if (s_best[w2] > best || (s_best[w2] == best && s_besti[w2] < besti)) { best = s_best[w2]; besti = s_besti[w2]; }
-        p.out_idx[row * p.k + q] = besti + p.item_offset;
-        p.out_score[row * p.k + q] = best;
-        s_prev = best;
-        s_previ = besti;
+      for (int i = tid; i < n; i += 256) {
+        const uint32_t key = f2key(sc[i]);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 255;
+        for (; b > 0; --b) {
+          if (cum + hist[b] >= krem) break;
+          cum += hist[b];
+        }
+        s_bin = b;
+        s_krem = krem - cum;
+      }
+      __syncthreads();
+      prefix |= (uint32_t)s_bin << shift;
+      mask |= 255u << shift;
+      krem = s_krem;
+      __syncthreads();
+    }
+    const float T = key2f(prefix);  // exactly the k-th largest score; krem of the entries == T are needed
+    if (tid == 0) { s_cnt_gt = 0; s_cnt_eq = 0; }
+    __syncthreads();
+    // ---- collect: every entry > T (k - krem of them), and the krem lowest-indexed entries == T (ordered scan)
+    for (int i0 = 0; i0 < n; i0 += 256) {
+      const int i = i0 + tid;
+      const float s = i < n ? sc[i] : -INFINITY;
+      const bool gt = i < n && s > T;
+      const bool eq = i < n && s == T;
+      if (gt) {
+        const int pos = atomicAdd(&s_cnt_gt, 1);
+        sel_s[pos] = s;
+        sel_i[pos] = i;
+      }
+      const unsigned beq = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_warp_tot[wid] = __popc(beq);
+      __syncthreads();
+      int before = s_cnt_eq;
+      for (int w2 = 0; w2 < wid; ++w2) before += s_warp_tot[w2];
+      const int my = before + __popc(beq & ((1u << lane) - 1u));
+      if (eq && my < krem) {  // slots [k - krem, k) hold the tied entries in index order
+        sel_s[k - krem + my] = s;
+        sel_i[k - krem + my] = i;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int tot = 0;
+        for (int w2 = 0; w2 < 8; ++w2) tot += s_warp_tot[w2];
+        s_cnt_eq += tot;
       }
       __syncthreads();
     }
+    // ---- rank the k selected entries
+    if (tid < k) {
+      const float s = sel_s[tid];
+      const int id = sel_i[tid];
+      int rank = 0;
+      for (int j = 0; j < k; ++j) rank += (sel_s[j] > s) || (sel_s[j] == s && sel_i[j] < id);
+      p.out_idx[row * k + rank] = id + p.item_offset;
+      p.out_score[row * k + rank] = s;
+    }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ operand packing
 // one warp per row: fp32 [n, ld] -> bf16 [n_pad, k_pad] (zero padded), row norm, optional global max norm
 __global__ void pack_bf16_kernel(const float* __restrict__ src, long long n, int r, int ld, __nv_bfloat16* __restrict__ dst,
-                                 long long n_pad, int k_pad, float* __restrict__ norms, int* __restrict__ max_norm_bits) {
+                                 long long n_pad, int k_pad, float* __restrict__ norms, int* __restrict__ max_norm_bits, int nan_pad) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_pad) return;
@@ -589,7 +907,9 @@ __global__ void pack_bf16_kernel(const float* __restrict__ src, long long n, int
     float v = 0.f;
     if (row < n && c < r) v = src[row * ld + c];
     ss = fmaf(v, v, ss);
-    dst[row * k_pad + c] = __float2bfloat16_rn(v);
+    // padded ITEM rows are NaN: their scores are NaN in every accumulator row, which fmaxf ignores and every
+    // >= test rejects -- the epilogue needs no per-column bounds checks
+    dst[row * k_pad + c] = (nan_pad && row >= n) ? __ushort_as_bfloat16((unsigned short)0x7FC0) : __float2bfloat16_rn(v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -631,9 +951,9 @@ static int make_tmap(CUtensorMap* map, void* base, long long rows, int k_pad, in
 }
 
 struct TopkLayout {
-  long long nu_pad, ni_pad;
+  long long nu_pad, ni_pad, batch_rows;
   int k_pad, kb;
-  size_t off_ub, off_vb, off_unorm, off_vnorm, off_vmax, off_cand, off_cnt, off_ovfc, off_ovfr, off_scratch, total;
+  size_t off_ub, off_vb, off_unorm, off_vnorm, off_vmax, off_cand, off_cnt, off_thr, off_ovfc, off_ovfr, off_scratch, total;
   int scratch_rows;
 };
 
@@ -643,6 +963,7 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   TopkLayout L{};
   L.nu_pad = cdiv(n_users, BM) * BM;
   L.ni_pad = cdiv(n_items, BN) * BN;
+  L.batch_rows = std::min<long long>(L.nu_pad, (long long)UB_BATCH * BM);
   L.k_pad = (int)(cdiv(r, BK) * BK);
   L.kb = L.k_pad / BK;
   size_t o = 0;
@@ -651,8 +972,9 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   L.off_unorm = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.off_vnorm = o; o = align_up(o + (size_t)L.ni_pad * 4, 256);
   L.off_vmax = o; o += 256;
-  L.off_cand = o; o = align_up(o + (size_t)L.nu_pad * CAP * 8, 256);
-  L.off_cnt = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
+  L.off_cand = o; o = align_up(o + (size_t)L.batch_rows * CAP * 8, 256);
+  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
+  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
   L.off_ovfc = o; o += 256;
   L.off_ovfr = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.scratch_rows = (int)std::min<long long>(32, n_users);
@@ -670,7 +992,7 @@ extern "C" int tmf_pack_bf16(const float* src, int64_t n, int32_t n_comp, int32_
   TMF_REQUIRE(n_pad >= n && k_pad >= n_comp && n_comp <= ld, "tmf_pack_bf16: bad shape");
   if (n_pad == 0) return TMF_OK;
   pack_bf16_kernel<<<(unsigned)cdiv(n_pad * 32, 256), 256, 0, as_stream(stream)>>>(src, n, n_comp, ld, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                                                n_pad, k_pad, norms, nullptr);
+                                                                                n_pad, k_pad, norms, nullptr, 0);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }
@@ -698,6 +1020,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   int* vmax_bits = reinterpret_cast<int*>(w + L.off_vmax);
   float2* cand = reinterpret_cast<float2*>(w + L.off_cand);
   int* cnt = reinterpret_cast<int*>(w + L.off_cnt);
+  float* thr = reinterpret_cast<float*>(w + L.off_thr);
   int* ovfc = reinterpret_cast<int*>(w + L.off_ovfc);
   int* ovfr = reinterpret_cast<int*>(w + L.off_ovfr);
   float* scratch = reinterpret_cast<float*>(w + L.off_scratch);
@@ -705,8 +1028,8 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   TMF_CUDA(cudaMemsetAsync(vmax_bits, 0, 4, st));
   TMF_CUDA(cudaMemsetAsync(ovfc, 0, 4, st));
-  pack_bf16_kernel<<<(unsigned)cdiv(L.nu_pad * 32, 256), 256, 0, st>>>(U, n_users, n_comp, ld, Ub, L.nu_pad, L.k_pad, unorm, nullptr);
-  pack_bf16_kernel<<<(unsigned)cdiv(L.ni_pad * 32, 256), 256, 0, st>>>(V, n_items, n_comp, ld, Vb, L.ni_pad, L.k_pad, vnorm, vmax_bits);
+  pack_bf16_kernel<<<(unsigned)cdiv(L.nu_pad * 32, 256), 256, 0, st>>>(U, n_users, n_comp, ld, Ub, L.nu_pad, L.k_pad, unorm, nullptr, 0);
+  pack_bf16_kernel<<<(unsigned)cdiv(L.ni_pad * 32, 256), 256, 0, st>>>(V, n_items, n_comp, ld, Vb, L.ni_pad, L.k_pad, vnorm, vmax_bits, 1);
   TMF_LAUNCH_CHECK();
 
   CUtensorMap tmapU, tmapV;
@@ -717,28 +1040,57 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   TopkParams p{};
   p.n_users = n_users; p.n_items = n_items;
-  p.n_ublocks = (int)(L.nu_pad / BM); p.n_tiles = (int)(L.ni_pad / BN); p.kb = L.kb;
+  p.n_tiles = (int)(L.ni_pad / BN); p.kb = L.kb;
   p.k = k; p.clamp = clamp ? 1 : 0; p.item_offset = item_offset;
   p.unorm = unorm; p.vmax = reinterpret_cast<const float*>(vmax_bits);
-  p.cand = cand; p.cnt = cnt; p.ovf_count = ovfc; p.ovf_rows = ovfr;
+  p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
   p.dump = dump; p.dump_ld = n_items;
-
-  const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 + 4 * 256 * sizeof(int);
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
-  score_topk_kernel<<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
-  TMF_LAUNCH_CHECK();
-  if (dump != nullptr) return TMF_OK;
+  { const char* e = getenv("TMF_TOPK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.prof = nullptr;
+  if (getenv("TMF_TOPK_PROF")) {
+    p.prof = reinterpret_cast<unsigned long long*>(w + L.off_vmax + 64);
+    TMF_CUDA(cudaMemsetAsync(p.prof, 0, 96, st));
+  }
 
   RerankParams q{};
   q.n_users = n_users; q.n_items = n_items; q.k = k; q.clamp = p.clamp; q.item_offset = item_offset; q.r = n_comp; q.ld = ld;
-  q.U = U; q.V = V; q.unorm = unorm; q.vmax = p.vmax; q.cand = cand; q.cnt = cnt; q.out_idx = out_idx; q.out_score = out_score;
-  const size_t rr_smem = (size_t)RR_WARPS * ((size_t)(32 * (n_comp + 1) + n_comp) * sizeof(float) + CAP * 8 + 256 * sizeof(int));
+  q.U = U; q.V = V; q.unorm = unorm; q.vmax = p.vmax; q.prof = p.prof; q.cand = cand; q.cnt = cnt; q.thr = thr; q.ovf_count = ovfc; q.ovf_rows = ovfr;
+  q.out_idx = out_idx; q.out_score = out_score;
+
+  const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 +
+                      (size_t)BM * HSTRIDE * sizeof(uint32_t) + 16 + (size_t)BM * QCAP * 8 + 4 * 8 * sizeof(float);
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8);
   TMF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
-  rerank_kernel<<<(unsigned)cdiv(n_users, RR_WARPS), RR_WARPS * 32, rr_smem, st>>>(q);
-  TMF_LAUNCH_CHECK();
+
+  // users go through in batches of UB_BATCH blocks so the candidate workspace stays bounded; V stays packed
+  const int total_ublocks = (int)(L.nu_pad / BM);
+  for (int ub0 = 0; ub0 < total_ublocks; ub0 += UB_BATCH) {
+    p.ub0 = ub0;
+    p.n_ublocks = std::min(UB_BATCH, total_ublocks - ub0);
+    const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
+    if (dump != nullptr) score_topk_kernel<true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    else score_topk_kernel<false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    TMF_LAUNCH_CHECK();
+    if (dump != nullptr) continue;
+    q.row0 = (long long)ub0 * BM;
+    q.n_rows = std::min<long long>((long long)p.n_ublocks * BM, n_users - q.row0);
+    rerank_kernel<<<(unsigned)cdiv(q.n_rows, RR_WARPS), RR_WARPS * 32, rr_smem, st>>>(q);
+    TMF_LAUNCH_CHECK();
+  }
+  if (dump != nullptr) return TMF_OK;
   exact_rows_kernel<<<L.scratch_rows, 256, 0, st>>>(q, ovfc, ovfr, scratch);
   TMF_LAUNCH_CHECK();
+  if (p.prof) {  // profiling aid only: synchronises
+    unsigned long long h[12]; int novf = 0;
+    TMF_CUDA(cudaStreamSynchronize(st));
+    TMF_CUDA(cudaMemcpy(h, p.prof, 96, cudaMemcpyDeviceToHost));
+    TMF_CUDA(cudaMemcpy(&novf, ovfc, 4, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-sweep, n=%llu) "
+                    "wait tfull %.3g, work %.3g, init %.3g cycles | overflow rows %d (main %llu, rerank %llu)\n",
+            (double)h[0], (double)h[1], (double)h[2], (double)h[3], h[7], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], novf, h[8], h[9]);
+  }
   return TMF_OK;
 }
 
