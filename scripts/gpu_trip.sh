@@ -1,25 +1,15 @@
 #!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench.  Logs go to gpurun_out/.
 mkdir -p gpurun_out
-echo "== score tests"; timeout 900 python -m pytest tests/test_gpu_score.py -m gpu -q --timeout 300 -x > gpurun_out/test_score.log 2>&1; echo "exit $?"; tail -4 gpurun_out/test_score.log
-for m in 0; do
-  TMF_TOPK_PROF=1 TMF_TOPK_DEBUG=$m python - <<'PY'
-import torch, math, sys, os
-sys.path.insert(0, '.')
-from teamoflow_b200 import _abi
-from teamoflow_b200.mf._engine import new_storage
-from teamoflow_b200.mf.matrix_factorization import score_topk
-for (n_u, n_i) in ((151552, 262144), (151552, 1000000)):
-    r, k = 128, 100
-    g = torch.Generator(device='cuda'); g.manual_seed(1)
-    U = new_storage(n_u, r); U[:, :r] = torch.randn(n_u, r, generator=g, device='cuda') / math.sqrt(r)
-    V = new_storage(n_i, r); V[:, :r] = torch.randn(n_i, r, generator=g, device='cuda') / math.sqrt(r)
-    for it in range(2):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); score_topk(U, V, r, k, False); e1.record(); torch.cuda.synchronize()
-    print('dbg', os.environ.get('TMF_TOPK_DEBUG'), n_u, n_i, 'total ms', e0.elapsed_time(e1), 'TF/s', 2*n_u*n_i*r/e0.elapsed_time(e1)/1e9, flush=True)
+echo "== tests"; timeout 1200 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/test_gpu.log 2>&1; echo "exit $?"; tail -5 gpurun_out/test_gpu.log
+echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "exit $?"; tail -1 gpurun_out/smoke.log
+echo "== bench full"; timeout 1500 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "exit $?"; python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_full.json'))
+print('train ms/step', d['ms_per_step'], 'value', d['value'], 'step_roofline', d['step_roofline']['frac'])
+print('phases', d['phases_ms'])
+print('e2e', d['e2e']['value'])
+print('topk', {k:d['topk'].get(k) for k in ('ms_per_step','value','spot_check_exact','error')}, d['topk'].get('roofline'))
+print('cpu', d.get('cpu_baseline'))
 PY
-done
-CMD="python bench.py --topk-only --topk 151552x1000000x128x100 --topk-steps 1"
-$CMD > gpurun_out/ncu_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'score_topk_kernel|rerank_kernel|exact_rows_kernel|pack_bf16_kernel' -c 5 --csv --log-file gpurun_out/launches_topk.csv $CMD > gpurun_out/ncu_launch.log 2>&1; echo "launch list exit $?"
-grep -E "score_topk|rerank|exact|pack" gpurun_out/launches_topk.csv | awk -F'","' '{print substr($5,1,30), $(NF-1), $NF}' | head -10
+tail -3 gpurun_out/bench_full.err
