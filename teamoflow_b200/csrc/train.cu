@@ -707,7 +707,7 @@ extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && ld > 0 && ld % 4 == 0 && n_comp <= ld, "tmf_user_pass: bad shape");
   TMF_REQUIRE(ld <= 256, "tmf_user_pass: n_components up to 256 supported (ld=%d)", ld);
   TMF_REQUIRE(aligned16(Eu) && aligned16(Ei) && aligned16(dEu), "tmf_user_pass: embeddings must be 16-byte aligned");
-  TMF_REQUIRE(row_ptr && col_idx && val && counter && loss_out && coef_out, "tmf_user_pass: null pointer");
+  TMF_REQUIRE(row_ptr && counter && loss_out && coef_out && (nnz == 0 || (col_idx && val)), "tmf_user_pass: null pointer");
   if (loss == TMF_LOSS_WMRB) TMF_REQUIRE(samp && n_samples > 0, "tmf_user_pass: WMRB needs samples (random_ind)");
   if (n_users == 0) return TMF_OK;
   UserPassParams p{};

@@ -211,3 +211,32 @@ def test_tensor_core_scores_within_stated_error_bound(n_u, n_i, r):
     assert (err <= bound + 1e-30).all(), f"max err/bound = {(err / bound).max():.3f}"
     # and it really is a bf16-operand product, not something sloppier: typical error well inside the bound
     assert np.median(err / bound) < 0.2
+
+
+def test_topk_degenerate_shapes():
+    rng = np.random.default_rng(11)
+    for n_u, n_i, r, k in ((1, 1, 1, 1), (1, 130, 3, 128), (257, 129, 7, 5), (3, 385, 2, 100), (5, 2049, 4, 9)):
+        U = rng.standard_normal((n_u, r)).astype(np.float32)
+        V = rng.standard_normal((n_i, r)).astype(np.float32)
+        for clamp in (False, True):
+            idx, sc = fused_topk(U, V, k, clamp)
+            widx, wsc = oracle_topk(U, V, k, clamp)
+            assert np.array_equal(idx, widx) and np.array_equal(sc, wsc), (n_u, n_i, r, k, clamp)
+
+
+def test_topk_larger_sweep_with_rebuilds_bit_exact():
+    """enough items per row (60k) that lists are rebuilt/compacted several times, k=100, r=128"""
+    rng = np.random.default_rng(12)
+    n_u, n_i, r, k = 300, 60_000, 128, 100
+    U = (rng.standard_normal((n_u, r)) / np.sqrt(r)).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) / np.sqrt(r)).astype(np.float32) * rng.uniform(0.5, 2.0, (n_i, 1)).astype(np.float32)
+    idx, sc = fused_topk(U, V, k, False)
+    # oracle on the few thousand best approximate candidates per row only (full 300 x 60k canonical is slow on CPU)
+    P = U.astype(np.float64) @ V.astype(np.float64).T
+    cand = np.argpartition(-P, 400, axis=1)[:, :400]
+    for u in range(n_u):
+        c = np.sort(cand[u])
+        s = o.canonical_pair_scores(U, V, np.full(c.size, u), c)
+        order = np.lexsort((c, -s.astype(np.float64)))[:k]
+        assert np.array_equal(idx[u], c[order].astype(np.int32)), u
+        assert np.array_equal(sc[u], s[order])

@@ -395,3 +395,49 @@ def test_standalone_get_loss_and_get_repr_entry_points():
     emb, tr = E.ReLUEmbedding().get_repr(torch.as_tensor(X), torch.as_tensor(W5, device="cuda"))
     want = np.maximum(X.astype(np.float64) @ cpu(tr[1]) + cpu(tr[2]), 0) @ W5
     close(cpu(emb), want, name="relu repr")
+
+
+# ------------------------------------------------------------------------------- edge cases
+
+
+def test_edge_cases_empty_and_degenerate_inputs():
+    E, I, L, eng, FM, SI, MF = _mods()
+    rng = np.random.default_rng(0)
+    # (1) no interactions at all: a step is a no-op on the weights (all gradients are exactly zero => Adam moves nothing)
+    n_u, n_i, r = 9, 11, 4
+    U0 = rng.standard_normal((n_u, r)).astype(np.float32); V0 = rng.standard_normal((n_i, r)).astype(np.float32)
+    for loss, S in (("mse", 1), ("wmrb", 3)):
+        samp = np.stack([rng.choice(n_i, S, replace=False) for _ in range(n_u)]).astype(np.int64)
+        m = build_model(loss, ("linear", "linear"), {"W": U0}, {"W": V0}, r, n_u, n_i, S, samp)
+        plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.zeros((0, 2), np.int64), np.zeros(0, np.float32), (n_u, n_i)))
+        plan.step(0.1)
+        assert np.array_equal(cpu(plan.u.W)[:, :r], U0) and np.array_equal(cpu(plan.i.W)[:, :r], V0)
+        assert plan.ip.loss_vector().numel() == 0
+    # (2) WMRB where one user has only non-positive interactions and another has none
+    rows = np.array([0, 0, 1, 3, 3]); cols = np.array([1, 4, 2, 0, 5]); vals = np.array([2.0, 1.0, -3.0, 5.0, -1.0], np.float32)
+    S = 4
+    samp = np.stack([rng.choice(n_i, S, replace=False) for _ in range(n_u)]).astype(np.int64)
+    m = build_model("wmrb", ("linear", "linear"), {"W": U0}, {"W": V0}, r, n_u, n_i, S, samp)
+    plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)))
+    plan.forward_backward()
+    want = oracle64("wmrb", np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32), ("linear", "linear"), {"W": U0}, {"W": V0},
+                    rows, cols, vals, samp, n_i, S, 0.1)
+    close(cpu(plan.ip.loss_vector()), want[0], name="loss")
+    close(cpu(plan.u.grads["W"])[:, :r], want[1]["W"], name="dU")
+    assert np.all(cpu(plan.u.grads["W"])[1] == 0) and np.all(cpu(plan.u.grads["W"])[2] == 0)  # user 1: only a negative; user 2: nothing
+    # (3) rank-1 model, a single sample, one interaction
+    m = build_model("wmrb", ("linear", "linear"), {"W": U0[:, :1].copy()}, {"W": V0[:, :1].copy()}, 1, n_u, n_i, 1, samp[:, :1].copy())
+    plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.array([[2, 3]]), np.array([1.0], np.float32), (n_u, n_i)))
+    plan.forward_backward()
+    want = oracle64("wmrb", np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32), ("linear", "linear"), {"W": U0[:, :1]},
+                    {"W": V0[:, :1]}, np.array([2]), np.array([3]), np.array([1.0], np.float32), samp[:, :1], n_i, 1, 0.1)
+    close(cpu(plan.ip.loss_vector()), want[0], name="loss r=1")
+    close(cpu(plan.i.grads["W"])[:, :1], want[2]["W"], name="dV r=1")
+    # (4) argument validation mirrors numpy / the reference's failure modes
+    from teamoflow_b200.mf.utils import random_sampler
+    with pytest.raises(ValueError):
+        random_sampler(5, 3, 6)  # n_samples > n_items without replacement
+    with pytest.raises(ValueError):
+        MF(3, loss_graph=L.WMRBLoss()).fit(1, torch.eye(4), torch.eye(5), SI(np.array([[0, 1]]), np.array([1.0], np.float32), (4, 5)))
+    with pytest.raises(TypeError):
+        MF(3, loss_graph=object()).fit(1, torch.eye(4), torch.eye(5), SI(np.array([[0, 1]]), np.array([1.0], np.float32), (4, 5)))
