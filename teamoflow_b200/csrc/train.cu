@@ -55,6 +55,15 @@ __device__ __forceinline__ float dotv(const float4 (&a)[VPL], const float4 (&b)[
 
 constexpr int kUserPassThreads = 256;
 
+// full-warp shuffles (constant mask, sub-warp width): every loop below is warp-uniform so that no variable-mask
+// convergence checks (MATCH/REDUX/BRA.DIV, ~6 instructions per shuffle group) are generated
+template <int LPR>
+__device__ __forceinline__ float gsum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LPR);
+  return v;
+}
+
 // JPL > 0 : each lane keeps JPL sample scores and JPL partial G sums in registers (S <= LPR*JPL)
 // JPL == 0: MSE (no samples)
 // JPL < 0 : generic WMRB, per-group G partials in shared memory
@@ -69,7 +78,6 @@ user_pass_kernel(const UserPassParams p) {
   const int tid = threadIdx.x;
   const int g = tid / LPR;
   const int lg = tid % LPR;
-  const unsigned gm = group_mask<LPR>();
   const int ld = p.ld;
   const int nv = ld >> 2;
   const int S = p.n_samples;
@@ -102,17 +110,19 @@ user_pass_kernel(const UserPassParams p) {
     float gj[JR];
     if constexpr (LOSS == TMF_LOSS_WMRB) {
       const int* su = p.samp + (long long)u * S;
-      for (int j0 = g * 4; j0 < S; j0 += NG * 4) {  // 4 independent row gathers in flight per group
-        int it[4];
+      const int n_sit = (S + NG * 4 - 1) / (NG * 4);
+      for (int it = 0; it < n_sit; ++it) {  // 4 independent row gathers in flight per group; warp-uniform trip count
+        const int j0 = (it * NG + g) * 4;
+        int idx[4];
         float4 row[4][VPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) it[q] = (j0 + q < S) ? su[j0 + q] : 0;
+        for (int q = 0; q < 4; ++q) idx[q] = (j0 + q < S) ? su[j0 + q] : 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) load_row<LPR, VPL>(p.Ei, it[q], ld, nv, lg, row[q]);
+        for (int q = 0; q < 4; ++q) load_row<LPR, VPL>(p.Ei, idx[q], ld, nv, lg, row[q]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q;
-          const float s = group_sum<LPR>(dotv<VPL>(eu, row[q]), gm);
+          const float s = gsum<LPR>(dotv<VPL>(eu, row[q]));
           if (j < S) {
             if (lg == 0) sS[j] = s;
             if (p.cache_rows) {
@@ -143,79 +153,99 @@ user_pass_kernel(const UserPassParams p) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- interactions of this user, strided over the NG row groups, next row prefetched
+    // ---- interactions of this user, strided over the NG row groups; warp-uniform trip count, next row prefetched.
+    // Each lane parks the (loss argument, coefficient) of ONE of every LPR consecutive iterations, so the ~30-instruction
+    // logf and the two stores run once per LPR interactions instead of once per interaction.
+    const int n_it = (b - a + NG - 1) / NG;
     int k = a + g;
     float4 row_n[VPL];
     float v_n = 0.f;
-    if (k < b) {
-      v_n = p.val[k];
-      load_row<LPR, VPL>(p.Ei, p.col_idx[k], ld, nv, lg, row_n);
+    {
+      const int kc = min(k, b - 1);
+      v_n = (k < b) ? p.val[kc] : 0.f;
+      load_row<LPR, VPL>(p.Ei, p.col_idx[kc], ld, nv, lg, row_n);
     }
-    for (; k < b; k += NG) {
+    float keep_d = 1.0f, keep_c = 0.f;  // parked: 1 + m (0 when the interaction carries no WMRB loss) and c
+    int keep_k = -1;
+    for (int it = 0; it < n_it; ++it, k += NG) {
       float4 row[VPL];
 #pragma unroll
       for (int v = 0; v < VPL; ++v) row[v] = row_n[v];
       const float a_k = v_n;
-      const int kn = k + NG;
-      if (kn < b) {
-        v_n = p.val[kn];
-        load_row<LPR, VPL>(p.Ei, p.col_idx[kn], ld, nv, lg, row_n);
+      const bool active = k < b;
+      {
+        const int kn = k + NG;
+        const int kc = min(kn, b - 1);
+        v_n = (kn < b) ? p.val[kc] : 0.f;
+        load_row<LPR, VPL>(p.Ei, p.col_idx[kc], ld, nv, lg, row_n);
       }
-      const float pk = group_sum<LPR>(dotv<VPL>(eu, row), gm);
-      float c = 0.f, l = 0.f;
+      const float pk = gsum<LPR>(dotv<VPL>(eu, row));
+      float c = 0.f, d = 0.f;
       if constexpr (LOSS == TMF_LOSS_MSE) {
-        const float d = a_k - pk;  // loss_graphs.py:52
-        l = d * d;
-        c = -2.0f * d;
+        const float df = a_k - pk;  // loss_graphs.py:52
+        d = df;
+        c = active ? -2.0f * df : 0.f;
       } else {
-        if (a_k > 0.f) {  // loss_graphs.py:74
-          const float base = __fsub_rn(1.0f, pk);
-          float sum = 0.f, cnt = 0.f;
-          if constexpr (JPL > 0) {
-            unsigned ind = 0;
+        const float base = __fsub_rn(1.0f, pk);
+        const bool pos = active && a_k > 0.f;  // loss_graphs.py:74
+        float sum = 0.f, cnt = 0.f;
+        if constexpr (JPL > 0) {
+          bool ind[JPL];
 #pragma unroll
-            for (int t = 0; t < JPL; ++t) {
-              const float h = __fadd_rn(base, sj[t]);   // (1 - p) + s, loss_graphs.py:84
-              sum += fmaxf(h, 0.f);                      // tf.maximum(h, 0)
-              ind |= (h >= 0.f) ? (1u << t) : 0u;        // its gradient goes to h when h >= 0
-            }
-            sum = group_sum<LPR>(sum, gm);
-            cnt = group_sum<LPR>((float)__popc(ind), gm);
-            const float m = p.scale * sum;                 // :86
-            const float d = __fadd_rn(1.0f, m);
-            l = logf(d);                                   // :88
-            const float w = __fdividef(p.scale, d);
-            c = -w * cnt;
+          for (int t = 0; t < JPL; ++t) {
+            const float h = __fadd_rn(base, sj[t]);   // (1 - p) + s, loss_graphs.py:84
+            sum += fmaxf(h, 0.f);                      // tf.maximum(h, 0)
+            ind[t] = h >= 0.f;                         // its gradient goes to h when h >= 0
+            cnt += ind[t] ? 1.f : 0.f;
+          }
+          sum = gsum<LPR>(sum);
+          cnt = gsum<LPR>(cnt);
+          const float m = p.scale * sum;                 // :86
+          d = __fadd_rn(1.0f, m);
+          const float w = pos ? __fdividef(p.scale, d) : 0.f;
+          c = -w * cnt;
 #pragma unroll
-            for (int t = 0; t < JPL; ++t)
-              if (ind & (1u << t)) gj[t] += w;
-          } else {
-            for (int j = lg; j < S; j += LPR) {
-              const float h = __fadd_rn(base, sS[j]);
-              if (h >= 0.f) {
-                sum += h;
-                cnt += 1.f;
-              }
-            }
-            sum = group_sum<LPR>(sum, gm);
-            cnt = group_sum<LPR>(cnt, gm);
-            const float m = p.scale * sum;
-            l = logf(__fadd_rn(1.0f, m));
-            const float w = p.scale / __fadd_rn(1.0f, m);
-            c = -w * cnt;
+          for (int t = 0; t < JPL; ++t)
+            if (ind[t]) gj[t] += w;
+          if (!pos) d = 0.f;
+        } else {
+          for (int j = lg; j < S; j += LPR) {
+            const float h = __fadd_rn(base, sS[j]);
+            sum += fmaxf(h, 0.f);
+            cnt += (h >= 0.f) ? 1.f : 0.f;
+          }
+          sum = gsum<LPR>(sum);
+          cnt = gsum<LPR>(cnt);
+          const float m = p.scale * sum;
+          d = __fadd_rn(1.0f, m);
+          const float w = pos ? __fdividef(p.scale, d) : 0.f;
+          c = -w * cnt;
+          if (pos) {
             for (int j = lg; j < S; j += LPR) {
               const float h = __fadd_rn(base, sS[j]);
               if (h >= 0.f) sG[g * p.s_pad + j] += w;
             }
           }
+          if (!pos) d = 0.f;
         }
-      }
-      if (lg == 0) {
-        p.loss_out[k] = l;
-        p.coef_out[k] = c;
       }
 #pragma unroll
       for (int v = 0; v < VPL; ++v) fma4(acc[v], c, row[v]);
+      if ((it & (LPR - 1)) == lg) {
+        keep_d = d;
+        keep_c = c;
+        keep_k = active ? k : -1;
+      }
+      if ((it & (LPR - 1)) == LPR - 1 || it == n_it - 1) {  // warp-uniform: flush the parked results
+        if (keep_k >= 0) {
+          float l;
+          if constexpr (LOSS == TMF_LOSS_MSE) l = keep_d * keep_d;
+          else l = keep_d > 0.f ? logf(keep_d) : 0.f;   // log(1 + m), :88
+          p.loss_out[keep_k] = l;
+          p.coef_out[keep_k] = keep_c;
+        }
+        keep_k = -1;
+      }
     }
 
     if constexpr (LOSS == TMF_LOSS_WMRB) {
