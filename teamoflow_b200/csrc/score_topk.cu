@@ -321,11 +321,18 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int 
     return;
   }
   const float thr = st.thr;  // invalid rows carry thr = +inf
-  if (!__any_sync(0xffffffffu, mx >= thr)) return;
+  // four independent group votes issued back to back (a vote -> branch -> vote chain costs ~30 cycles per link, and
+  // the two epilogue warps of a sub-partition are latency-bound)
+  const bool gh0 = m8[0] >= thr, gh1 = m8[1] >= thr, gh2 = m8[2] >= thr, gh3 = m8[3] >= thr;
+  const bool a0 = __any_sync(0xffffffffu, gh0), a1 = __any_sync(0xffffffffu, gh1);
+  const bool a2 = __any_sync(0xffffffffu, gh2), a3 = __any_sync(0xffffffffu, gh3);
+  if (!(a0 || a1 || a2 || a3)) return;
+  (void)mx;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const bool gh = m8[g] >= thr;
-    if (__any_sync(0xffffffffu, gh)) {
+    const bool gh = g == 0 ? gh0 : (g == 1 ? gh1 : (g == 2 ? gh2 : gh3));
+    const bool ag = g == 0 ? a0 : (g == 1 ? a1 : (g == 2 ? a2 : a3));
+    if (ag) {
       if (__any_sync(0xffffffffu, gh && st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
       if (gh) {
 #pragma unroll
