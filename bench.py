@@ -281,6 +281,32 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         if s >= warmup:
             times.append(float(ms))
     launches = (_abi.launch_count - l0) // (warmup + steps)
+    # the alternative decomposition (users sharded, items replicated: no merge), reported beside the item-sharded one
+    user_sharded = None
+    if world > 1:
+        ub = tdist.shard_bounds(n_u, world)
+        n_loc = ub[1] - ub[0]  # equal slices (the bench sizes divide evenly; a short last slice is padded)
+        Uloc = new_storage(n_loc, r)
+        Uloc[:ub[rank + 1] - ub[rank]] = U[ub[rank]:ub[rank + 1]]
+        gv = torch.Generator(device=dev); gv.manual_seed(30000)
+        Vfull = new_storage(n_i, r); Vfull[:, :r] = torch.randn(n_i, r, generator=gv, device=dev) / math.sqrt(r)
+        ts = []
+        for s in range(warmup + steps):
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tdist.user_sharded_topk(Uloc, Vfull, r, k, False)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_u = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            torch.distributed.all_reduce(ms_u, op=torch.distributed.ReduceOp.MAX)
+            if s >= warmup:
+                ts.append(float(ms_u))
+        ms_us = float(np.mean(ts))
+        user_sharded = {"ms_per_step": ms_us, "value": float(n_u) * float(n_i) / (ms_us * 1e-3), "unit": "pairs/s",
+                        "note": "users sharded, items replicated on every GPU, result all-gathered; no merge needed"}
+        del Uloc, Vfull
     # spot-check exactness of a few rows against the fp64 canonical definition (single GPU only)
     ok = None
     if world == 1:
@@ -306,7 +332,7 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
                          "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": None},
             "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
                     "d2h_bytes_per_step": out.numel() * 4},
-            "gpu_launches": launches, "spot_check_exact": ok}
+            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded}
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
@@ -359,7 +385,16 @@ def cpu_reference_step(wl_name, budget_s=20.0, n_sub=None):
 # ------------------------------------------------------------------------------------------- main
 
 
+def _claim_stdout():
+    """Everything except the final JSON line goes to stderr: NCCL (and others) print banners on fd 1."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -382,12 +417,12 @@ def main():
         if rank != 0:
             return
         val, desc, cores = cpu_reference_step(args.workload, budget_s=max(20.0, 8.0 * args.steps))
-        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
+        print(file=out_stream, flush=True, *[json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": w["desc"], "sample": desc},
                           "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port", "sample": desc},
-                          "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
@@ -404,7 +439,7 @@ def main():
         tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
         res = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak)
         if rank == 0:
-            print(json.dumps(res))
+            print(json.dumps(res), file=out_stream, flush=True)
         return
 
     wl = Workload(args.workload, rank, world)
@@ -500,7 +535,7 @@ def main():
         except Exception as e:
             out["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

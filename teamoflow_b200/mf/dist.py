@@ -138,3 +138,20 @@ def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None):
     out_s = torch.empty(n_u, k, dtype=torch.float32, device=idx.device)
     _abi.call("tmf_topk_merge", _abi.ptr(all_idx), _abi.ptr(all_sc), world, n_u, k, _abi.ptr(out_i), _abi.ptr(out_s))
     return out_i, out_s
+
+
+def user_sharded_topk(U_local, V, r, k, clamp, group=None, gather=True):
+    """Alternative to ``sharded_topk``: users are sharded, every rank holds all items.  No merge is needed (a
+    row's top-k is computed entirely on one rank); with ``gather`` the ``[n_users, k]`` result is assembled on
+    every rank by one all-gather (ranks must hold equally sized user slices, the last one may be padded)."""
+    from .matrix_factorization import score_topk
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    idx, sc = score_topk(U_local, V, r, min(k, V.shape[0]), clamp, 0)
+    if world == 1 or not gather:
+        return idx, sc
+    n_loc = idx.shape[0]
+    all_idx = torch.empty(world * n_loc, idx.shape[1], dtype=torch.int32, device=idx.device)
+    all_sc = torch.empty(world * n_loc, idx.shape[1], dtype=torch.float32, device=idx.device)
+    dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_sc, sc.contiguous(), group=group)
+    return all_idx, all_sc
