@@ -61,7 +61,7 @@ def _ref_signatures(path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
-@pytest.mark.parametrize("module", ["matrix_factorization", "loss_graphs", "embedding_graphs", "initializer_graphs",
+@pytest.mark.parametrize("module", ["matrix_factorization", "loss_graphs", "embedding_graphs", "initializer_graphs", "input_utils",
                                     "predict_graphs", "utils"])
 def test_plugin_surface_matches_reference(module):
     import importlib
