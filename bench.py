@@ -484,6 +484,10 @@ def main():
     kernel_of = {"user_pass": "user_pass_kernel", "item_pass": "spmm_seg_kernel (item-major)", "embed_fwd": "spmm_seg_kernel (X.W)",
                  "embed_bwd": "spmm_seg_kernel (X^T.dE)", "adam": "adam1_kernel"}
     step_gbs = wl.bytes["total"] / (ms_step * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (C3 only)
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.workload == "c3" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(kernel_of[dom])
 
     # ---- end to end through the plugin API from pinned host buffers (one fit call of K epochs)
     e2e = None
@@ -515,7 +519,7 @@ def main():
                           (wl.nnz * 28 + w["n_u"] * max(w["S"], 1) * 16) / 1e9),
                       "loss_after": loss_now},
            "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                        "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                         "alg_bytes_per_launch": phase_bytes[dom], "ms_per_launch": phases[dom]},
            "step_roofline": {"alg_bytes_per_step": wl.bytes["total"], "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": step_gbs / hbm_peak},
