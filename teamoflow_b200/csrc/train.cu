@@ -27,7 +27,13 @@ struct UserPassParams {
   const float* Eu;
   const float* Ei;
   const int* samp;
-  const int* order;
+  const int* work_user;   // optional work list: (user, [a, b) slice of its interactions, partial slot or -1)
+  const int* work_a;
+  const int* work_b;
+  const int* work_slot;
+  int n_work;
+  float* part_G;          // [n_slots][s_pad] partial G of split users
+  float* part_E;          // [n_slots][ld]    partial dE_u of split users (without the sample term)
   int* counter;
   float* loss_out;
   float* coef_out;
@@ -90,11 +96,14 @@ user_pass_kernel(const UserPassParams p) {
     __syncthreads();
     if (tid == 0) s_next = atomicAdd(p.counter, 1);
     __syncthreads();
-    const int t_user = s_next;
-    if (t_user >= p.n_users) break;
-    const int u = p.order ? p.order[t_user] : t_user;
-    const int a = p.row_ptr[u];
-    const int b = p.row_ptr[u + 1];
+    const int t_work = s_next;
+    if (t_work >= p.n_work) break;
+    // a work item is a whole user or, for very heavy users, one slice of its interactions (load balance: a user
+    // with millions of interactions would otherwise be one CTA's serial tail)
+    const int u = p.work_user ? p.work_user[t_work] : t_work;
+    const int a = p.work_user ? p.work_a[t_work] : p.row_ptr[u];
+    const int b = p.work_user ? p.work_b[t_work] : p.row_ptr[u + 1];
+    const int slot = p.work_user ? p.work_slot[t_work] : -1;
 
     if (a == b) {  // no interactions: all gradients of this user are zero
       if (LOSS == TMF_LOSS_WMRB)
@@ -260,13 +269,14 @@ user_pass_kernel(const UserPassParams p) {
       for (int j = tid; j < S; j += NT) {  // fixed group order => deterministic
         float G = sG[j];
         for (int gg = 1; gg < NG; ++gg) G += sG[gg * p.s_pad + j];
-        p.coef_out[p.nnz + (long long)u * S + j] = G;
+        if (slot < 0) p.coef_out[p.nnz + (long long)u * S + j] = G;
+        else p.part_G[(long long)slot * p.s_pad + j] = G;   // summed over the user's slices by the fix-up kernel
         sS[j] = G;
       }
       __syncthreads();
       const int* su = p.samp + (long long)u * S;
 #pragma unroll 4
-      for (int j = g; j < S; j += NG) {
+      for (int j = (slot < 0 ? g : S); j < S; j += NG) {  // split users: the sample term is added once, in the fix-up
         const float G = sS[j];
         float4 row[VPL];
         if (p.cache_rows) {
@@ -294,7 +304,45 @@ user_pass_kernel(const UserPassParams p) {
     for (int c = tid; c < ld; c += NT) {
       float s = sAcc[c];
       for (int gg = 1; gg < NG; ++gg) s += sAcc[gg * ld + c];
-      p.dEu[(long long)u * ld + c] = s;
+      if (slot < 0) p.dEu[(long long)u * ld + c] = s;
+      else p.part_E[(long long)slot * ld + c] = s;
+    }
+  }
+}
+
+// One CTA per split user: G = sum of the slices' partial G (slice order), dE_u = sum of the slices' partial dE_u
+// (slice order) + sum_j G_j * E_i[J_uj].  Fixed association order => deterministic.
+__global__ void __launch_bounds__(256) user_fixup_kernel(const UserPassParams p, int loss, int n_split, const int* __restrict__ split_user,
+                                                         const int* __restrict__ split_first, const int* __restrict__ split_nseg) {
+  extern __shared__ __align__(16) float fsm[];
+  float* sG = fsm;            // [s_pad]
+  float* sE = sG + p.s_pad;   // [ld]
+  const int tid = threadIdx.x;
+  for (int w = blockIdx.x; w < n_split; w += gridDim.x) {
+    const int u = split_user[w], first = split_first[w], nseg = split_nseg[w];
+    const int S = p.n_samples;
+    __syncthreads();
+    if (loss == TMF_LOSS_WMRB) {
+      for (int j = tid; j < S; j += 256) {
+        float G = 0.f;
+        for (int sg = 0; sg < nseg; ++sg) G += p.part_G[(long long)(first + sg) * p.s_pad + j];
+        p.coef_out[p.nnz + (long long)u * S + j] = G;
+        sG[j] = G;
+      }
+    }
+    for (int c = tid; c < p.ld; c += 256) {
+      float s = 0.f;
+      for (int sg = 0; sg < nseg; ++sg) s += p.part_E[(long long)(first + sg) * p.ld + c];
+      sE[c] = s;
+    }
+    __syncthreads();
+    for (int c = tid; c < p.ld; c += 256) {
+      float s = sE[c];
+      if (loss == TMF_LOSS_WMRB) {
+        const int* su = p.samp + (long long)u * S;
+        for (int j = 0; j < S; ++j) s = fmaf(sG[j], p.Ei[(long long)su[j] * p.ld + c], s);
+      }
+      p.dEu[(long long)u * p.ld + c] = s;
     }
   }
 }
@@ -315,7 +363,7 @@ static int launch_user_pass(const UserPassParams& p, cudaStream_t st) {
   TMF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kUserPassThreads, smem));
   if (occ < 1) occ = 1;
   long long grid = (long long)kNumSMs * occ;
-  if (grid > p.n_users) grid = p.n_users;
+  if (grid > p.n_work) grid = p.n_work;
   TMF_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(int), st));
   kern<<<(unsigned)grid, kUserPassThreads, smem, st>>>(q);
   TMF_LAUNCH_CHECK();
@@ -731,8 +779,9 @@ using namespace tmf;
 
 extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int64_t nnz, const int32_t* row_ptr, const int32_t* col_idx,
                              const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
-                             const int32_t* samp, int32_t n_samples, const int32_t* order, int32_t* counter,
-                             float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream) {
+                             const int32_t* samp, int32_t n_samples, int32_t n_work, const int32_t* work_user,
+                             const int32_t* work_a, const int32_t* work_b, const int32_t* work_slot, float* part_G,
+                             float* part_E, int32_t* counter, float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream) {
   TMF_REQUIRE(loss == TMF_LOSS_MSE || loss == TMF_LOSS_WMRB, "tmf_user_pass: unknown loss %d", loss);
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && ld > 0 && ld % 4 == 0 && n_comp <= ld, "tmf_user_pass: bad shape");
   TMF_REQUIRE(ld <= 256, "tmf_user_pass: n_components up to 256 supported (ld=%d)", ld);
@@ -744,7 +793,10 @@ extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int
   p.n_users = n_users; p.n_items = n_items; p.ld = ld; p.n_comp = n_comp;
   p.n_samples = loss == TMF_LOSS_WMRB ? n_samples : 0;
   p.s_pad = (p.n_samples + 3) & ~3;
-  p.row_ptr = row_ptr; p.col_idx = col_idx; p.val = val; p.Eu = Eu; p.Ei = Ei; p.samp = samp; p.order = order;
+  p.row_ptr = row_ptr; p.col_idx = col_idx; p.val = val; p.Eu = Eu; p.Ei = Ei; p.samp = samp;
+  p.work_user = work_user; p.work_a = work_a; p.work_b = work_b; p.work_slot = work_slot; p.part_G = part_G; p.part_E = part_E;
+  p.n_work = work_user ? n_work : n_users;
+  TMF_REQUIRE(!work_user || (work_a && work_b && work_slot), "tmf_user_pass: incomplete work list");
   p.counter = counter; p.loss_out = loss_out; p.coef_out = coef_out; p.dEu = dEu;
   p.scale = loss == TMF_LOSS_WMRB ? (float)((double)n_items / (double)n_samples) : 0.f;
   cudaStream_t st = as_stream(stream);
@@ -912,6 +964,23 @@ extern "C" int tmf_wmrb_forward(int64_t n_pos, const int32_t* pos_rows, const fl
   if (n_pos == 0) return TMF_OK;
   wmrb_forward_kernel<<<(unsigned)cdiv(n_pos * 32, 256), 256, 0, as_stream(stream)>>>(n_pos, pos_rows, pos_pred, sample_pred,
                                                                                    n_samples, scale, loss_out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_user_pass_fixup(int32_t loss, int32_t n_split, const int32_t* split_user, const int32_t* split_first,
+                                   const int32_t* split_nseg, const float* Ei, int32_t ld, const int32_t* samp, int32_t n_samples,
+                                   int64_t nnz, const float* part_G, const float* part_E, float* coef_out, float* dEu,
+                                   tmf_stream_t stream) {
+  if (n_split == 0) return TMF_OK;
+  TMF_REQUIRE(split_user && split_first && split_nseg && part_E && dEu, "tmf_user_pass_fixup: null pointer");
+  UserPassParams p{};
+  p.ld = ld; p.n_samples = loss == TMF_LOSS_WMRB ? n_samples : 0; p.s_pad = (p.n_samples + 3) & ~3; p.nnz = nnz;
+  p.Ei = Ei; p.samp = samp; p.part_G = const_cast<float*>(part_G); p.part_E = const_cast<float*>(part_E);
+  p.coef_out = coef_out; p.dEu = dEu;
+  const size_t smem = (size_t)(p.s_pad + ld) * sizeof(float);
+  TMF_REQUIRE(smem <= 48 * 1024, "tmf_user_pass_fixup: n_samples too large");
+  user_fixup_kernel<<<std::min(n_split, 148 * 4), 256, smem, as_stream(stream)>>>(p, loss, n_split, split_user, split_first, split_nseg);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }

@@ -209,8 +209,7 @@ class InteractionPlan:
         self.t_user = torch.empty(max(self.T, 1), dtype=torch.int32, device=dev)
         _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
                   _abi.ptr(self.t_user))
-        lens = (self.row_ptr[1:] - self.row_ptr[:-1])
-        self.order = torch.argsort(lens, descending=True, stable=True).to(torch.int32).contiguous()
+        self._build_work_list()
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.coef = torch.zeros(max(self.nnz + self.n_users * self.S, 1), dtype=torch.float32, device=dev)
         self.loss_k = torch.zeros(max(self.nnz, 1), dtype=torch.float32, device=dev)
@@ -221,13 +220,54 @@ class InteractionPlan:
         self.spmm_ws = None
         self.n_pos = int((self.vals > 0).sum()) if loss == WMRB else self.nnz
 
+    # users with more interactions than this are processed as several slices (load balance, tmf_user_pass)
+    SPLIT = 4096
+
+    def _build_work_list(self):
+        """Work items of the user pass: whole users, or SPLIT-sized slices of very heavy users, heaviest first."""
+        dev = self.vals.device
+        rp = self.row_ptr.to(torch.int64)
+        lens = rp[1:] - rp[:-1]
+        nseg = torch.clamp((lens + self.SPLIT - 1) // self.SPLIT, min=1)
+        first_seg = torch.cumsum(nseg, 0) - nseg
+        w_user = torch.repeat_interleave(torch.arange(self.n_users, device=dev), nseg)
+        seg = torch.arange(w_user.numel(), device=dev) - first_seg[w_user]
+        w_a = rp[w_user] + seg * self.SPLIT
+        w_b = torch.minimum(w_a + self.SPLIT, rp[w_user + 1])
+        split = nseg[w_user] > 1
+        slot = torch.cumsum(split.to(torch.int64), 0) - 1
+        w_slot = torch.where(split, slot, torch.full_like(slot, -1))
+        order = torch.argsort(w_b - w_a, descending=True, stable=True)
+        i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
+        self.n_work = int(w_user.numel())
+        self.w_user, self.w_a, self.w_b, self.w_slot = i32(w_user[order]), i32(w_a[order]), i32(w_b[order]), i32(w_slot[order])
+        su = torch.nonzero(nseg > 1).reshape(-1)
+        self.n_split = int(su.numel())
+        self.n_slots = int(split.sum())
+        self.split_user = i32(su)
+        self.split_first = i32(slot[first_seg[su]]) if self.n_split else i32(su)
+        self.split_nseg = i32(nseg[su])
+        self.part_G = self.part_E = None
+
+    def _partials(self, ld):
+        if self.n_slots and (self.part_E is None or self.part_E.shape[1] != ld):
+            dev = self.vals.device
+            self.part_E = torch.zeros(self.n_slots, ld, dtype=torch.float32, device=dev)
+            self.part_G = torch.zeros(self.n_slots, max((self.S + 3) // 4 * 4, 4), dtype=torch.float32, device=dev)
+
     def user_pass(self, Eu, Ei, r, dEu):
         """scores + loss + coefficients + dE_u."""
         if self.loss in (MSE, WMRB):
+            self._partials(Eu.shape[1])
             _abi.call("tmf_user_pass", _LOSS_CODE[self.loss], self.n_users, self.n_items, self.nnz,
                       _abi.ptr(self.row_ptr), _abi.ptr(self.col_idx), _abi.ptr(self.vals), _abi.ptr(Eu), _abi.ptr(Ei),
-                      Eu.shape[1], r, _abi.ptr(self.samp), self.S, _abi.ptr(self.order), _abi.ptr(self.counter),
-                      _abi.ptr(self.loss_k), _abi.ptr(self.coef), _abi.ptr(dEu))
+                      Eu.shape[1], r, _abi.ptr(self.samp), self.S, self.n_work, _abi.ptr(self.w_user), _abi.ptr(self.w_a),
+                      _abi.ptr(self.w_b), _abi.ptr(self.w_slot), _abi.ptr(self.part_G), _abi.ptr(self.part_E),
+                      _abi.ptr(self.counter), _abi.ptr(self.loss_k), _abi.ptr(self.coef), _abi.ptr(dEu))
+            if self.n_split:
+                _abi.call("tmf_user_pass_fixup", _LOSS_CODE[self.loss], self.n_split, _abi.ptr(self.split_user),
+                          _abi.ptr(self.split_first), _abi.ptr(self.split_nseg), _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.samp),
+                          self.S, self.nnz, _abi.ptr(self.part_G), _abi.ptr(self.part_E), _abi.ptr(self.coef), _abi.ptr(dEu))
         else:
             _abi.call("tmf_pair_dots", self.nnz, _abi.ptr(self.coo_rows), _abi.ptr(self.col_idx), _abi.ptr(Eu),
                       _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.p))

@@ -441,3 +441,30 @@ def test_edge_cases_empty_and_degenerate_inputs():
         MF(3, loss_graph=L.WMRBLoss()).fit(1, torch.eye(4), torch.eye(5), SI(np.array([[0, 1]]), np.array([1.0], np.float32), (4, 5)))
     with pytest.raises(TypeError):
         MF(3, loss_graph=object()).fit(1, torch.eye(4), torch.eye(5), SI(np.array([[0, 1]]), np.array([1.0], np.float32), (4, 5)))
+
+
+def test_heavy_users_are_split_and_still_deterministic_and_exact():
+    """users above InteractionPlan.SPLIT interactions are processed as several slices + a fix-up; results must not change"""
+    E, I, L, eng, FM, SI, MF = _mods()
+    n_u, n_i, r, S = 6, 9000, 16, 20
+    rng = np.random.default_rng(21)
+    lens = [8999, 5000, 4097, 4096, 3, 0]
+    rows = np.concatenate([np.full(n, u) for u, n in enumerate(lens)])
+    cols = np.concatenate([np.sort(rng.choice(n_i, n, replace=False)) for n in lens]).astype(np.int64)
+    vals = rng.choice(np.array([1.0, 2.0, -1.0], np.float32), rows.size)
+    samp = np.stack([rng.choice(n_i, S, replace=False) for _ in range(n_u)]).astype(np.int64)
+    pu = {"W": (rng.standard_normal((n_u, r)) * 0.2).astype(np.float32)}
+    pi = {"W": (rng.standard_normal((n_i, r)) * 0.2).astype(np.float32)}
+    for loss in ("wmrb", "mse"):
+        m = build_model(loss, ("linear", "linear"), pu, pi, r, n_u, n_i, S, samp)
+        plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)))
+        assert plan.ip.n_split == 3 and plan.ip.n_slots == 3 + 2 + 2
+        plan.forward_backward()
+        want = oracle64(loss, np.eye(n_u, dtype=np.float32), sparse.eye(n_i, dtype=np.float32, format="csr"), ("linear", "linear"),
+                        pu, pi, rows, cols, vals, samp, n_i, S, 0.1)
+        close(cpu(plan.ip.loss_vector()), want[0], name="loss")
+        close(cpu(plan.u.grads["W"])[:, :r], want[1]["W"], name="dU")
+        close(cpu(plan.i.grads["W"])[:, :r], want[2]["W"], name="dV")
+        g1 = plan.u.grads["W"].clone()
+        plan.forward_backward()
+        assert torch.equal(g1, plan.u.grads["W"])
