@@ -240,40 +240,45 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
   return keep_threshold(edge - slack, E, clamp);
 }
 
-// warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane)
+// warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane).  Iterations are
+// independent of each other -- fire-and-forget histogram increments (red.shared), list stores that nobody waits
+// for, threshold fixed for the duration -- so they pipeline; the threshold advances once at the end.
 __device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
   int maxq = st.cq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
-#pragma unroll 1
-  for (int s = 0; s < maxq; ++s) {
-    if (s < st.cq) {
-      const float2 e = lds_f2(queue + 8u * (uint32_t)s);
-      if (e.x >= st.thr) {  // the threshold may have risen since the entry was queued
-        if (st.cnt < CAP) __stcg(buf + st.cnt, e);
-        ++st.cnt;           // > CAP marks saturation
-        if (e.x >= st.lo) {
-          const int b = (int)fminf((e.x - st.lo) * st.inv_w, (float)(NBINS - 1));
-          const uint32_t wa = hrow + 4u * (uint32_t)(b >> 1);
-          sts_u32(wa, lds_u32(wa) + (1u << ((b & 1) * 16)));
-          if (b >= st.bthr) {
-            ++st.A;
-            bool moved = false;
-            while (st.bthr < NBINS - 1) {
-              const int hb = hist_get_s(hrow, st.bthr);
-              if (st.A - hb < k) break;
-              st.A -= hb;
-              ++st.bthr;
-              moved = true;
-            }
-            if (moved) st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, clamp);
-          }
-        }
-      }
-    }
+  const float thr = st.thr, lo = st.lo, inv_w = st.inv_w;
+  const int bthr = st.bthr;
+#pragma unroll 4
+  for (int s = 0; s < maxq; ++s) {  // branch-free body: nested divergent ifs cost a single warp ~100 cycles each
+    const float2 e = lds_f2(queue + 8u * (uint32_t)s);  // slots >= cq hold stale but readable data
+    const bool ok = (s < st.cq) && (e.x >= thr);
+    const bool okh = ok && (e.x >= lo);
+    const int b = (int)fminf(fmaxf((e.x - lo) * inv_w, 0.f), (float)(NBINS - 1));
+    const int st_ok = ok && (st.cnt < CAP);
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %0, 0;\n\t"
+        "setp.ne.s32 q, %1, 0;\n\t"
+        "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
+        "@q red.shared.add.u32 [%5], %6;\n\t}"
+        ::"r"(st_ok), "r"((int)okh), "l"(buf + st.cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)(b >> 1)),
+          "r"(1u << ((b & 1) * 16))
+        : "memory");
+    st.cnt += ok ? 1 : 0;  // > CAP marks saturation
+    st.A += (okh && b >= bthr) ? 1 : 0;
   }
   st.cq = 0;
   __syncwarp();
+  bool moved = false;
+  while (st.bthr < NBINS - 1) {
+    const int hb = hist_get_s(hrow, st.bthr);
+    if (st.A - hb < k) break;
+    st.A -= hb;
+    ++st.bthr;
+    moved = true;
+  }
+  if (moved) st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, clamp);
 }
 
 // Filter one 32-column slice of a row's accumulator against its running threshold.  The fast path is a
@@ -360,11 +365,21 @@ __device__ __noinline__ float warp_select_kth(const float2* buf, int n, int k, i
 #pragma unroll
     for (int i = 0; i < 8; ++i) radix[lane * 8 + i] = 0;
     __syncwarp();
-    for (int e = lane; e < n; e += 32) {
-      const float sc = __ldcg(&buf[e].x);
-      mx = fmaxf(mx, sc);
-      const uint32_t key = f2key(sc);
-      if ((key & mask) == prefix) smem_inc(&radix[(key >> shift) & 255u]);
+    for (int e0 = 0; e0 < n; e0 += 32 * 8) {  // 8 independent loads in flight per lane (one L2 round trip per 256 entries)
+      float sc[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int e = e0 + 32 * t + lane;
+        sc[t] = (e < n) ? __ldcg(&buf[e].x) : -INFINITY;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (e0 + 32 * t + lane < n) {
+          mx = fmaxf(mx, sc[t]);
+          const uint32_t key = f2key(sc[t]);
+          if ((key & mask) == prefix) smem_inc(&radix[(key >> shift) & 255u]);
+        }
+      }
     }
     __syncwarp();
     int c[8];
@@ -622,7 +637,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         long long t2 = clock64();
         w_work += t2 - t1;
         if (!DUMP) {
-          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) {
+            const long long td = clock64();
+            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+            if (p.prof && lane == 0) { atomicAdd(p.prof + 10, (unsigned long long)(clock64() - td)); atomicAdd(p.prof + 11, 1ull); }
+          }
           // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
           // the same tile because everything is appended until then), later whenever a list is about to saturate
           const bool first = !warp_inited && __any_sync(0xffffffffu, valid && st.cnt >= INIT_N - BN);
@@ -1095,8 +1114,8 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
     TMF_CUDA(cudaMemcpy(h, p.prof, 96, cudaMemcpyDeviceToHost));
     TMF_CUDA(cudaMemcpy(&novf, ovfc, 4, cudaMemcpyDeviceToHost));
     fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-sweep, n=%llu) "
-                    "wait tfull %.3g, work %.3g, init %.3g cycles | overflow rows %d (main %llu, rerank %llu)\n",
-            (double)h[0], (double)h[1], (double)h[2], (double)h[3], h[7], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], novf, h[8], h[9]);
+                    "wait tfull %.3g, work %.3g, init %.3g cycles | overflow rows %d (main %llu, rerank %llu) | tile-end drains: %llu, %.0f cycles each\n",
+            (double)h[0], (double)h[1], (double)h[2], (double)h[3], h[7], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], novf, h[8], h[9], h[11], h[11] ? (double)h[10] / h[11] : 0.0);
   }
   return TMF_OK;
 }
