@@ -314,6 +314,31 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         sc64 = (U[rows, :r].double() @ V[:, :r].double().T)
         want = torch.sort(sc64, dim=1, descending=True, stable=True).indices[:, :k].int()
         ok = bool((idx[rows] == want).float().mean() > 0.99)
+    # the recall_at_k path at the same scale (clamped scores, CSR interaction table; single GPU only)
+    recall = None
+    if world == 1:
+        try:
+            from teamoflow_b200.mf.matrix_factorization import MatrixFactorization
+            from teamoflow_b200.mf._tensors import SparseInteractions
+            mdl = MatrixFactorization(r)
+            mdl.user_embedding, mdl.item_embedding = U[:, :r], V[:, :r]
+            ga = torch.Generator(device=dev); ga.manual_seed(777)
+            npos = min(50 * n_u, 50_000_000)
+            keys = torch.unique(torch.randint(0, n_u * n_i, (npos,), generator=ga, device=dev, dtype=torch.int64))
+            A = SparseInteractions(torch.stack([keys // n_i, keys % n_i], 1), torch.ones(keys.numel(), device=dev), (n_u, n_i))
+            A.csr()
+            del keys
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rec = mdl.recall_at_k(A, k=k)
+            e1.record()
+            torch.cuda.synchronize()
+            recall = {"ms": e0.elapsed_time(e1), "recall_at_k_mean": float(rec.mean()), "positives": int(A.nnz),
+                      "note": "MatrixFactorization.recall_at_k(A, k): clamped fused top-k + CSR membership kernel"}
+            del A, mdl
+        except Exception as e:
+            recall = {"error": f"{type(e).__name__}: {e}"}
     ms = float(np.mean(times))
     pairs = float(n_u) * float(n_i)
     flops = 2.0 * pairs * r
@@ -332,7 +357,7 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
                          "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": None},
             "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
                     "d2h_bytes_per_step": out.numel() * 4},
-            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded}
+            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded, "recall_path": recall}
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
