@@ -49,14 +49,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// suspend-time hint: without it try_wait returns after ~30 cycles and the single-thread TMA / MMA waiters spin at full
+// issue rate (ncu: 550 M TRYWAITs per 17 ms), stealing issue slots from the epilogue warps of their SM sub-partition
+constexpr uint32_t kSuspendHintNs = 4000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }
@@ -96,6 +99,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_for8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait that also pins the loaded registers behind it (consumers cannot be scheduled above the wait)
@@ -281,10 +296,8 @@ __device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float
   if (moved) st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, clamp);
 }
 
-// Filter one 32-column slice of a row's accumulator against its running threshold.  The fast path is a
-// 3-input max tree (FMNMX3) and one compare; 8-column groups that contain a survivor are rescanned and the
-// survivors queued.  Before a row's threshold exists (first 3 tiles) every column is appended directly.
-// (Clamp-mode "filler" items -- the k <= 128 lowest ids -- therefore need no special case here.)
+// One 32-column slice of a row's accumulator BEFORE the row's threshold exists (first 3 tiles): every column is
+// appended directly.  (Clamp-mode "filler" items -- the k <= 128 lowest ids -- therefore need no special case.)
 template <bool DUMP>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int n_items, bool tail_tile, bool valid, bool warp_inited,
                                                RowState& st, uint32_t queue, float2* buf, uint32_t hrow, long long row,
@@ -311,8 +324,10 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int 
     }
     return;
   }
-  // (padded item columns of the last tile hold NaN scores -- see pack_bf16_kernel -- and never qualify)
-  float m8[4];
+}
+
+// 8-column group maxima of one 32-column slice (3-input max tree, no branches)
+__device__ __forceinline__ void group_max4(const uint32_t (&r)[32], float* m8) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float a = fmaxf(fmaxf(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
@@ -320,35 +335,56 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int 
     const float c = fmaxf(fmaxf(b, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
     m8[g] = fmaxf(c, __uint_as_float(r[8 * g + 7]));
   }
-  const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-  if (p.dbg == 1) {  // keep the max tree alive without ever appending
-    if (mx == 123456.0f) buf[0] = make_float2(mx, 0.f);
-    return;
-  }
-  const float thr = st.thr;  // invalid rows carry thr = +inf
-  // four independent group votes issued back to back (a vote -> branch -> vote chain costs ~30 cycles per link, and
-  // the two epilogue warps of a sub-partition are latency-bound)
-  const bool gh0 = m8[0] >= thr, gh1 = m8[1] >= thr, gh2 = m8[2] >= thr, gh3 = m8[3] >= thr;
-  const bool a0 = __any_sync(0xffffffffu, gh0), a1 = __any_sync(0xffffffffu, gh1);
-  const bool a2 = __any_sync(0xffffffffu, gh2), a3 = __any_sync(0xffffffffu, gh3);
-  if (!(a0 || a1 || a2 || a3)) return;
-  (void)mx;
+}
+
+// Steady-state filter of one 128-column accumulator tile (rows with a threshold).  Pass 1 streams the tile through
+// registers once and keeps only the 16 group maxima -- no votes, no branches, all four TMEM loads pipelined.  One
+// REDUX.OR of the per-lane hit masks then names the 8-column groups in which ANY row of the warp has a survivor
+// (about 3 of 16 per tile at 1M items); only those are re-read from TMEM (x8) and their survivors queued with
+// predicated stores, all lanes convergent.  (The previous slice-at-a-time version spent ~700 cycles per slice in
+// vote -> branch -> vote chains and divergent push blocks; two epilogue warps per sub-partition cannot hide that.)
+__device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
+                                              const TopkParams& p) {
+  uint32_t ra[32], rb[32];
+  float m8[4];
+  const float thr = st.thr;  // invalid rows carry thr = +inf; NaN-padded columns never win a max or a compare
+  unsigned hm = 0;
+  tmem_ld32(t_base, ra);
+  tmem_ld32(t_base + 32u, rb);
+  tmem_ld_wait_for(ra);   // (wait::ld covers both loads; the next pair is issued right behind)
+  group_max4(ra, m8);
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const bool gh = g == 0 ? gh0 : (g == 1 ? gh1 : (g == 2 ? gh2 : gh3));
-    const bool ag = g == 0 ? a0 : (g == 1 ? a1 : (g == 2 ? a2 : a3));
-    if (ag) {
-      if (__any_sync(0xffffffffu, gh && st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-      if (gh) {
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (1u << g) : 0u;
+  tmem_ld32(t_base + 64u, ra);
+  tmem_ld_wait_for(rb);
+  group_max4(rb, m8);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = __uint_as_float(r[8 * g + j]);
-          // predicated push onto the lane's queue (no branch: 8 sites per group stay convergent)
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
-                       ::"f"(v), "f"(thr), "r"(queue + 8u * (uint32_t)st.cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
-          st.cq += (v >= thr) ? 1 : 0;
-        }
-      }
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (16u << g) : 0u;
+  tmem_ld32(t_base + 96u, rb);
+  tmem_ld_wait_for(ra);
+  group_max4(ra, m8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (256u << g) : 0u;
+  tmem_ld_wait_for(rb);
+  group_max4(rb, m8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (4096u << g) : 0u;
+  unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
+  if (p.dbg == 1) gmask = 0;
+  const int id0 = p.item_offset + col0;
+  while (gmask) {  // warp-uniform
+    const int g = __ffs(gmask) - 1;
+    gmask &= gmask - 1;
+    uint32_t v[8];
+    tmem_ld8(t_base + (uint32_t)(8 * g), v);
+    if (__any_sync(0xffffffffu, st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+    tmem_ld_wait_for8(v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = __uint_as_float(v[j]);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
+                   ::"f"(x), "f"(thr), "r"(queue + 8u * (uint32_t)st.cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
+      st.cq += (x >= thr) ? 1 : 0;
     }
   }
 }
@@ -477,7 +513,7 @@ __device__ __noinline__ void warp_rebuild_row(float2* buf, int n, int k, int cla
 }
 
 // ------------------------------------------------------------------ the fused kernel
-template <bool DUMP>
+template <bool DUMP, bool PROF>
 __global__ void __launch_bounds__(TOPK_THREADS, 2)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -498,6 +534,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   float* init_out = reinterpret_cast<float*>(queues + BM * QCAP);  // [4 warps][8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto now = [] () -> long long { return PROF ? clock64() : 0ll; };  // cycle counters only in the profiling build
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapU) : "memory");
@@ -525,24 +562,24 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-        long long t0 = clock64();
+        long long t0 = now();
         mbar_wait(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
-        long long w_empty = 0, w_aempty = clock64() - t0;
+        long long w_empty = 0, w_aempty = now() - t0;
         mbar_expect_tx(smem_u32(a_full), p.kb * A_SUB_BYTES);
         for (int kb = 0; kb < p.kb; ++kb)
           tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
         a_phase ^= 1;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.kb; ++kb) {
-            t0 = clock64();
+            t0 = now();
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            w_empty += clock64() - t0;
+            w_empty += now() - t0;
             mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + stage * B_STAGE_BYTES), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
             if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
-        if (p.prof) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
+        if (PROF) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
       }
     }
   } else if (warp == 1) {
@@ -555,15 +592,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
-          long long t0 = clock64();
+          long long t0 = now();
           mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
-          w_tempty += clock64() - t0;
+          w_tempty += now() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
-            t0 = clock64();
+            t0 = now();
             mbar_wait(smem_u32(&full_bar[stage]), phase);
-            w_full += clock64() - t0;
+            w_full += now() - t0;
             tcgen05_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
             const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
@@ -580,7 +617,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           if (acc == 0) acc_phase ^= 1;
         }
         tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
-        if (p.prof) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
+        if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
   } else if (warp >= 4) {
@@ -607,16 +644,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       float2* buf = p.cand + lrow * CAP;
       long long w_tfull = 0, w_work = 0, w_init = 0;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
-        long long t0 = clock64();
+        long long t0 = now();
         mbar_wait(smem_u32(&tfull[acc]), acc_phase);
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
-        long long t1 = clock64();
+        long long t1 = now();
         w_tfull += t1 - t0;
         tcgen05_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
         const bool tail_tile = (nt + 1) * BN > n_items;
-        uint32_t ra[32], rb[32];
-        if (p.dbg < 3) {
+        if (!DUMP && warp_inited && p.dbg < 2) {
+          epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, p);
+        } else if (p.dbg < 3) {
+          uint32_t ra[32], rb[32];
           tmem_ld32(t_base, ra);
 #pragma unroll 1
           for (int ch = 0; ch < BN / 32; ch += 2) {
@@ -634,13 +673,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         mbar_arrive(smem_u32(&tempty[acc]));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
-        long long t2 = clock64();
+        long long t2 = now();
         w_work += t2 - t1;
         if (!DUMP) {
           if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) {
-            const long long td = clock64();
+            const long long td = now();
             drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-            if (p.prof && lane == 0) { atomicAdd(p.prof + 10, (unsigned long long)(clock64() - td)); atomicAdd(p.prof + 11, 1ull); }
+            if (PROF && lane == 0) { atomicAdd(p.prof + 10, (unsigned long long)(now() - td)); atomicAdd(p.prof + 11, 1ull); }
           }
           // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
           // the same tile because everything is appended until then), later whenever a list is about to saturate
@@ -672,10 +711,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           }
           if (first) warp_inited = true;
         }
-        w_init += clock64() - t2;
+        w_init += now() - t2;
       }
       if (!DUMP) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-      if (p.prof && lane == 0) {
+      if (PROF && lane == 0) {
         atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
         atomicAdd(p.prof + 6, (unsigned long long)w_init); atomicAdd(p.prof + 7, 1ull);
       }
@@ -683,7 +722,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       if (valid && ovf) {
         const int slot = atomicAdd(p.ovf_count, 1);
         p.ovf_rows[slot] = (int)row;
-        if (p.prof) atomicAdd(p.prof + 8, 1ull);
+        if (PROF) atomicAdd(p.prof + 8, 1ull);
       }
       p.cnt[lrow] = valid ? (ovf ? -1 : st.cnt) : 0;
       p.thr_out[lrow] = st.thr;
@@ -1085,8 +1124,9 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 +
                       (size_t)BM * HSTRIDE * sizeof(uint32_t) + 16 + (size_t)BM * QCAP * 8 + 4 * 8 * sizeof(float);
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8);
   TMF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
 
@@ -1096,8 +1136,9 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
     p.ub0 = ub0;
     p.n_ublocks = std::min(UB_BATCH, total_ublocks - ub0);
     const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
-    if (dump != nullptr) score_topk_kernel<true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
-    else score_topk_kernel<false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    if (dump != nullptr) score_topk_kernel<true, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    else if (p.prof) score_topk_kernel<false, true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    else score_topk_kernel<false, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
     TMF_LAUNCH_CHECK();
     if (dump != nullptr) continue;
     q.row0 = (long long)ub0 * BM;
