@@ -759,15 +759,77 @@ struct RerankParams {
   float* out_score;
 };
 
+// k-th largest of m (<= SEL_CAP) scores held in shared memory pairs (score, id): 8-bit radix select, one warp
+__device__ __forceinline__ float smem_select_kth(const float2* pr, int m, int k, int* radix) {
+  const int lane = threadIdx.x & 31;
+  uint32_t prefix = 0, mask = 0;
+  int krem = k;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) radix[lane * 8 + i] = 0;
+    __syncwarp();
+    for (int e = lane; e < m; e += 32) {
+      const uint32_t key = f2key(pr[e].x);
+      if ((key & mask) == prefix) smem_inc(&radix[(key >> shift) & 255u]);
+    }
+    __syncwarp();
+    int c[8];
+    int lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // lane L owns bins 255-8L .. 248-8L, visited in descending order
+      c[i] = radix[255 - 8 * lane - i];
+      lsum += c[i];
+    }
+    int incl = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= krem);
+    const int F = reach ? __ffs(reach) - 1 : 31;
+    int bin = 0, knew = 0;
+    if (lane == F) {
+      int cum = incl - lsum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cum + c[i] >= krem) { bin = 255 - 8 * lane - i; knew = krem - cum; break; }
+        cum += c[i];
+      }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, F);
+    krem = __shfl_sync(0xffffffffu, knew, F);
+    prefix |= (uint32_t)bin << shift;
+    mask |= 255u << shift;
+    __syncwarp();
+  }
+  return key2f(prefix);
+}
+
+constexpr int STG_COLS = 64;              // fp32 components per staged slice of an item row
+constexpr int STG_STRIDE = STG_COLS + 4;  // floats; 272-byte rows keep the per-lane float4 reads conflict-free
+
+// One warp per user row.
+//  1. the row's candidate list is streamed ONCE from global memory; entries that pass the main kernel's final
+//     threshold (a superset of the answer, ~2k of them) land in shared memory;
+//  2. the exact k-th largest approximate score of that superset tightens the threshold (k-th - 2E) -> ~1.5k candidates;
+//  3. the candidates' fp32 item rows are staged through shared memory by per-lane bulk async copies (one 256-byte
+//     copy per candidate and slice: 8 KB in flight per warp, where the per-lane strided loads of the first version
+//     exposed a full DRAM latency every 16 bytes), and every lane runs ONE candidate's fp64 FMA chain in
+//     component order -- bit-identical to oracle.canonical_scores;
+//  4. (score, id) are packed into one 64-bit key and ranked by counting (branch-free).
 __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParams p) {
   extern __shared__ __align__(16) unsigned char rr_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t per_warp = (size_t)p.ld * sizeof(double) + SEL_CAP * 8;
+  const size_t per_warp = (size_t)p.ld * sizeof(double) + SEL_CAP * 8 + 32 * STG_STRIDE * 4 + 16;
   unsigned char* base = rr_smem + (size_t)w * per_warp;
-  double* ud = reinterpret_cast<double*>(base);            // [ld] this user's row, widened once
-  float* ex = reinterpret_cast<float*>(ud + p.ld);          // [SEL_CAP] canonical scores
-  int* id = reinterpret_cast<int*>(ex + SEL_CAP);           // [SEL_CAP] item ids
-  int* radix = id;                                          // radix-select scratch (256 ints) before id[] is filled
+  double* ud = reinterpret_cast<double*>(base);                       // [ld] this user's row, widened once
+  float2* pr = reinterpret_cast<float2*>(ud + p.ld);                  // [SEL_CAP] (approx score, id), later 64-bit rank keys
+  float* stg = reinterpret_cast<float*>(pr + SEL_CAP);                // [32][STG_STRIDE] staged item-row slices
+  int* radix = reinterpret_cast<int*>(stg);                           // radix-select scratch before staging starts
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stg + 32 * STG_STRIDE); // this warp's copy-completion barrier
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(pr);
 
   const long long lrow = (long long)blockIdx.x * RR_WARPS + w;
   if (lrow >= p.n_rows) return;
@@ -776,33 +838,71 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   if (n < 0) return;  // overflowed in the main kernel: exact_rows_kernel owns it
   const float2* buf = p.cand + lrow * CAP;
   const int k = p.k;
-  // final keep-threshold from the exact k-th largest approximate score of the list (tighter than the running
-  // histogram edge the main kernel stopped at: fewer canonical scores to evaluate)
-  float thr = p.thr[lrow];
-  if (n > k) {
-    float mx;
-    const float kth = warp_select_kth(buf, n, k, radix, mx);
-    thr = fmaxf(thr, keep_threshold(kth, ERR_FACTOR * p.unorm[row] * (*p.vmax) + 1e-30f, p.clamp));
-  }
-  // ---- pass 1: stream the list once, keep what the final threshold (or the clamp-mode filler rule) keeps
-  int m = 0;
   const unsigned lt = (1u << lane) - 1u;
-  for (int b0 = 0; b0 < n; b0 += 128) {
-    float2 x[4];
+  if (lane == 0) mbar_init(smem_u32(bar), 1);
+  for (int c = lane; c < p.ld; c += 32) ud[c] = (double)p.U[row * p.ld + c];
+  float thr = p.thr[lrow];
+  // ---- 1. superset by the main kernel's final threshold (or the clamp-mode filler rule)
+  int m = 0;
+  for (int b0 = 0; b0 < n; b0 += 256) {
+    float2 x[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 8; ++t) {
       const int e = b0 + 32 * t + lane;
-      x[t] = (e < n) ? buf[e] : make_float2(-INFINITY, 0.f);
+      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
     }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 8; ++t) {
       const int e = b0 + 32 * t + lane;
-      const int item = __float_as_int(x[t].y);
-      const bool keep = e < n && (x[t].x >= thr || (p.clamp && item - p.item_offset < k));
+      const bool keep = e < n && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       const int pos = m + __popc(bal & lt);
-      if (keep && pos < SEL_CAP) id[pos] = item;
+      if (keep && pos < SEL_CAP) pr[pos] = x[t];
       m += __popc(bal);
+    }
+  }
+  __syncwarp();
+  // ---- 2. exact k-th largest approximate score -> final keep-threshold, compact in place
+  if (n > k) {
+    float kth;
+    if (m <= SEL_CAP) {
+      kth = smem_select_kth(pr, m, k, radix);
+    } else {  // loose running threshold (badly placed histogram): select over the whole list in global memory
+      float mx;
+      kth = warp_select_kth(buf, n, k, radix, mx);
+    }
+    thr = fmaxf(thr, keep_threshold(kth, ERR_FACTOR * p.unorm[row] * (*p.vmax) + 1e-30f, p.clamp));
+    if (m <= SEL_CAP) {
+      int m2 = 0;
+      for (int e0 = 0; e0 < m; e0 += 32) {
+        const int e = e0 + lane;
+        const float2 x = e < m ? pr[e] : make_float2(-INFINITY, 0.f);
+        const bool keep = e < m && (x.x >= thr || (p.clamp && __float_as_int(x.y) - p.item_offset < k));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();  // all reads of this batch precede its writes (which land at or below e0)
+        if (keep) pr[m2 + __popc(bal & lt)] = x;
+        m2 += __popc(bal);
+      }
+      m = m2;
+    } else {
+      m = 0;
+      for (int b0 = 0; b0 < n; b0 += 128) {
+        float2 x[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = b0 + 32 * t + lane;
+          x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = b0 + 32 * t + lane;
+          const bool keep = e < n && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          const int pos = m + __popc(bal & lt);
+          if (keep && pos < SEL_CAP) pr[pos] = x[t];
+          m += __popc(bal);
+        }
+      }
     }
   }
   if (m > SEL_CAP) {  // too many near-ties to rank here
@@ -813,52 +913,75 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
     }
     return;
   }
-  for (int c = lane; c < p.ld; c += 32) ud[c] = (double)p.U[row * p.ld + c];
   __syncwarp();
-  // ---- canonical scores: one fp64 FMA chain per candidate in component order (bit-identical to
-  // oracle.canonical_scores; zero pad columns add +0.0), RR_CHAINS independent chains per lane for ILP
-  for (int t0 = lane; t0 < m; t0 += 32 * RR_CHAINS) {
-    const float* vr[RR_CHAINS];
-    double acc[RR_CHAINS];
-#pragma unroll
-    for (int q = 0; q < RR_CHAINS; ++q) {
-      const int t = t0 + 32 * q;
-      vr[q] = p.V + (long long)((t < m ? id[t] : id[t0]) - p.item_offset) * p.ld;
-      acc[q] = 0.0;
-    }
-    for (int c = 0; c < p.ld; c += 4) {
-      float4 x[RR_CHAINS];
-#pragma unroll
-      for (int q = 0; q < RR_CHAINS; ++q) x[q] = ldg4(vr[q] + c);
-      const double u0 = ud[c], u1 = ud[c + 1], u2 = ud[c + 2], u3 = ud[c + 3];
-#pragma unroll
-      for (int q = 0; q < RR_CHAINS; ++q) {
-        acc[q] = fma(u0, (double)x[q].x, acc[q]);
-        acc[q] = fma(u1, (double)x[q].y, acc[q]);
-        acc[q] = fma(u2, (double)x[q].z, acc[q]);
-        acc[q] = fma(u3, (double)x[q].w, acc[q]);
+  // ---- 3. canonical scores: 32 candidates per batch, item rows staged slice by slice
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  uint32_t parity = 0;
+  const int n_slices = (p.ld + STG_COLS - 1) / STG_COLS;
+  for (int t0 = 0; t0 < m; t0 += 32) {
+    const int t = t0 + lane;
+    const bool have = t < m;
+    const int item = have ? __float_as_int(pr[t].y) : 0;
+    const float* vrow = p.V + (long long)(item - p.item_offset) * p.ld;
+    const int nb = min(32, m - t0);
+    double acc = 0.0;
+    for (int sl = 0; sl < n_slices; ++sl) {
+      const int c0 = sl * STG_COLS;
+      const int ncol = min(STG_COLS, p.ld - c0);  // multiple of 4
+      // the previous slice's shared-memory reads (generic proxy) must be ordered before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(smem_u32(bar), (uint32_t)(nb * ncol * 4));
+      __syncwarp();
+      if (have) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(stg + lane * STG_STRIDE)), "l"(vrow + c0), "r"(ncol * 4), "r"(smem_u32(bar))
+                     : "memory");
+      }
+      mbar_wait(smem_u32(bar), parity);
+      parity ^= 1;
+      const float4* mine = reinterpret_cast<const float4*>(stg + lane * STG_STRIDE);
+      const double2* u2 = reinterpret_cast<const double2*>(ud + c0);
+#pragma unroll 4
+      for (int c4 = 0; c4 < ncol / 4; ++c4) {
+        const float4 x = mine[c4];
+        const double2 ua = u2[2 * c4], ub = u2[2 * c4 + 1];
+        acc = fma(ua.x, (double)x.x, acc);
+        acc = fma(ua.y, (double)x.y, acc);
+        acc = fma(ub.x, (double)x.z, acc);
+        acc = fma(ub.y, (double)x.w, acc);
       }
     }
-#pragma unroll
-    for (int q = 0; q < RR_CHAINS; ++q) {
-      const int t = t0 + 32 * q;
-      if (t < m) {
-        float s = (float)acc[q];
-        if (p.clamp) s = s > 0.f ? s : 0.f;  // tf.where(p > 0, p, 0.0)
-        ex[t] = s + 0.0f;
-      }
+    if (have) {
+      float sc = (float)acc;
+      if (p.clamp) sc = sc > 0.f ? sc : 0.f;  // tf.where(p > 0, p, 0.0)
+      sc = sc + 0.0f;                         // -0 -> +0 like the oracle
+      keys[t] = ((unsigned long long)f2key(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
     }
   }
   __syncwarp();
-  // ---- rank by counting with comparator (score desc, item id asc); ids are distinct so ranks are too
-  for (int t = lane; t < m; t += 32) {
-    const float s = ex[t];
-    const int my = id[t];
-    int rank = 0;
-    for (int o = 0; o < m; ++o) rank += (ex[o] > s) || (ex[o] == s && id[o] < my);
-    if (rank < k) {
-      p.out_idx[row * k + rank] = my;
-      p.out_score[row * k + rank] = s;
+  // ---- 4. rank by counting: larger key = (higher score, then lower item id); ids are distinct so ranks are too
+  for (int g0 = 0; g0 < m; g0 += 128) {
+    unsigned long long mk[4];
+    int rank[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = g0 + 32 * i + lane;
+      mk[i] = t < m ? keys[t] : ~0ull;
+      rank[i] = 0;
+    }
+    for (int o = 0; o < m; ++o) {
+      const unsigned long long ko = keys[o];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rank[i] += ko > mk[i] ? 1 : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = g0 + 32 * i + lane;
+      if (t < m && rank[i] < k) {
+        p.out_idx[row * k + rank[i]] = (int)(0xffffffffu - (uint32_t)(mk[i] & 0xffffffffull));
+        p.out_score[row * k + rank[i]] = key2f((uint32_t)(mk[i] >> 32));
+      }
     }
   }
 }
@@ -1127,7 +1250,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8);
+  const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8 + 32 * STG_STRIDE * 4 + 16);
   TMF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
 
   // users go through in batches of UB_BATCH blocks so the candidate workspace stays bounded; V stays packed
