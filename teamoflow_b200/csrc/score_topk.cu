@@ -258,42 +258,50 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
 // warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane).  Iterations are
 // independent of each other -- fire-and-forget histogram increments (red.shared), list stores that nobody waits
 // for, threshold fixed for the duration -- so they pipeline; the threshold advances once at the end.
-__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
-  int maxq = st.cq;
+struct DrainRet { float thr; int cnt, bthr, A; };
+// (out of line, state by value in registers: inlining it at every call site costs registers in the tile loop)
+__device__ __noinline__ DrainRet drain_queues_nl(float thr, float lo, float w, float inv_w, float E, int cnt, int cq, int bthr, int A,
+                                                 uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
+  int maxq = cq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
-  const float thr = st.thr, lo = st.lo, inv_w = st.inv_w;
-  const int bthr = st.bthr;
 #pragma unroll 4
-  for (int s = 0; s < maxq; ++s) {  // branch-free body: nested divergent ifs cost a single warp ~100 cycles each
-    const float2 e = lds_f2(queue + 8u * (uint32_t)s);  // slots >= cq hold stale but readable data
-    const bool ok = (s < st.cq) && (e.x >= thr);
+  for (int s = 0; s < maxq; ++s) {
+    const float2 e = lds_f2(queue + 8u * (uint32_t)s);
+    const bool ok = (s < cq) && (e.x >= thr);
     const bool okh = ok && (e.x >= lo);
     const int b = (int)fminf(fmaxf((e.x - lo) * inv_w, 0.f), (float)(NBINS - 1));
-    const int st_ok = ok && (st.cnt < CAP);
+    const int st_ok = ok && (cnt < CAP);
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.s32 p, %0, 0;\n\t"
         "setp.ne.s32 q, %1, 0;\n\t"
         "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
         "@q red.shared.add.u32 [%5], %6;\n\t}"
-        ::"r"(st_ok), "r"((int)okh), "l"(buf + st.cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)(b >> 1)),
+        ::"r"(st_ok), "r"((int)okh), "l"(buf + cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)(b >> 1)),
           "r"(1u << ((b & 1) * 16))
         : "memory");
-    st.cnt += ok ? 1 : 0;  // > CAP marks saturation
-    st.A += (okh && b >= bthr) ? 1 : 0;
+    cnt += ok ? 1 : 0;
+    A += (okh && b >= bthr) ? 1 : 0;
   }
-  st.cq = 0;
   __syncwarp();
   bool moved = false;
-  while (st.bthr < NBINS - 1) {
-    const int hb = hist_get_s(hrow, st.bthr);
-    if (st.A - hb < k) break;
-    st.A -= hb;
-    ++st.bthr;
+  while (bthr < NBINS - 1) {
+    const int hb = hist_get_s(hrow, bthr);
+    if (A - hb < k) break;
+    A -= hb;
+    ++bthr;
     moved = true;
   }
-  if (moved) st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, clamp);
+  if (moved) thr = edge_threshold(lo, w, bthr, E, clamp);
+  DrainRet r;
+  r.thr = thr; r.cnt = cnt; r.bthr = bthr; r.A = A;
+  return r;
+}
+__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
+  const DrainRet r = drain_queues_nl(st.thr, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, st.bthr, st.A, queue, buf, hrow, k, clamp);
+  st.thr = r.thr; st.cnt = r.cnt; st.bthr = r.bthr; st.A = r.A;
+  st.cq = 0;
 }
 
 // One 32-column slice of a row's accumulator BEFORE the row's threshold exists (first 3 tiles): every column is
