@@ -281,6 +281,25 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         if s >= warmup:
             times.append(float(ms))
     launches = (_abi.launch_count - l0) // (warmup + steps)
+    # phases of one rank's call (CUDA events on the launching stream; separate, untimed-for-the-headline pass)
+    phases = None
+    if world > 1:
+        n_s = tdist.bound_sample_size(hi - lo, n_i, k, world)
+        ubs = tdist.shard_bounds(n_u, world)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.distributed.barrier(); torch.cuda.synchronize()
+        ev[0].record()
+        rb = None
+        if n_s > 0:
+            rb = tdist._gather_rows(tdist.topk_row_bounds(U, V, r, k, False, lo, ubs[rank], ubs[rank + 1], n_s), ubs, None).contiguous()
+        ev[1].record()
+        from teamoflow_b200.mf.matrix_factorization import score_topk as _st
+        _st(U, V, r, k, False, lo, row_bound=rb)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_b, t_m = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        phases = {"bound_pass_ms": t_b, "slab_scoring_ms": t_m, "exchange_merge_ms": max(float(np.mean(times)) - t_b - t_m, 0.0),
+                  "bound_sample_items": n_s, "exchange": tdist.exchange_mode()}
     # the alternative decomposition (users sharded, items replicated: no merge), reported beside the item-sharded one
     user_sharded = None
     if world > 1:
@@ -351,13 +370,15 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     out = idx2.cpu()
     t1 = time.perf_counter()
     return {"metric": "top-k scored user-item pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-            "config": {"workload": f"{n_u} users x {n_i} items rank-{r} top-{k} (raw scores), item-sharded x{world}", "k": k},
+            "config": {"workload": f"{n_u} users x {n_i} items rank-{r} top-{k} (raw scores), item-sharded x{world}", "k": k,
+                       "exchange": (tdist.exchange_mode() + " (bounds all-gathered, lists merged over NVLink peer memory)") if world > 1 else "none"},
             "dtype": "bf16 operands, fp32 accumulate in TMEM, fp64-accumulated rerank",
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": None},
             "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
                     "d2h_bytes_per_step": out.numel() * 4},
-            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded, "recall_path": recall}
+            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded, "recall_path": recall,
+            "phases_ms": phases}
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
@@ -540,6 +561,7 @@ def main():
            "data": "synthetic",
            "config": {"workload": w["desc"], "n_users_per_gpu": w["n_u"], "n_items": w["n_i"], "nnz_per_gpu": wl.nnz, "rank": w["r"],
                       "n_samples": w["S"], "parallelism": f"user-sharded dp{world}" if world > 1 else "single GPU",
+                      "grad_exchange": ("tmf_peer_reduce_push over NVLink peer memory" if comm.peer else "NCCL all-reduce") if comm is not None else "none",
                       "l2_policy": "working set per step (interactions + lists + embeddings, ~%.1f GB) exceeds the 126 MB L2; no flush" % (
                           (wl.nnz * 28 + w["n_u"] * max(w["S"], 1) * 16) / 1e9),
                       "loss_after": loss_now},

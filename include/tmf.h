@@ -10,7 +10,8 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
  *   - the caller owns all buffers, including workspaces; the library allocates nothing
- *     persistent and holds no global state (except a per-thread error string);
+ *     persistent (tmf_peer_alloc is an explicit allocation the caller frees) and holds no
+ *     global state (except a per-thread error string);
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no call
  *     synchronises the device unless its comment says so;
  *   - return value: 0 = ok, negative = TMF_E_* (message via tmf_last_error());
@@ -174,7 +175,18 @@ TMF_API int tmf_score_topk(const float* U, int64_t n_users, const float* V, int6
 TMF_API int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                          float* P, void* ws, size_t ws_bytes, tmf_stream_t stream);
 
-/* merge G per-shard top-k lists ([G, n_users, k]) -> [n_users, k], comparator (score desc, idx asc). */
+/* Item-sharded scoring with an externally supplied per-row bound: row_bound[n_users] (may be NULL) holds, per
+ * user, a LOWER bound of the k-th best canonical score over ALL item slabs (e.g. the k-th best score of the user
+ * against any subset of the items, exchanged between GPUs).  A slab then only lists candidates that can still be in
+ * the global top-k, skips the per-row warm-up, and rows with fewer than k such candidates are padded with
+ * (score -inf, id INT32_MAX) entries, which lose every comparison in tmf_topk_merge*.  The merged result is
+ * identical to tmf_score_topk over the concatenated slabs. */
+TMF_API int tmf_score_topk_bounded(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                           int32_t k, int32_t clamp, int32_t item_offset, const float* row_bound, int32_t* out_idx,
+                           float* out_score, void* ws, size_t ws_bytes, tmf_stream_t stream);
+
+/* merge G per-shard top-k lists ([G, n_users, k], each row sorted as tmf_score_topk writes it) -> [n_users, k],
+ * comparator (score desc, idx asc); G <= 16. */
 TMF_API int tmf_topk_merge(const int32_t* idx_in, const float* score_in, int32_t n_lists, int64_t n_users, int32_t k,
                    int32_t* out_idx, float* out_score, tmf_stream_t stream);
 
@@ -197,6 +209,40 @@ TMF_API int tmf_dcg(const int32_t* topk, int64_t n_users, int32_t k, const int32
 /* idcg[u]: gains of row u sorted descending (zeros between positives and negatives), first k (:370-384) */
 TMF_API int tmf_idcg(int64_t n_users, int64_t n_items, int32_t k, const int32_t* a_ptr, const float* a_val, float* idcg,
              float* row_nnz, tmf_stream_t stream);
+
+/* ------------------------------------------------------------------ multi-GPU exchange over NVLink peer memory
+ * (new-build, SURVEY 8e: the reference has no distribution).  One process per GPU; a rank allocates its exchange
+ * buffers with tmf_peer_alloc (plain cudaMalloc, zero-filled, SYNCHRONOUS), exports them with tmf_ipc_export (64-byte
+ * handle, exchanged by the host, e.g. torch.distributed.all_gather_object) and maps the peers' buffers with
+ * tmf_ipc_open.  Arrays named *_host below are HOST arrays of `world` device pointers, index = rank (the own
+ * entry is the local pointer).  These three calls and tmf_peer_free/tmf_ipc_close take no stream. */
+#define TMF_IPC_HANDLE_BYTES 64
+#define TMF_MAX_PEERS 16
+TMF_API int tmf_peer_alloc(size_t bytes, void** out);
+TMF_API int tmf_peer_free(void* p);
+TMF_API int tmf_ipc_export(const void* dev_ptr, void* handle_host);
+TMF_API int tmf_ipc_open(const void* handle_host, void** out);
+TMF_API int tmf_ipc_close(void* p);
+
+/* Stream-ordered barrier between the ranks: pads_host[g] = rank g's pad (>= TMF_MAX_PEERS uint32, zero-initialised,
+ * in peer memory); every rank calls it with the same, strictly increasing `epoch` (>= 1).  Work enqueued before the
+ * barrier on any rank is visible to work enqueued after it on every rank.  A peer missing for 20 s traps. */
+TMF_API int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, tmf_stream_t stream);
+
+/* all-to-all + merge + all-gather of item-sharded top-k lists in one kernel: for rows [row_lo, row_lo + n_rows) read
+ * the `world` per-slab lists idx_host[g] / score_host[g] ([n_users, k] each, in rank g's memory), merge them like
+ * tmf_topk_merge and store the merged rows into out_idx_host[d] / out_score_host[d] for d < n_out. */
+TMF_API int tmf_topk_merge_peer(const void* const* idx_host, const void* const* score_host, int32_t world, int64_t row_lo,
+                        int64_t n_rows, int32_t k, const void* const* out_idx_host, const void* const* out_score_host,
+                        int32_t n_out, tmf_stream_t stream);
+
+/* reduce-scatter + (optional Adam step 1) + all-gather of an fp32 buffer in one kernel: for elements
+ * [elem_off, elem_off + n_elems) (multiples of 4) s = sum_g part_host[g][e] in rank order (deterministic; every rank
+ * receives the same bits); lr < 0: dst_host[g][e] = s for every g (all-reduce of the item-side gradient dE_i between
+ * the item-major pass and the update, matrix_factorization.py:171 under user sharding; dst may alias part);
+ * lr >= 0: dst_host[g][e] = adam1(dst_host[rank][e], s) (the update of :176 fused in, dst = the replicated weights). */
+TMF_API int tmf_peer_reduce_push(const void* const* part_host, const void* const* dst_host, int32_t world, int32_t rank,
+                         int64_t elem_off, int64_t n_elems, float lr, tmf_stream_t stream);
 
 #ifdef __cplusplus
 }

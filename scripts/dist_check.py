@@ -67,20 +67,37 @@ def main():
 
     b = tdist.balanced_user_bounds(np.bincount(rows, minlength=n_u), world)
     lo, hi = b[rank], b[rank + 1]
-    comm = tdist.GradientSync(shared_user_rows=hi - lo)
-    plan = make(lo, hi, comm)
-    comm.broadcast_params(plan.u, plan.i)
-    plan.forward_backward()
     ref = make(0, n_u, None)  # every rank also runs the whole problem on its own GPU
     ref.forward_backward()
-    e_item = rel_err(plan.i.grads["W"], ref.i.grads["W"])
-    e_user = rel_err(plan.u.grads["W"][:hi - lo], ref.u.grads["W"][lo:hi])
-    e_shared = rel_err(plan.u.grads["W"][hi - lo:], ref.u.grads["W"][n_u:])
-    loss_dp = comm.mean_loss(plan.ip)
-    loss_1 = ref.ip.mean_loss()
-    ok = e_item < 1e-5 and e_user < 1e-5 and e_shared < 1e-5 and abs(loss_dp - loss_1) < 1e-5 * abs(loss_1)
-    print(f"[rank {rank}] train: rel err item {e_item:.2e} user {e_user:.2e} shared {e_shared:.2e} loss {loss_dp:.6f}/{loss_1:.6f}",
-          flush=True)
+    ok = True
+    for peer in (True, False):  # NVLink peer-memory reduction (tmf_peer_reduce_push), then the NCCL all-reduce
+        comm = tdist.GradientSync(shared_user_rows=hi - lo, peer=peer)
+        plan = make(lo, hi, comm)
+        comm.broadcast_params(plan.u, plan.i)
+        plan.forward_backward()
+        e_item = rel_err(plan.i.grads["W"], ref.i.grads["W"])
+        e_user = rel_err(plan.u.grads["W"][:hi - lo], ref.u.grads["W"][lo:hi])
+        e_shared = rel_err(plan.u.grads["W"][hi - lo:], ref.u.grads["W"][n_u:])
+        loss_dp = comm.mean_loss(plan.ip)
+        loss_1 = ref.ip.mean_loss()
+        good = e_item < 1e-5 and e_user < 1e-5 and e_shared < 1e-5 and abs(loss_dp - loss_1) < 1e-5 * abs(loss_1)
+        print(f"[rank {rank}] train ({'peer' if comm.peer else 'nccl'}{'' if comm.peer == peer else ' FALLBACK'}): rel err item {e_item:.2e} "
+              f"user {e_user:.2e} shared {e_shared:.2e} loss {loss_dp:.6f}/{loss_1:.6f}", flush=True)
+        ok = ok and good
+        if comm.peer:
+            # fused step: reduce-scatter + Adam step 1 + all-gather in one kernel == tmf_adam1 on the summed gradient, bit for bit,
+            # and every replica holds the same bits
+            from teamoflow_b200 import _abi
+            want = plan.i.W.clone()
+            g_full = plan.i.grads["W"].clone()
+            _abi.call("tmf_adam1", _abi.ptr(want), _abi.ptr(g_full), want.numel(), 0.1)
+            fused = plan.forward_backward(lr=0.1)
+            same = bool(torch.equal(plan.i.W, want))
+            allW = [torch.empty_like(want) for _ in range(world)]
+            dist.all_gather(allW, plan.i.W.clone())
+            repl = all(bool(torch.equal(w, allW[0])) for w in allW)
+            print(f"[rank {rank}] fused reduce+adam: fused={fused} bit-exact={same} replicas identical={repl}", flush=True)
+            ok = ok and fused and same and repl
 
     # ---- item-sharded top-k
     g = torch.Generator(device="cuda"); g.manual_seed(5)
@@ -90,11 +107,16 @@ def main():
     V[ni2 - 1] = V[0]  # a tie across shards
     ib = tdist.shard_bounds(ni2, world)
     for clamp in (False, True):
-        idx, sc = tdist.sharded_topk(U, V[ib[rank]:ib[rank + 1]].contiguous(), r2, k, clamp, ib[rank])
         idx1, sc1 = score_topk(U, V, r2, k, clamp)
-        same = bool(torch.equal(idx, idx1) and torch.equal(sc, sc1))
-        print(f"[rank {rank}] sharded top-k clamp={clamp}: {'exact' if same else 'MISMATCH'}", flush=True)
-        ok = ok and same
+        for exchange, bound in (("peer", "force"), ("peer", False), ("nccl", "force"), ("nccl", False)):
+            try:
+                idx, sc = tdist.sharded_topk(U, V[ib[rank]:ib[rank + 1]].contiguous(), r2, k, clamp, ib[rank], exchange=exchange, bound=bound)
+                same = bool(torch.equal(idx, idx1) and torch.equal(sc, sc1))
+                msg = "exact" if same else "MISMATCH"
+            except RuntimeError as e:
+                same, msg = False, f"ERROR {e}"
+            print(f"[rank {rank}] sharded top-k clamp={clamp} exchange={exchange} bound={bound}: {msg}", flush=True)
+            ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -49,6 +49,7 @@ SIGNATURES = {
     "tmf_pack_bf16": (_i32, [_p, _i64, _i32, _i32, _p, _i64, _i32, _p, _p]),
     "tmf_score_topk_ws_bytes": (_sz, [_i64, _i64, _i32, _i32]),
     "tmf_score_topk": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tmf_score_topk_bounded": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "tmf_score_dense_bf16": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "tmf_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "tmf_predict_dense": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p]),
@@ -57,6 +58,14 @@ SIGNATURES = {
     "tmf_metrics_hits": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "tmf_dcg": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tmf_idcg": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p]),
+    "tmf_peer_alloc": (_i32, [_sz, _p]),
+    "tmf_peer_free": (_i32, [_p]),
+    "tmf_ipc_export": (_i32, [_p, _p]),
+    "tmf_ipc_open": (_i32, [_p, _p]),
+    "tmf_ipc_close": (_i32, [_p]),
+    "tmf_peer_barrier": (_i32, [_p, _i32, _i32, C.c_uint32, _p]),
+    "tmf_topk_merge_peer": (_i32, [_p, _p, _i32, _i64, _i64, _i32, _p, _p, _i32, _p]),
+    "tmf_peer_reduce_push": (_i32, [_p, _p, _i32, _i32, _i64, _i64, _f32, _p]),
 }
 
 _lib = None
@@ -65,7 +74,7 @@ call_count = 0
 launch_count = 0
 # kernels per ABI call where it is not 1 (memsets are not counted)
 KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5,
-                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 5}
+                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 5, "tmf_score_topk_bounded": 5}
 
 
 class TmfError(RuntimeError):
@@ -115,6 +124,15 @@ def call(name, *args):
     rc = getattr(h, name)(*args, stream())
     call_count += 1
     launch_count += KERNELS_PER_CALL.get(name, 1)
+    if rc != 0:
+        raise TmfError(f"{name} failed ({rc}): {h.tmf_last_error().decode()}")
+
+
+def call_nostream(name, *args):
+    """Entry points that take no stream (peer-memory allocation / IPC mapping); raises on a non-zero return code."""
+    require_cuda()
+    h = lib()
+    rc = getattr(h, name)(*args)
     if rc != 0:
         raise TmfError(f"{name} failed ({rc}): {h.tmf_last_error().decode()}")
 

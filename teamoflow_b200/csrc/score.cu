@@ -43,39 +43,6 @@ __global__ void rank_prep_kernel(const float* __restrict__ P, long long n_rows, 
   }
 }
 
-// ---- top-k list merge: comparator (score desc, index asc); one warp per user, rank by counting
-constexpr int kMergeWarps = 4;
-__global__ void __launch_bounds__(kMergeWarps * 32) topk_merge_kernel(const int* __restrict__ idx_in, const float* __restrict__ sc_in,
-                                                                      int G, long long n_users, int k, int* __restrict__ out_idx,
-                                                                      float* __restrict__ out_sc) {
-  extern __shared__ unsigned char smraw[];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long u = (long long)blockIdx.x * kMergeWarps + w;
-  if (u >= n_users) return;
-  const int n = G * k;
-  float* ss = reinterpret_cast<float*>(smraw) + (size_t)w * n;
-  int* si = reinterpret_cast<int*>(smraw + (size_t)kMergeWarps * n * sizeof(float)) + (size_t)w * n;
-  for (int t = lane; t < n; t += 32) {
-    const int g = t / k, q = t % k;
-    ss[t] = sc_in[((long long)g * n_users + u) * k + q];
-    si[t] = idx_in[((long long)g * n_users + u) * k + q];
-  }
-  __syncwarp();
-  for (int t = lane; t < n; t += 32) {
-    const float s = ss[t];
-    const int id = si[t];
-    int rank = 0;
-    for (int o = 0; o < n; ++o) {
-      const float so = ss[o];
-      rank += (so > s) || (so == s && si[o] < id);
-    }
-    if (rank < k) {
-      out_idx[u * k + rank] = id;
-      out_sc[u * k + rank] = s;
-    }
-  }
-}
-
 __device__ __forceinline__ float csr_lookup(const int* __restrict__ a_idx, const float* __restrict__ a_val, int lo, int hi, int item) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -230,19 +197,6 @@ extern "C" int tmf_rank_rows(const float* P, int64_t n_rows, int64_t n_cols, int
   // stable LSD radix sort: equal keys keep ascending column order == tf.math.top_k tie order
   TMF_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(temp, temp_bytes, (const float*)keys, keys_out, (const int*)vals, out_idx,
                                                               (int)total, (int)n_rows, offs, offs + 1, 0, 32, st));
-  return TMF_OK;
-}
-
-extern "C" int tmf_topk_merge(const int32_t* idx_in, const float* score_in, int32_t n_lists, int64_t n_users, int32_t k,
-                              int32_t* out_idx, float* out_score, tmf_stream_t stream) {
-  TMF_REQUIRE(n_lists >= 1 && k >= 1, "tmf_topk_merge: bad sizes");
-  if (n_users == 0) return TMF_OK;
-  const size_t smem = (size_t)kMergeWarps * n_lists * k * 8;
-  TMF_REQUIRE(smem <= 200 * 1024, "tmf_topk_merge: n_lists*k too large");
-  if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  topk_merge_kernel<<<(unsigned)cdiv(n_users, kMergeWarps), kMergeWarps * 32, smem, as_stream(stream)>>>(
-      idx_in, score_in, n_lists, n_users, k, out_idx, out_score);
-  TMF_LAUNCH_CHECK();
   return TMF_OK;
 }
 

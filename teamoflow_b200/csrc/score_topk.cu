@@ -214,6 +214,7 @@ struct TopkParams {
   int* ovf_rows;                // [n_users_pad] global rows handed to the exact path
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
+  const float* row_bound;       // optional [n_users]: lower bounds of the rows' k-th best TRUE score (cross-GPU exchange), raw mode only
   unsigned long long* prof;     // optional [8] cycle counters (env TMF_TOPK_PROF=1): where the warps wait
   int dbg;                      // profiling aid (env TMF_TOPK_DEBUG): 1 = no appends, 2 = no filtering, 3 = no TMEM reads
 };
@@ -236,6 +237,7 @@ __device__ __forceinline__ float keep_threshold(float kth, float E, int clamp) {
 // once per survivor with 1-3 active lanes (measured: 400-600 cycles per survivor in the divergent versions).
 struct RowState {
   float thr;      // current keep-threshold (+inf for padded rows)
+  float thr_ext;  // externally supplied floor of the threshold (-inf when there is none)
   float lo, w, inv_w, E;
   int cnt;        // list length; > CAP = saturated (-> exact path)
   int cq;         // entries waiting in the lane's queue
@@ -260,7 +262,7 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
 // for, threshold fixed for the duration -- so they pipeline; the threshold advances once at the end.
 struct DrainRet { float thr; int cnt, bthr, A; };
 // (out of line, state by value in registers: inlining it at every call site costs registers in the tile loop)
-__device__ __noinline__ DrainRet drain_queues_nl(float thr, float lo, float w, float inv_w, float E, int cnt, int cq, int bthr, int A,
+__device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float lo, float w, float inv_w, float E, int cnt, int cq, int bthr, int A,
                                                  uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
   int maxq = cq;
 #pragma unroll
@@ -293,13 +295,13 @@ __device__ __noinline__ DrainRet drain_queues_nl(float thr, float lo, float w, f
     ++bthr;
     moved = true;
   }
-  if (moved) thr = edge_threshold(lo, w, bthr, E, clamp);
+  if (moved) thr = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
   DrainRet r;
   r.thr = thr; r.cnt = cnt; r.bthr = bthr; r.A = A;
   return r;
 }
 __device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
-  const DrainRet r = drain_queues_nl(st.thr, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, st.bthr, st.A, queue, buf, hrow, k, clamp);
+  const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, st.bthr, st.A, queue, buf, hrow, k, clamp);
   st.thr = r.thr; st.cnt = r.cnt; st.bthr = r.bthr; st.A = r.A;
   st.cq = 0;
 }
@@ -649,6 +651,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       st.E = ERR_FACTOR * p.unorm[row] * vmax + 1e-30f;
       st.cnt = 0; st.cq = 0; st.bthr = 0; st.A = 0;
       bool warp_inited = false;
+      // External bound (item-sharded scoring): B = a lower bound of the row's k-th best CANONICAL score over all
+      // slabs, so a member of the global top-k has s~ >= B - E.  Clamp mode: only a positive bound says anything
+      // (with B <= 0 the zero-score fillers matter).  When every valid row of the warp has such a floor the
+      // warm-up (3 unfiltered tiles + radix-select rebuild per row) is skipped: the rows start filtering at the
+      // floor with an idle histogram (lo = +inf); a list that still fills up heals through the usual rebuild.
+      st.thr_ext = -INFINITY;
+      if (!DUMP && p.row_bound != nullptr) {
+        if (valid) {
+          const float B = p.row_bound[row];
+          if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
+        }
+        if (__all_sync(0xffffffffu, !valid || st.thr_ext > -INFINITY)) {
+          warp_inited = true;
+          if (valid) st.thr = st.thr_ext;
+          st.lo = INFINITY;
+        }
+      }
       float2* buf = p.cand + lrow * CAP;
       long long w_tfull = 0, w_work = 0, w_init = 0;
       for (int nt = 0; nt < p.n_tiles; ++nt) {
@@ -709,7 +728,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               st.lo = iout[0]; st.w = iout[1]; st.inv_w = iout[2];
               st.bthr = __float_as_int(iout[3]); st.A = __float_as_int(iout[4]);
               st.cnt = __float_as_int(iout[5]);
-              st.thr = edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp);
+              st.thr = fmaxf(edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp), st.thr_ext);
               if (st.cnt > CAP - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
                 st.cnt = CAP + 1;
                 st.thr = INFINITY;
@@ -871,7 +890,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   }
   __syncwarp();
   // ---- 2. exact k-th largest approximate score -> final keep-threshold, compact in place
-  if (n > k) {
+  if (n > k && m > k) {  // (m <= k: an externally bounded row with few local candidates keeps them all)
     float kth;
     if (m <= SEL_CAP) {
       kth = smem_select_kth(pr, m, k, radix);
@@ -991,6 +1010,11 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
         p.out_score[row * k + rank[i]] = key2f((uint32_t)(mk[i] >> 32));
       }
     }
+  }
+  // fewer than k local candidates (only with an external bound): pad with entries that lose every comparison
+  for (int t = m + lane; t < k; t += 32) {
+    p.out_idx[row * k + t] = 0x7fffffff;
+    p.out_score[row * k + t] = -INFINITY;
   }
 }
 
@@ -1200,7 +1224,7 @@ extern "C" size_t tmf_score_topk_ws_bytes(int64_t n_users, int64_t n_items, int3
 
 static int score_topk_impl(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                            int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
-                           size_t ws_bytes, tmf_stream_t stream, float* dump) {
+                           size_t ws_bytes, tmf_stream_t stream, float* dump, const float* row_bound = nullptr) {
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && n_comp > 0 && n_comp <= ld, "tmf_score_topk: bad shape");
   TMF_REQUIRE(n_comp <= MAX_KB * BK, "tmf_score_topk: n_components up to %d supported", MAX_KB * BK);
   TMF_REQUIRE(k >= 1 && k <= 128 && k <= n_items, "tmf_score_topk: need 1 <= k <= min(128, n_items) (k=%d)", k);
@@ -1241,6 +1265,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.unorm = unorm; p.vmax = reinterpret_cast<const float*>(vmax_bits);
   p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
   p.dump = dump; p.dump_ld = n_items;
+  p.row_bound = row_bound;
   { const char* e = getenv("TMF_TOPK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = nullptr;
   if (getenv("TMF_TOPK_PROF")) {
@@ -1296,6 +1321,13 @@ extern "C" int tmf_score_topk(const float* U, int64_t n_users, const float* V, i
                               int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
                               size_t ws_bytes, tmf_stream_t stream) {
   return score_topk_impl(U, n_users, V, n_items, n_comp, ld, k, clamp, item_offset, out_idx, out_score, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int tmf_score_topk_bounded(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                                      int32_t k, int32_t clamp, int32_t item_offset, const float* row_bound, int32_t* out_idx,
+                                      float* out_score, void* ws, size_t ws_bytes, tmf_stream_t stream) {
+  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, k, clamp, item_offset, out_idx, out_score, ws, ws_bytes, stream, nullptr,
+                         row_bound);
 }
 
 extern "C" int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,

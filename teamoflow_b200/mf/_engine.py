@@ -4,7 +4,8 @@
 the kernel sequence that replaces ``matrix_factorization.py:130-176``:
 
     embed fwd (spmm / alias)  ->  fused user pass (scores, loss, dL/dscore, dE_u)
-    ->  item-major segment-sum (dE_i)  ->  [all-reduce dE_i over NCCL when user-sharded]
+    ->  item-major segment-sum (dE_i)  ->  [sum of dE_i over the ranks when user-sharded: one NVLink peer-memory
+        kernel, Adam fused in when the item tower is an identity-feature Linear one; NCCL as the fallback]
     ->  embed bwd  ->  Adam step-1 on every trainable
 
 Embedding matrices live in padded storage ``[n, ld]`` (``ld = ceil4(r)``, pad columns zero) so rows
@@ -168,9 +169,10 @@ class Tower:
             return {"W": self.W, "b": self.b}
         return {"W": self.W, "Wr": self.Wr, "br": self.br}
 
-    def update(self, lr):
+    def update(self, lr, skip=()):
         for k, w in self.trainables().items():
-            adam1(w, self.grads[k], lr)
+            if k not in skip:
+                adam1(w, self.grads[k], lr)
 
 
 # ----------------------------------------------------------------------------- interaction structure
@@ -316,20 +318,26 @@ class TrainPlan:
     def __init__(self, user_tower: Tower, item_tower: Tower, inter_plan: InteractionPlan, r, comm=None):
         self.u, self.i, self.ip, self.r = user_tower, item_tower, inter_plan, int(r)
         self.comm = comm  # optional teamoflow_b200.mf.dist.GradientSync
+        if comm is not None:
+            comm.attach(self)  # item-side gradient (and fusable weights) move into NVLink peer memory
 
-    def forward_backward(self):
+    def forward_backward(self, lr=None):
+        """One forward + backward.  With ``lr`` (training step) the multi-GPU exchange may fuse the Adam update of the
+        item weights into its reduction kernel; returns True when it did."""
         Eu = self.u.forward()
         Ei = self.i.forward()
         self.ip.user_pass(Eu, Ei, self.r, self.u.dE)
         self.ip.item_pass(Eu, self.r, self.i.dE)
+        fused = False
         if self.comm is not None:
-            self.comm.sync_item_grad(self.i.dE)
+            fused = self.comm.sync_item_grad(self.i.dE, lr=lr, tower=self.i)
         self.u.backward()
         self.i.backward()
         if self.comm is not None:
             self.comm.sync_shared_grads(self.u, self.i)
+        return fused
 
     def step(self, lr):
-        self.forward_backward()
+        fused = self.forward_backward(lr)
         self.u.update(lr)
-        self.i.update(lr)
+        self.i.update(lr, skip=("W",) if fused else ())

@@ -8,9 +8,10 @@ The reference has no distribution at all; this is the new-build desi
   all-reduce per epoch, stream-ordered between the item-major pass and the Adam step.  The update is
   elementwise in the summed gradient, so replicas stay bit-identical.
 * top-k     -- items are sharded; every rank scores all users against its own item slab
-  (``tmf_score_topk`` with ``item_offset``), the per-rank ``[n_users, k]`` lists are all-gathered and
-  merged with the (score desc, item id asc) comparator (``tmf_topk_merge``).  A global top-k member is
-  always in its slab's local top-k, so the merge is exact.
+  (``tmf_score_topk_bounded`` with ``item_offset`` and cross-rank score bounds), the per-rank ``[n_users, k]``
+  lists are exchanged and merged with the (score desc, item id asc) comparator -- over NVLink peer memory in one
+  kernel (``tmf_topk_merge_peer``) or through NCCL (``tmf_topk_merge``).  A global top-k member is always in
+  its slab's local top-k, so the merge is exact.
 """
 from __future__ import annotations
 
@@ -47,19 +48,75 @@ class GradientSync:
     (side-feature rows after the rank-local identity block); ``None`` = no shared rows.
     """
 
-    def __init__(self, group=None, shared_user_rows=None):
+    def __init__(self, group=None, shared_user_rows=None, peer=True):
         self.group = group
         self.shared_user_rows = shared_user_rows
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bytes_reduced = 0
+        # peer=True: the item-side gradient is reduced by tmf_peer_reduce_push over NVLink peer memory (and, for an
+        # identity-feature Linear item tower, the Adam step is fused into the same kernel); False / IPC unavailable: NCCL
+        self.peer = bool(peer) and self.world_size > 1 and torch.cuda.is_available()
+        self._ar = None
+        self._dE = self._W = None
+        self._dE_off = self._W_off = None
+        self._rows = None
 
     def _allreduce(self, t):
         if self.world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.bytes_reduced += t.numel() * t.element_size()
 
-    def sync_item_grad(self, dEi):
-        self._allreduce(dEi)
+    def attach(self, plan):
+        """Move the item tower's gradient buffer (and, when the update can be fused, its weights) into peer memory.
+        Collective; called by ``TrainPlan``.  The arena is cached per group: one attached plan at a time."""
+        if not self.peer:
+            return
+        it = plan.i
+        a256 = lambda n: (int(n) + 255) // 256 * 256  # noqa: E731
+        fuse = it.kind == "linear" and it.X.identity
+        n_dE, n_W = a256(it.dE.numel() * 4), (a256(it.W.numel() * 4) if fuse else 0)
+        ar = peer_arena(n_dE + n_W, self.group, tag="grad")
+        if ar is None:
+            self.peer = False
+            return
+        self._ar = ar
+        self._dE_off, self._W_off = 0, (n_dE if fuse else None)
+        self._dE = ar.local(0, tuple(it.dE.shape), torch.float32)
+        self._dE.zero_()
+        it.dE = self._dE
+        if fuse:
+            self._W = ar.local(n_dE, tuple(it.W.shape), torch.float32)
+            self._W.copy_(it.W)
+            it.W = it.E = self._W
+        self._rows = shard_bounds(it.dE.shape[0], self.world_size)
+
+    def detach(self, plan):
+        """End of fit: weights that live in the (shared, reusable) arena are copied out."""
+        it = plan.i
+        if self._W is not None and it.W.data_ptr() == self._W.data_ptr():
+            it.W = it.W.clone()
+            it.E = it.W
+        self._W = None
+
+    def sync_item_grad(self, dEi, lr=None, tower=None):
+        """Sum ``dE_i`` over the ranks (in place).  Returns True when the Adam step of ``tower.W`` was fused in
+        (then ``dEi`` keeps the LOCAL partial and the caller must skip that update)."""
+        if self.world_size == 1:
+            return False
+        if self._ar is None or self._dE is None or dEi.data_ptr() != self._dE.data_ptr():
+            self._allreduce(dEi)
+            return False
+        from .. import _abi
+        ar, ld = self._ar, dEi.shape[1]
+        lo, hi = self._rows[self.rank], self._rows[self.rank + 1]
+        fused = (lr is not None and self._W is not None and tower is not None and tower.W.data_ptr() == self._W.data_ptr())
+        ar.barrier()  # every rank's partial is complete
+        _abi.call("tmf_peer_reduce_push", ar.ptrs(self._dE_off), ar.ptrs(self._W_off if fused else self._dE_off), self.world_size,
+                  self.rank, lo * ld, (hi - lo) * ld, float(lr) if fused else -1.0)
+        ar.barrier()  # every rank's slice has landed everywhere; partial buffers may be rewritten
+        self.bytes_reduced += dEi.numel() * 4
+        return fused
 
     def _shared_slices(self, u):
         out = []
@@ -114,30 +171,227 @@ def merge_topk_lists(idx_lists, score_lists, k):
     return np.take_along_axis(idx, order, 1), np.take_along_axis(sc, order, 1)
 
 
-def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None):
-    """Item-sharded exact top-k: local fused scoring, all-gather of the ``[n_users, k]`` lists, merge.
-    ``U`` (all users) and ``V_local`` (this rank's item slab) are padded storages on this rank's GPU.
-    Every rank returns the full merged ``(idx, score)``."""
+# ----------------------------------------------------------------------------- NVLink peer memory
+
+
+class _DevMem:
+    """Raw device memory as a ``__cuda_array_interface__`` provider (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerArena:
+    """A block of this rank's HBM that every rank of the group can address directly over NVLink (CUDA IPC
+    mappings of plain ``cudaMalloc`` memory, ``tmf_peer_alloc`` / ``tmf_ipc_*``), plus the flag pad of the
+    stream-ordered barrier (``tmf_peer_barrier``).  Collective: every rank constructs it with the same size."""
+
+    PAD_BYTES = 256
+
+    def __init__(self, nbytes, group=None):
+        import ctypes as C
+        from .. import _abi
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.nbytes = (int(nbytes) + 255) // 256 * 256
+        total = self.PAD_BYTES + self.nbytes
+        base = C.c_void_p()
+        _abi.call_nostream("tmf_peer_alloc", total, C.byref(base))
+        self._base = base.value
+        handle = C.create_string_buffer(64)
+        _abi.call_nostream("tmf_ipc_export", C.c_void_p(self._base), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.bases = []
+        for g, h in enumerate(handles):
+            if g == self.rank:
+                self.bases.append(self._base)
+            else:
+                p = C.c_void_p()
+                _abi.call_nostream("tmf_ipc_open", C.create_string_buffer(h, 64), C.byref(p))
+                self.bases.append(p.value)
+        self.epoch = 0
+        self._mem = torch.as_tensor(_DevMem(self._base + self.PAD_BYTES, self.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+        self._pads = (C.c_void_p * self.world)(*self.bases)
+
+    def local(self, offset, shape, dtype):
+        """Tensor view of this rank's arena at byte ``offset`` (256-byte aligned offsets)."""
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        assert offset % 256 == 0 and offset + n <= self.nbytes
+        return self._mem[offset:offset + n].view(dtype).reshape(shape)
+
+    def ptrs(self, offset):
+        """Host array of the ``world`` device pointers to byte ``offset`` of every rank's arena."""
+        import ctypes as C
+        return (C.c_void_p * self.world)(*[b + self.PAD_BYTES + int(offset) for b in self.bases])
+
+    def barrier(self):
+        """Stream-ordered barrier over the group (no host synchronisation)."""
+        from .. import _abi
+        self.epoch += 1
+        _abi.call("tmf_peer_barrier", self._pads, self.world, self.rank, self.epoch)
+
+    def close(self):
+        from .. import _abi
+        import ctypes as C
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for g, b in enumerate(self.bases):
+            if g != self.rank:
+                _abi.call_nostream("tmf_ipc_close", C.c_void_p(b))
+        self._mem = None
+        _abi.call_nostream("tmf_peer_free", C.c_void_p(self._base))
+        self.bases = []
+
+
+_arenas = {}
+_peer_disabled = {}
+
+
+def peer_arena(nbytes, group=None, tag="default"):
+    """The cached arena of ``group`` (grown collectively when too small), or None when peer memory is unavailable
+    (IPC refused by the platform): callers then use the NCCL exchange.  The failure is reported once on stderr."""
+    import sys
+    key = (id(group) if group is not None else 0, tag)
+    if _peer_disabled.get(key):
+        return None
+    ar = _arenas.get(key)
+    if ar is not None and ar.nbytes >= nbytes:
+        return ar
+    if ar is not None:
+        ar.close()
+        _arenas.pop(key)
+    ok = 1
+    try:
+        ar = PeerArena(nbytes, group)
+    except Exception as e:  # noqa: BLE001 -- any rank failing disables the peer path on all of them
+        print(f"[teamoflow_b200] peer memory unavailable on rank {dist.get_rank(group)} ({type(e).__name__}: {e}); "
+              "falling back to the NCCL exchange", file=sys.stderr, flush=True)
+        ok, ar = 0, None
+    flag = torch.tensor([ok], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag) == 0:
+        _peer_disabled[key] = True
+        return None
+    _arenas[key] = ar
+    return ar
+
+
+def exchange_mode(group=None, tag="topk"):
+    """``"peer"`` when the group's arena of that purpose is live, else ``"nccl"`` (reporting aid)."""
+    return "peer" if (id(group) if group is not None else 0, tag) in _arenas else "nccl"
+
+
+# ----------------------------------------------------------------------------- item-sharded top-k
+
+
+def bound_sample_size(n_local_items, n_items_total, k, world=None):
+    """Items of the own slab the bound pass scores (0 = no bound pass).  The k-th best score against ``n_s`` items
+    lets about ``k * n_local / n_s`` candidates per (user, slab) through the main pass and removes its per-row
+    warm-up, for ``n_u/G * n_s`` extra score pairs.  Measured on B200 (1M x 1M, r=128, k=100, one rank's work,
+    ``scripts/topk_shard_probe.py``): G=8 100 -> 66 ms and G=4 139 -> 113 ms with the whole slab as the sample,
+    G=2 206 -> 225+ ms with any sample -- so the pass runs from 4 ranks up."""
+    if world is not None and world < 4:
+        return 0
+    return int(n_local_items)
+
+
+def topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s):
+    """Bound pass of one rank: exact k-th best canonical score of users ``[lo_u, hi_u)`` against the first ``n_s``
+    items of the own slab -- a lower bound of those users' global k-th best score (``-inf`` when the slab is tiny)."""
+    from .matrix_factorization import score_topk
+    n = hi_u - lo_u
+    if n_s < k or n == 0:
+        return torch.full((n,), float("-inf"), dtype=torch.float32, device=U.device)
+    _, sc = score_topk(U[lo_u:hi_u], V_local[:n_s], r, k, clamp, item_offset)
+    return sc[:, k - 1].contiguous()
+
+
+def _gather_rows(local, bounds, group):
+    """all-gather of row blocks of unequal sizes ``bounds[g+1]-bounds[g]`` (padded to the largest)."""
+    world = len(bounds) - 1
+    n_max = max(bounds[g + 1] - bounds[g] for g in range(world))
+    pad = torch.zeros((n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    allp = torch.empty((world * n_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(allp, pad, group=group)
+    if all(bounds[g + 1] - bounds[g] == n_max for g in range(world)):
+        return allp
+    return torch.cat([allp[g * n_max:g * n_max + bounds[g + 1] - bounds[g]] for g in range(world)])
+
+
+def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="auto", bound=True, n_items_total=None):
+    """Item-sharded exact top-k (north_star: "each GPU scoring its own item slab ... merged by allgather").
+
+    1. bound pass -- rank g scores ITS SLICE of the users against a sample of its slab; the k-th best score is a
+       lower bound of those users' global k-th best; the bounds are all-gathered (4 bytes per user);
+    2. every rank scores ALL users against its slab with those bounds (``tmf_score_topk_bounded``): per (user, slab)
+       only candidates that can still reach the global top-k are listed and reranked, so the per-row work shrinks
+       with the slab instead of being repeated on every GPU;
+    3. exchange -- ``"peer"``: one kernel per rank pulls its user slice's G lists over NVLink, merges them and pushes
+       the merged rows to every rank (``tmf_topk_merge_peer``, all-to-all + merge + all-gather in one launch);
+       ``"nccl"``: all-to-all, ``tmf_topk_merge``, all-gather.  ``"auto"`` = peer when IPC works.
+    ``U`` (all users) and ``V_local`` (this rank's slab) are padded storages.  Every rank returns the full merged
+    ``(idx, score)``, identical to ``score_topk`` over the concatenated slabs."""
     from .. import _abi
     from .matrix_factorization import score_topk
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    k_local = min(k, V_local.shape[0])
-    idx, sc = score_topk(U, V_local, r, k_local, clamp, item_offset)
+    n_loc_items = V_local.shape[0]
     if world == 1:
-        return idx, sc
+        return score_topk(U, V_local, r, min(k, n_loc_items), clamp, item_offset)
+    rank = dist.get_rank(group)
+    n_u = U.shape[0]
+    dev = U.device
+    ub = shard_bounds(n_u, world)
+    lo_u, hi_u = ub[rank], ub[rank + 1]
+    # ---- 1. bounds
+    row_bound = None
+    if bound:
+        n_s = bound_sample_size(n_loc_items, n_items_total, k, world) if bound != "force" else n_loc_items
+        if n_s > 0:
+            b_loc = topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s)
+            row_bound = _gather_rows(b_loc, ub, group).contiguous()
+    # ---- 2. local lists (in peer memory when the peer exchange is used)
+    arena = None
+    if exchange in ("auto", "peer"):
+        list_bytes = (n_u * k * 4 + 255) // 256 * 256
+        arena = peer_arena(4 * list_bytes, group, tag="topk")
+        if arena is None and exchange == "peer":
+            raise RuntimeError("peer-memory exchange requested but CUDA IPC is unavailable")
+    k_local = min(k, n_loc_items)
+    if arena is not None:
+        l_idx = arena.local(0, (n_u, k), torch.int32)
+        l_sc = arena.local(list_bytes, (n_u, k), torch.float32)
+        out = (l_idx, l_sc) if k_local == k else None
+    else:
+        out = None
+    idx, sc = score_topk(U, V_local, r, k_local, clamp, item_offset, row_bound=row_bound, out=out)
     if k_local < k:  # tiny slab: pad with entries that can never win
-        pad_i = torch.full((idx.shape[0], k - k_local), 2 ** 31 - 1, dtype=torch.int32, device=idx.device)
-        pad_s = torch.full((idx.shape[0], k - k_local), float("-inf"), dtype=torch.float32, device=idx.device)
+        pad_i = torch.full((n_u, k - k_local), 2 ** 31 - 1, dtype=torch.int32, device=dev)
+        pad_s = torch.full((n_u, k - k_local), float("-inf"), dtype=torch.float32, device=dev)
         idx, sc = torch.cat([idx, pad_i], 1).contiguous(), torch.cat([sc, pad_s], 1).contiguous()
-    n_u = idx.shape[0]
-    all_idx = torch.empty(world, n_u, k, dtype=torch.int32, device=idx.device)
-    all_sc = torch.empty(world, n_u, k, dtype=torch.float32, device=idx.device)
-    dist.all_gather_into_tensor(all_idx, idx, group=group)
-    dist.all_gather_into_tensor(all_sc, sc, group=group)
-    out_i = torch.empty(n_u, k, dtype=torch.int32, device=idx.device)
-    out_s = torch.empty(n_u, k, dtype=torch.float32, device=idx.device)
-    _abi.call("tmf_topk_merge", _abi.ptr(all_idx), _abi.ptr(all_sc), world, n_u, k, _abi.ptr(out_i), _abi.ptr(out_s))
-    return out_i, out_s
+        if arena is not None:
+            l_idx.copy_(idx)
+            l_sc.copy_(sc)
+    # ---- 3. exchange + merge
+    if arena is not None:
+        arena.barrier()  # every rank's lists are complete and visible
+        _abi.call("tmf_topk_merge_peer", arena.ptrs(0), arena.ptrs(list_bytes), world, lo_u, hi_u - lo_u, k,
+                  arena.ptrs(2 * list_bytes), arena.ptrs(3 * list_bytes), world)
+        arena.barrier()  # every rank's pushes have landed; the lists may be overwritten by the next call
+        return (arena.local(2 * list_bytes, (n_u, k), torch.int32).clone(),
+                arena.local(3 * list_bytes, (n_u, k), torch.float32).clone())
+    n_loc = hi_u - lo_u
+    splits = [ub[g + 1] - ub[g] for g in range(world)]
+    r_idx = torch.empty(world * n_loc, k, dtype=torch.int32, device=dev)
+    r_sc = torch.empty(world * n_loc, k, dtype=torch.float32, device=dev)
+    dist.all_to_all_single(r_idx, idx, output_split_sizes=[n_loc] * world, input_split_sizes=splits, group=group)
+    dist.all_to_all_single(r_sc, sc, output_split_sizes=[n_loc] * world, input_split_sizes=splits, group=group)
+    m_idx = torch.empty(n_loc, k, dtype=torch.int32, device=dev)
+    m_sc = torch.empty(n_loc, k, dtype=torch.float32, device=dev)
+    _abi.call("tmf_topk_merge", _abi.ptr(r_idx), _abi.ptr(r_sc), world, n_loc, k, _abi.ptr(m_idx), _abi.ptr(m_sc))
+    return _gather_rows(m_idx, ub, group), _gather_rows(m_sc, ub, group)
 
 
 def user_sharded_topk(U_local, V, r, k, clamp, group=None, gather=True):

@@ -185,6 +185,8 @@ class MatrixFactorization:
                 self.loss_history.append((epoch + 1, loss_one_epoch))
                 if verbose:
                     print(f'Epoch {epoch + 1} Complete | Loss {loss_one_epoch} | Runtime {cumulative_time:.5} s')
+        if comm is not None and hasattr(comm, "detach"):
+            comm.detach(plan)
         # ref:186-187 -- embeddings recomputed from the final weights
         r = self.n_components
         self.user_embedding = _public(plan.u.forward(), r)
@@ -316,16 +318,29 @@ class MatrixFactorization:
 # ---------------------------------------------------------------------- module helpers
 
 
-def score_topk(U, V, r, k, clamp, item_offset=0):
+def score_topk(U, V, r, k, clamp, item_offset=0, row_bound=None, out=None):
     """Fused tcgen05 ``U V^T`` + per-row top-k (``tmf_score_topk``).  ``U``/``V`` are padded storages.
-    Returns ``(idx int32 [n_u, k], score fp32 [n_u, k])``."""
+    Returns ``(idx int32 [n_u, k], score fp32 [n_u, k])``.
+
+    ``row_bound`` (fp32 ``[n_u]``, item-sharded scoring only): per-user lower bounds of the k-th best score over ALL
+    slabs (``tmf_score_topk_bounded``); rows may then end in ``(-inf, INT32_MAX)`` padding.  ``out``: optional
+    ``(idx, score)`` buffers to fill (e.g. views of a peer arena)."""
     n_u, n_i = U.shape[0], V.shape[0]
-    idx = torch.empty(n_u, k, dtype=torch.int32, device=U.device)
-    score = torch.empty(n_u, k, dtype=torch.float32, device=U.device)
+    if out is None:
+        idx = torch.empty(n_u, k, dtype=torch.int32, device=U.device)
+        score = torch.empty(n_u, k, dtype=torch.float32, device=U.device)
+    else:
+        idx, score = out
+        assert idx.shape == (n_u, k) and score.shape == (n_u, k) and idx.is_contiguous() and score.is_contiguous()
     ws_bytes = _abi.query("tmf_score_topk_ws_bytes", n_u, n_i, r, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=U.device)
-    _abi.call("tmf_score_topk", _abi.ptr(U), n_u, _abi.ptr(V), n_i, r, U.shape[1], k, int(bool(clamp)), int(item_offset),
-              _abi.ptr(idx), _abi.ptr(score), _abi.ptr(ws), ws_bytes)
+    if row_bound is None:
+        _abi.call("tmf_score_topk", _abi.ptr(U), n_u, _abi.ptr(V), n_i, r, U.shape[1], k, int(bool(clamp)), int(item_offset),
+                  _abi.ptr(idx), _abi.ptr(score), _abi.ptr(ws), ws_bytes)
+    else:
+        assert row_bound.dtype == torch.float32 and row_bound.numel() == n_u and row_bound.is_contiguous()
+        _abi.call("tmf_score_topk_bounded", _abi.ptr(U), n_u, _abi.ptr(V), n_i, r, U.shape[1], k, int(bool(clamp)),
+                  int(item_offset), _abi.ptr(row_bound), _abi.ptr(idx), _abi.ptr(score), _abi.ptr(ws), ws_bytes)
     return idx, score
 
 

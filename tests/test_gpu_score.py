@@ -240,3 +240,154 @@ def test_topk_larger_sweep_with_rebuilds_bit_exact():
         order = np.lexsort((c, -s.astype(np.float64)))[:k]
         assert np.array_equal(idx[u], c[order].astype(np.int32)), u
         assert np.array_equal(sc[u], s[order])
+
+
+# ------------------------------------------------------------------ item-sharded scoring with exchanged bounds
+
+
+def _bounded_slabs(U, V, k, clamp, bounds, n_virtual, sample_frac=1.0):
+    """The protocol of dist.sharded_topk with the ranks played one after the other on this GPU: bound pass per
+    (user slice, slab sample), bounded main pass per slab, merge."""
+    from teamoflow_b200 import _abi
+    from teamoflow_b200.mf import dist as tdist
+    from teamoflow_b200.mf._engine import new_storage
+    from teamoflow_b200.mf.matrix_factorization import score_topk
+    r = U.shape[1]
+    n_u = U.shape[0]
+    Us = new_storage(n_u, r, torch.as_tensor(U, device="cuda"))
+    slabs = [new_storage(b - a, r, torch.as_tensor(V[a:b], device="cuda")) for a, b in zip(bounds[:-1], bounds[1:])]
+    ub = tdist.shard_bounds(n_u, n_virtual)
+    rb = torch.cat([tdist.topk_row_bounds(Us, slabs[g], r, k, clamp, bounds[g], ub[g], ub[g + 1],
+                                          max(int(slabs[g].shape[0] * sample_frac), 1)) for g in range(n_virtual)]).contiguous()
+    idxs, scs = [], []
+    for g in range(n_virtual):
+        i, s = score_topk(Us, slabs[g], r, k, clamp, bounds[g], row_bound=rb)
+        idxs.append(i); scs.append(s)
+    idx_in, sc_in = torch.stack(idxs).contiguous(), torch.stack(scs).contiguous()
+    out_i = torch.empty(n_u, k, dtype=torch.int32, device="cuda")
+    out_s = torch.empty(n_u, k, dtype=torch.float32, device="cuda")
+    _abi.call("tmf_topk_merge", _abi.ptr(idx_in), _abi.ptr(sc_in), n_virtual, n_u, k, _abi.ptr(out_i), _abi.ptr(out_s))
+    torch.cuda.synchronize()
+    n_pad = int((idx_in == 2 ** 31 - 1).sum())
+    return cpu(out_i), cpu(out_s), n_pad, cpu(rb)
+
+
+@pytest.mark.parametrize("clamp", [False, True])
+@pytest.mark.parametrize("sample_frac", [1.0, 0.3])
+def test_bounded_item_slabs_merge_equals_single_shot(clamp, sample_frac):
+    rng = np.random.default_rng(12)
+    n_u, n_i, r, k = 700, 6000, 48, 25
+    U = (rng.standard_normal((n_u, r)) / 7).astype(np.float32)
+    V = (rng.standard_normal((n_i, r)) / 7).astype(np.float32)
+    V[100] = V[5900]  # a tie across slabs
+    idx, sc, n_pad, rb = _bounded_slabs(U, V, k, clamp, [0, 2000, 4000, 6000], 3, sample_frac)
+    widx, wsc = oracle_topk(U, V, k, clamp)
+    assert np.array_equal(idx, widx) and np.array_equal(sc, wsc)
+    # a bound is a lower bound of the global k-th best score
+    assert np.all(rb <= wsc[:, k - 1])
+
+
+def test_bounded_item_slabs_exact_ties_and_nonpositive_rows():
+    # grid-valued embeddings: every score exact in fp32, massive ties; rows whose scores are all <= 0 get no usable
+    # bound in clamp mode (B <= 0) and must fall back to the filler rule (k lowest ids of each slab)
+    rng = np.random.default_rng(3)
+    n_u, n_i, r, k = 300, 3000, 16, 20
+    U = rng.integers(-4, 5, (n_u, r)).astype(np.float32) / 8
+    V = rng.integers(-4, 5, (n_i, r)).astype(np.float32) / 8
+    U[:40] = -np.abs(U[:40]); V[:, :] = np.abs(V)  # rows 0..39: every score <= 0
+    for clamp in (False, True):
+        idx, sc, _, _ = _bounded_slabs(U, V, k, clamp, [0, 1000, 2100, 3000], 3)
+        widx, wsc = oracle_topk(U, V, k, clamp)
+        assert np.array_equal(idx, widx) and np.array_equal(sc, wsc)
+
+
+def test_bounded_scoring_at_scale_matches_unbounded():
+    # more tiles per slab than the warm-up, a user count that is not a multiple of the 128-row block
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    from teamoflow_b200 import _abi
+    from teamoflow_b200.mf import dist as tdist
+    from teamoflow_b200.mf._engine import new_storage
+    from teamoflow_b200.mf.matrix_factorization import score_topk
+    n_u, n_i, r, k, G_ = 3001, 60_000, 128, 100, 4
+    U = new_storage(n_u, r); U[:, :r] = torch.randn(n_u, r, generator=g, device="cuda") / r ** 0.5
+    V = new_storage(n_i, r); V[:, :r] = torch.randn(n_i, r, generator=g, device="cuda") / r ** 0.5
+    ib, ub = tdist.shard_bounds(n_i, G_), tdist.shard_bounds(n_u, G_)
+    want_i, want_s = score_topk(U, V, r, k, False)
+    rb = torch.cat([tdist.topk_row_bounds(U, V[ib[q]:ib[q + 1]], r, k, False, ib[q], ub[q], ub[q + 1],
+                                          tdist.bound_sample_size(ib[q + 1] - ib[q], n_i, k)) for q in range(G_)]).contiguous()
+    lists = [score_topk(U, V[ib[q]:ib[q + 1]], r, k, False, ib[q], row_bound=rb) for q in range(G_)]
+    idx_in = torch.stack([l[0] for l in lists]).contiguous()
+    sc_in = torch.stack([l[1] for l in lists]).contiguous()
+    out_i, out_s = torch.empty_like(want_i), torch.empty_like(want_s)
+    _abi.call("tmf_topk_merge", _abi.ptr(idx_in), _abi.ptr(sc_in), G_, n_u, k, _abi.ptr(out_i), _abi.ptr(out_s))
+    assert torch.equal(out_i, want_i) and torch.equal(out_s, want_s)
+
+
+# ------------------------------------------------------------------ peer-memory kernels with local "peers"
+
+
+def _ptr_array(tensors):
+    import ctypes as C
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def test_peer_merge_kernel_with_local_peers():
+    from teamoflow_b200 import _abi
+    rng = np.random.default_rng(8)
+    n_u, n_i, r, k, G_ = 257, 5000, 32, 17, 4
+    U = (rng.standard_normal((n_u, r)) / 5).astype(np.float32)
+    V = (rng.integers(-3, 4, (n_i, r)) / 4).astype(np.float32)
+    b = [0, 1250, 2500, 3750, 5000]
+    lists = [fused_topk(U, V[a:c], k, False, item_offset=a) for a, c in zip(b[:-1], b[1:])]
+    li = [torch.as_tensor(l[0], device="cuda").contiguous() for l in lists]
+    ls = [torch.as_tensor(l[1], device="cuda").contiguous() for l in lists]
+    outs_i = [torch.full((n_u, k), -7, dtype=torch.int32, device="cuda") for _ in range(2)]
+    outs_s = [torch.full((n_u, k), -7.0, dtype=torch.float32, device="cuda") for _ in range(2)]
+    lo, n = 31, 150  # a user slice: rows outside it stay untouched
+    _abi.call("tmf_topk_merge_peer", _ptr_array(li), _ptr_array(ls), G_, lo, n, k, _ptr_array(outs_i), _ptr_array(outs_s), 2)
+    torch.cuda.synchronize()
+    widx, wsc = oracle_topk(U, V, k, False)
+    for oi, os_ in zip(outs_i, outs_s):
+        assert np.array_equal(cpu(oi)[lo:lo + n], widx[lo:lo + n]) and np.array_equal(cpu(os_)[lo:lo + n], wsc[lo:lo + n])
+        assert (cpu(oi)[:lo] == -7).all() and (cpu(oi)[lo + n:] == -7).all()
+
+
+def test_peer_reduce_push_sum_order_and_fused_adam():
+    from teamoflow_b200 import _abi
+    rng = np.random.default_rng(4)
+    G_, n = 3, 4096 + 8
+    parts = [torch.as_tensor(rng.standard_normal(n).astype(np.float32), device="cuda") for _ in range(G_)]
+    want = cpu(parts[0]).copy()
+    for p_ in parts[1:]:
+        want = want + cpu(p_)  # rank order, fp32
+    dsts = [torch.zeros(n, dtype=torch.float32, device="cuda") for _ in range(G_)]
+    off, cnt = 8, 4000
+    _abi.call("tmf_peer_reduce_push", _ptr_array(parts), _ptr_array(dsts), G_, 1, off, cnt, -1.0)
+    torch.cuda.synchronize()
+    for d in dsts:
+        assert np.array_equal(cpu(d)[off:off + cnt], want[off:off + cnt]) and not cpu(d)[:off].any() and not cpu(d)[off + cnt:].any()
+    # fused Adam step 1: identical bits to tmf_adam1 applied to the summed gradient
+    w0 = torch.as_tensor(rng.standard_normal(n).astype(np.float32), device="cuda")
+    ws = [w0.clone() for _ in range(G_)]
+    _abi.call("tmf_peer_reduce_push", _ptr_array(parts), _ptr_array(ws), G_, 2, 0, n, 0.1)
+    ref = w0.clone()
+    gsum = torch.as_tensor(want, device="cuda")
+    _abi.call("tmf_adam1", _abi.ptr(ref), _abi.ptr(gsum), n, 0.1)
+    torch.cuda.synchronize()
+    for w in ws:
+        assert torch.equal(w, ref)
+
+
+def test_peer_alloc_export_and_barrier_single_rank():
+    import ctypes as C
+    from teamoflow_b200 import _abi
+    base = C.c_void_p()
+    _abi.call_nostream("tmf_peer_alloc", 4096, C.byref(base))
+    handle = C.create_string_buffer(64)
+    _abi.call_nostream("tmf_ipc_export", base, handle)
+    assert any(handle.raw)
+    pads = (C.c_void_p * 1)(base.value)
+    for epoch in (1, 2, 3):
+        _abi.call("tmf_peer_barrier", pads, 1, 0, epoch)
+    torch.cuda.synchronize()
+    _abi.call_nostream("tmf_peer_free", base)
