@@ -281,25 +281,16 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         if s >= warmup:
             times.append(float(ms))
     launches = (_abi.launch_count - l0) // (warmup + steps)
-    # phases of one rank's call (CUDA events on the launching stream; separate, untimed-for-the-headline pass)
+    # phases of one rank's call (CUDA events on the launching stream; a separate pass, not the headline timing)
     phases = None
     if world > 1:
-        n_s = tdist.bound_sample_size(hi - lo, n_i, k, world)
-        ubs = tdist.shard_bounds(n_u, world)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         torch.distributed.barrier(); torch.cuda.synchronize()
-        ev[0].record()
-        rb = None
-        if n_s > 0:
-            rb = tdist._gather_rows(tdist.topk_row_bounds(U, V, r, k, False, lo, ubs[rank], ubs[rank + 1], n_s), ubs, None).contiguous()
-        ev[1].record()
-        from teamoflow_b200.mf.matrix_factorization import score_topk as _st
-        _st(U, V, r, k, False, lo, row_bound=rb)
-        ev[2].record()
+        evs = []
+        tdist.sharded_topk(U, V, r, k, False, lo, events=evs)
         torch.cuda.synchronize()
-        t_b, t_m = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-        phases = {"bound_pass_ms": t_b, "slab_scoring_ms": t_m, "exchange_merge_ms": max(float(np.mean(times)) - t_b - t_m, 0.0),
-                  "bound_sample_items": n_s, "exchange": tdist.exchange_mode()}
+        phases = {f"{name}_ms": evs[j][1].elapsed_time(e) for j, (name, e) in enumerate(evs[1:])}
+        phases["bound_sample_items"] = tdist.bound_sample_size(hi - lo, n_i, k, world)
+        phases["exchange"] = tdist.exchange_mode()
     # the alternative decomposition (users sharded, items replicated: no merge), reported beside the item-sharded one
     user_sharded = None
     if world > 1:

@@ -35,7 +35,13 @@ constexpr int TOPK_THREADS = 256;
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
-constexpr float ERR_FACTOR = 1.05f / 256.0f;
+// Error bound of the tensor-core score s~ = fl32(sum u~_c v~_c) against the real score s = sum u_c v_c, with u~ = bf16(u),
+// du = u - u~ (both known exactly):  s - sum u~_c v~_c = du.v + u~.dv  =>  |s~ - s| <= |du||v| + |u~||dv| + accumulation.
+// The residual norms are computed from the data by pack_bf16_kernel, so the bound is rigorous (unit roundoff of bf16 is
+// 2^-8 per operand: worst case 2^-7 |u||v|) AND tight for typical data (about 0.8 * 2^-8 |u||v|).
+// ACC_UNIT: slack per accumulated k-step for the fp32 accumulation inside the tensor core, relative to |u~||v~|.
+constexpr float ACC_UNIT = 2.4e-7f;
+constexpr float NORM_SLACK = 1.0001f;  // rounding of the fp32 norm arithmetic itself
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,8 +211,7 @@ struct TopkParams {
   int ub0, n_ublocks;           // this launch covers user blocks [ub0, ub0 + n_ublocks)
   int n_tiles, kb;              // item tiles of BN, k-blocks of BK
   int k, clamp, item_offset;
-  const float* unorm;           // [n_users_pad] l2 norm of each user row (global row index)
-  const float* vmax;            // [1] max item-row norm
+  const float* erow;            // [n_users_pad] error bound E of each user row against this item slab (global row index)
   float2* cand;                 // [batch rows][CAP] (approx score, item id bits), batch-local row index
   int* cnt;                     // [batch rows] candidates per row, -1 = overflow (exact path)
   float* thr_out;               // [batch rows] final keep-threshold of the row
@@ -640,7 +645,6 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     const int n_items = (int)p.n_items;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const float vmax = *p.vmax;
     for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
       const long long lrow = (long long)ub * BM + q * 32 + lane;       // batch-local row (candidate buffers)
       const long long row = (long long)p.ub0 * BM + lrow;              // global row
@@ -648,7 +652,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       RowState st;
       st.thr = valid ? -INFINITY : INFINITY;
       st.lo = 0.f; st.w = 0.f; st.inv_w = 0.f;
-      st.E = ERR_FACTOR * p.unorm[row] * vmax + 1e-30f;
+      st.E = p.erow[row];
       st.cnt = 0; st.cq = 0; st.bthr = 0; st.A = 0;
       bool warp_inited = false;
       // External bound (item-sharded scoring): B = a lower bound of the row's k-th best CANONICAL score over all
@@ -774,8 +778,7 @@ struct RerankParams {
   int k, clamp, item_offset, r, ld;
   const float* U;
   const float* V;
-  const float* unorm;
-  const float* vmax;
+  const float* erow;
   const float2* cand;
   const int* cnt;
   const float* thr;
@@ -898,7 +901,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
       float mx;
       kth = warp_select_kth(buf, n, k, radix, mx);
     }
-    thr = fmaxf(thr, keep_threshold(kth, ERR_FACTOR * p.unorm[row] * (*p.vmax) + 1e-30f, p.clamp));
+    thr = fmaxf(thr, keep_threshold(kth, p.erow[row], p.clamp));
     if (m <= SEL_CAP) {
       int m2 = 0;
       for (int e0 = 0; e0 < m; e0 += 32) {
@@ -1116,28 +1119,54 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const RerankParams p, c
 }
 
 // ------------------------------------------------------------------ operand packing
-// one warp per row: fp32 [n, ld] -> bf16 [n_pad, k_pad] (zero padded), row norm, optional global max norm
+// one warp per row: fp32 [n, ld] -> bf16 [n_pad, k_pad] (zero padded); per row the l2 norms of the row, of its bf16
+// image and of the rounding residual; optional global maxima of the row norm and the residual norm
 __global__ void pack_bf16_kernel(const float* __restrict__ src, long long n, int r, int ld, __nv_bfloat16* __restrict__ dst,
-                                 long long n_pad, int k_pad, float* __restrict__ norms, int* __restrict__ max_norm_bits, int nan_pad) {
+                                 long long n_pad, int k_pad, float* __restrict__ norms, float* __restrict__ norms_bf,
+                                 float* __restrict__ norms_res, int* __restrict__ max_bits, int nan_pad) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_pad) return;
-  float ss = 0.f;
+  float ss = 0.f, sb = 0.f, sd = 0.f;
   for (int c = lane; c < k_pad; c += 32) {
     float v = 0.f;
     if (row < n && c < r) v = src[row * ld + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float vb = __bfloat162float(h);
+    const float d = v - vb;  // exact
     ss = fmaf(v, v, ss);
+    sb = fmaf(vb, vb, sb);
+    sd = fmaf(d, d, sd);
     // padded ITEM rows are NaN: their scores are NaN in every accumulator row, which fmaxf ignores and every
     // >= test rejects -- the epilogue needs no per-column bounds checks
-    dst[row * k_pad + c] = (nan_pad && row >= n) ? __ushort_as_bfloat16((unsigned short)0x7FC0) : __float2bfloat16_rn(v);
+    dst[row * k_pad + c] = (nan_pad && row >= n) ? __ushort_as_bfloat16((unsigned short)0x7FC0) : h;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane == 0) {
-    const float nrm = sqrtf(ss) * 1.0001f;
-    norms[row] = nrm;
-    if (max_norm_bits) atomicMax(max_norm_bits, __float_as_int(nrm));  // non-negative floats order like ints
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
   }
+  if (lane == 0) {
+    const float nrm = sqrtf(ss) * NORM_SLACK, nb = sqrtf(sb) * NORM_SLACK, nd = sqrtf(sd) * NORM_SLACK;
+    if (norms) norms[row] = nrm;
+    if (norms_bf) norms_bf[row] = nb;
+    if (norms_res) norms_res[row] = nd;
+    if (max_bits) {  // non-negative floats order like ints
+      atomicMax(max_bits, __float_as_int(nrm));
+      atomicMax(max_bits + 1, __float_as_int(nd));
+    }
+  }
+}
+
+// E[row] = |du| max|v| + |u~| max|dv| + accumulation slack (see ACC_UNIT)
+__global__ void row_error_kernel(const float* __restrict__ unorm_bf, const float* __restrict__ unorm_res, const int* __restrict__ vmax_bits,
+                                 int k_pad, float* __restrict__ erow, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vmax = __int_as_float(vmax_bits[0]), dvmax = __int_as_float(vmax_bits[1]);
+  const float e = unorm_res[i] * vmax + unorm_bf[i] * dvmax + ACC_UNIT * (float)k_pad * unorm_bf[i] * vmax;
+  erow[i] = e * NORM_SLACK + 1e-30f;
 }
 
 // ------------------------------------------------------------------ host side
@@ -1173,7 +1202,7 @@ static int make_tmap(CUtensorMap* map, void* base, long long rows, int k_pad, in
 struct TopkLayout {
   long long nu_pad, ni_pad, batch_rows;
   int k_pad, kb;
-  size_t off_ub, off_vb, off_unorm, off_vnorm, off_vmax, off_cand, off_cnt, off_thr, off_ovfc, off_ovfr, off_scratch, total;
+  size_t off_ub, off_vb, off_unorm, off_ures, off_erow, off_vnorm, off_vmax, off_cand, off_cnt, off_thr, off_ovfc, off_ovfr, off_scratch, total;
   int scratch_rows;
 };
 
@@ -1190,6 +1219,8 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   L.off_ub = o; o = align_up(o + (size_t)L.nu_pad * L.k_pad * 2, 1024);
   L.off_vb = o; o = align_up(o + (size_t)L.ni_pad * L.k_pad * 2, 1024);
   L.off_unorm = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
+  L.off_ures = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
+  L.off_erow = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.off_vnorm = o; o = align_up(o + (size_t)L.ni_pad * 4, 256);
   L.off_vmax = o; o += 256;
   L.off_cand = o; o = align_up(o + (size_t)L.batch_rows * CAP * 8, 256);
@@ -1212,7 +1243,7 @@ extern "C" int tmf_pack_bf16(const float* src, int64_t n, int32_t n_comp, int32_
   TMF_REQUIRE(n_pad >= n && k_pad >= n_comp && n_comp <= ld, "tmf_pack_bf16: bad shape");
   if (n_pad == 0) return TMF_OK;
   pack_bf16_kernel<<<(unsigned)cdiv(n_pad * 32, 256), 256, 0, as_stream(stream)>>>(src, n, n_comp, ld, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                                                n_pad, k_pad, norms, nullptr, 0);
+                                                                                n_pad, k_pad, norms, nullptr, nullptr, nullptr, 0);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }
@@ -1235,7 +1266,9 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   unsigned char* w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
   __nv_bfloat16* Ub = reinterpret_cast<__nv_bfloat16*>(w + L.off_ub);
   __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(w + L.off_vb);
-  float* unorm = reinterpret_cast<float*>(w + L.off_unorm);
+  float* unorm = reinterpret_cast<float*>(w + L.off_unorm);  // |bf16(u)|
+  float* ures = reinterpret_cast<float*>(w + L.off_ures);    // |u - bf16(u)|
+  float* erow = reinterpret_cast<float*>(w + L.off_erow);
   float* vnorm = reinterpret_cast<float*>(w + L.off_vnorm);
   int* vmax_bits = reinterpret_cast<int*>(w + L.off_vmax);
   float2* cand = reinterpret_cast<float2*>(w + L.off_cand);
@@ -1246,10 +1279,13 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   float* scratch = reinterpret_cast<float*>(w + L.off_scratch);
   cudaStream_t st = as_stream(stream);
 
-  TMF_CUDA(cudaMemsetAsync(vmax_bits, 0, 4, st));
+  TMF_CUDA(cudaMemsetAsync(vmax_bits, 0, 8, st));
   TMF_CUDA(cudaMemsetAsync(ovfc, 0, 4, st));
-  pack_bf16_kernel<<<(unsigned)cdiv(L.nu_pad * 32, 256), 256, 0, st>>>(U, n_users, n_comp, ld, Ub, L.nu_pad, L.k_pad, unorm, nullptr, 0);
-  pack_bf16_kernel<<<(unsigned)cdiv(L.ni_pad * 32, 256), 256, 0, st>>>(V, n_items, n_comp, ld, Vb, L.ni_pad, L.k_pad, vnorm, vmax_bits, 1);
+  pack_bf16_kernel<<<(unsigned)cdiv(L.nu_pad * 32, 256), 256, 0, st>>>(U, n_users, n_comp, ld, Ub, L.nu_pad, L.k_pad, nullptr, unorm, ures,
+                                                                       nullptr, 0);
+  pack_bf16_kernel<<<(unsigned)cdiv(L.ni_pad * 32, 256), 256, 0, st>>>(V, n_items, n_comp, ld, Vb, L.ni_pad, L.k_pad, vnorm, nullptr, nullptr,
+                                                                       vmax_bits, 1);
+  row_error_kernel<<<(unsigned)cdiv(L.nu_pad, 256), 256, 0, st>>>(unorm, ures, vmax_bits, L.k_pad, erow, L.nu_pad);
   TMF_LAUNCH_CHECK();
 
   CUtensorMap tmapU, tmapV;
@@ -1262,7 +1298,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.n_users = n_users; p.n_items = n_items;
   p.n_tiles = (int)(L.ni_pad / BN); p.kb = L.kb;
   p.k = k; p.clamp = clamp ? 1 : 0; p.item_offset = item_offset;
-  p.unorm = unorm; p.vmax = reinterpret_cast<const float*>(vmax_bits);
+  p.erow = erow;
   p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
   p.dump = dump; p.dump_ld = n_items;
   p.row_bound = row_bound;
@@ -1275,7 +1311,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   RerankParams q{};
   q.n_users = n_users; q.n_items = n_items; q.k = k; q.clamp = p.clamp; q.item_offset = item_offset; q.r = n_comp; q.ld = ld;
-  q.U = U; q.V = V; q.unorm = unorm; q.vmax = p.vmax; q.prof = p.prof; q.cand = cand; q.cnt = cnt; q.thr = thr; q.ovf_count = ovfc; q.ovf_rows = ovfr;
+  q.U = U; q.V = V; q.erow = erow; q.prof = p.prof; q.cand = cand; q.cnt = cnt; q.thr = thr; q.ovf_count = ovfc; q.ovf_rows = ovfr;
   q.out_idx = out_idx; q.out_score = out_score;
 
   const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 +

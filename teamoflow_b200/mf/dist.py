@@ -297,15 +297,18 @@ def bound_sample_size(n_local_items, n_items_total, k, world=None):
     return int(n_local_items)
 
 
-def topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s):
+def topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s, with_lists=False):
     """Bound pass of one rank: exact k-th best canonical score of users ``[lo_u, hi_u)`` against the first ``n_s``
-    items of the own slab -- a lower bound of those users' global k-th best score (``-inf`` when the slab is tiny)."""
+    items of the own slab -- a lower bound of those users' global k-th best score (``-inf`` when the slab is tiny).
+    ``with_lists``: also return the ``(idx, score)`` lists the bounds were read from."""
     from .matrix_factorization import score_topk
     n = hi_u - lo_u
     if n_s < k or n == 0:
-        return torch.full((n,), float("-inf"), dtype=torch.float32, device=U.device)
-    _, sc = score_topk(U[lo_u:hi_u], V_local[:n_s], r, k, clamp, item_offset)
-    return sc[:, k - 1].contiguous()
+        b = torch.full((n,), float("-inf"), dtype=torch.float32, device=U.device)
+        return (b, None, None) if with_lists else b
+    idx, sc = score_topk(U[lo_u:hi_u], V_local[:n_s], r, k, clamp, item_offset)
+    b = sc[:, k - 1].contiguous()
+    return (b, idx, sc) if with_lists else b
 
 
 def _gather_rows(local, bounds, group):
@@ -321,7 +324,7 @@ def _gather_rows(local, bounds, group):
     return torch.cat([allp[g * n_max:g * n_max + bounds[g + 1] - bounds[g]] for g in range(world)])
 
 
-def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="auto", bound=True, n_items_total=None):
+def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="auto", bound=True, n_items_total=None, events=None):
     """Item-sharded exact top-k (north_star: "each GPU scoring its own item slab ... merged by allgather").
 
     1. bound pass -- rank g scores ITS SLICE of the users against a sample of its slab; the k-th best score is a
@@ -333,7 +336,15 @@ def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="aut
        the merged rows to every rank (``tmf_topk_merge_peer``, all-to-all + merge + all-gather in one launch);
        ``"nccl"``: all-to-all, ``tmf_topk_merge``, all-gather.  ``"auto"`` = peer when IPC works.
     ``U`` (all users) and ``V_local`` (this rank's slab) are padded storages.  Every rank returns the full merged
-    ``(idx, score)``, identical to ``score_topk`` over the concatenated slabs."""
+    ``(idx, score)``, identical to ``score_topk`` over the concatenated slabs.  ``events``: optional list that
+    receives ``(phase name, CUDA event)`` marks (bench.py's phase breakdown)."""
+
+    def mark(name):
+        if events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            events.append((name, e))
+
     from .. import _abi
     from .matrix_factorization import score_topk
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -346,12 +357,16 @@ def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="aut
     ub = shard_bounds(n_u, world)
     lo_u, hi_u = ub[rank], ub[rank + 1]
     # ---- 1. bounds
-    row_bound = None
+    mark("start")
+    row_bound = own = None
     if bound:
         n_s = bound_sample_size(n_loc_items, n_items_total, k, world) if bound != "force" else n_loc_items
         if n_s > 0:
-            b_loc = topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s)
+            b_loc, own_i, own_s = topk_row_bounds(U, V_local, r, k, clamp, item_offset, lo_u, hi_u, n_s, with_lists=True)
             row_bound = _gather_rows(b_loc, ub, group).contiguous()
+            if n_s == n_loc_items and own_i is not None:
+                own = (own_i, own_s)  # the whole slab was scored: these ARE this rank's lists of its own user slice
+    mark("bound_pass")
     # ---- 2. local lists (in peer memory when the peer exchange is used)
     arena = None
     if exchange in ("auto", "peer"):
@@ -361,27 +376,32 @@ def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="aut
             raise RuntimeError("peer-memory exchange requested but CUDA IPC is unavailable")
     k_local = min(k, n_loc_items)
     if arena is not None:
-        l_idx = arena.local(0, (n_u, k), torch.int32)
-        l_sc = arena.local(list_bytes, (n_u, k), torch.float32)
-        out = (l_idx, l_sc) if k_local == k else None
+        idx = arena.local(0, (n_u, k), torch.int32)
+        sc = arena.local(list_bytes, (n_u, k), torch.float32)
     else:
-        out = None
-    idx, sc = score_topk(U, V_local, r, k_local, clamp, item_offset, row_bound=row_bound, out=out)
+        idx = torch.empty(n_u, k, dtype=torch.int32, device=dev)
+        sc = torch.empty(n_u, k, dtype=torch.float32, device=dev)
     if k_local < k:  # tiny slab: pad with entries that can never win
-        pad_i = torch.full((n_u, k - k_local), 2 ** 31 - 1, dtype=torch.int32, device=dev)
-        pad_s = torch.full((n_u, k - k_local), float("-inf"), dtype=torch.float32, device=dev)
-        idx, sc = torch.cat([idx, pad_i], 1).contiguous(), torch.cat([sc, pad_s], 1).contiguous()
-        if arena is not None:
-            l_idx.copy_(idx)
-            l_sc.copy_(sc)
+        ti, ts = score_topk(U, V_local, r, k_local, clamp, item_offset, row_bound=row_bound)
+        idx[:, :k_local], sc[:, :k_local] = ti, ts
+        idx[:, k_local:], sc[:, k_local:] = 2 ** 31 - 1, float("-inf")
+    elif own is not None:  # rows of the own slice come from the bound pass, the others are scored against the bounds
+        idx[lo_u:hi_u], sc[lo_u:hi_u] = own
+        for a, b in ((0, lo_u), (hi_u, n_u)):
+            if b > a:
+                score_topk(U[a:b], V_local, r, k, clamp, item_offset, row_bound=row_bound[a:b], out=(idx[a:b], sc[a:b]))
+    else:
+        score_topk(U, V_local, r, k, clamp, item_offset, row_bound=row_bound, out=(idx, sc))
+    mark("slab_scoring")
     # ---- 3. exchange + merge
     if arena is not None:
         arena.barrier()  # every rank's lists are complete and visible
         _abi.call("tmf_topk_merge_peer", arena.ptrs(0), arena.ptrs(list_bytes), world, lo_u, hi_u - lo_u, k,
                   arena.ptrs(2 * list_bytes), arena.ptrs(3 * list_bytes), world)
         arena.barrier()  # every rank's pushes have landed; the lists may be overwritten by the next call
-        return (arena.local(2 * list_bytes, (n_u, k), torch.int32).clone(),
-                arena.local(3 * list_bytes, (n_u, k), torch.float32).clone())
+        res = (arena.local(2 * list_bytes, (n_u, k), torch.int32).clone(), arena.local(3 * list_bytes, (n_u, k), torch.float32).clone())
+        mark("exchange_merge")
+        return res
     n_loc = hi_u - lo_u
     splits = [ub[g + 1] - ub[g] for g in range(world)]
     r_idx = torch.empty(world * n_loc, k, dtype=torch.int32, device=dev)
@@ -391,7 +411,9 @@ def sharded_topk(U, V_local, r, k, clamp, item_offset, group=None, exchange="aut
     m_idx = torch.empty(n_loc, k, dtype=torch.int32, device=dev)
     m_sc = torch.empty(n_loc, k, dtype=torch.float32, device=dev)
     _abi.call("tmf_topk_merge", _abi.ptr(r_idx), _abi.ptr(r_sc), world, n_loc, k, _abi.ptr(m_idx), _abi.ptr(m_sc))
-    return _gather_rows(m_idx, ub, group), _gather_rows(m_sc, ub, group)
+    res = (_gather_rows(m_idx, ub, group), _gather_rows(m_sc, ub, group))
+    mark("exchange_merge")
+    return res
 
 
 def user_sharded_topk(U_local, V, r, k, clamp, group=None, gather=True):
