@@ -140,3 +140,73 @@ def _mean_loss(rank, world):
 
 def test_mean_loss_is_weighted_over_ranks():
     _spawn(_mean_loss)
+
+
+# ---- the full item-sharded protocol (bound pass -> bounded slab lists -> all-to-all -> merge -> all-gather) with the
+# two kernels replaced by oracle-backed CPU stand-ins: only dist.sharded_topk's host logic is under test
+
+
+def _fake_score_topk(U, V, r, k, clamp, item_offset=0, row_bound=None, out=None):
+    P = o.canonical_scores(U[:, :r].numpy(), V[:, :r].numpy())
+    if clamp:
+        P = np.where(P > 0, P, np.float32(0))
+    loc = o.topk_stable(P, k)
+    sc = np.take_along_axis(P, loc.astype(np.int64), 1)
+    idx = (loc + item_offset).astype(np.int32)
+    if row_bound is not None:  # what tmf_score_topk_bounded may drop: entries strictly below the bound
+        rb = row_bound.numpy()[:, None]
+        drop = sc < rb
+        if clamp:
+            drop &= rb > 0
+        # surviving entries stay sorted in front, dropped slots become padding
+        order = np.argsort(drop, axis=1, kind="stable")
+        idx, sc, drop = (np.take_along_axis(a, order, 1) for a in (idx, sc, drop))
+        idx = np.where(drop, np.int32(2 ** 31 - 1), idx)
+        sc = np.where(drop, np.float32(-np.inf), sc)
+    ti, ts = torch.from_numpy(idx.copy()), torch.from_numpy(sc.astype(np.float32).copy())
+    if out is not None:
+        out[0].copy_(ti); out[1].copy_(ts)
+        return out
+    return ti, ts
+
+
+class _FakeAbi:
+    @staticmethod
+    def ptr(t):
+        return t
+
+    @staticmethod
+    def call(name, idx_in, sc_in, n_lists, n_users, k, out_idx, out_sc):
+        assert name == "tmf_topk_merge"
+        i = idx_in.reshape(n_lists, n_users, k).numpy()
+        s = sc_in.reshape(n_lists, n_users, k).numpy()
+        mi, ms = tdist.merge_topk_lists(list(i), list(s), k)
+        out_idx.copy_(torch.from_numpy(mi.astype(np.int32)))
+        out_sc.copy_(torch.from_numpy(ms.astype(np.float32)))
+
+
+def _bounded_protocol(rank, world):
+    import teamoflow_b200 as pkg
+    import teamoflow_b200.mf.matrix_factorization as mfm
+    mfm.score_topk = _fake_score_topk
+    pkg._abi = _FakeAbi  # `from .. import _abi` inside sharded_topk resolves to the package attribute
+    rng = np.random.default_rng(21)
+    n_u, n_i, r, k = 23, 120, 8, 6  # 23 users over 2 ranks: unequal slices
+    U = rng.integers(-4, 5, (n_u, r)).astype(np.float32) / 8
+    V = rng.integers(-4, 5, (n_i, r)).astype(np.float32) / 8
+    b = tdist.shard_bounds(n_i, world)
+    lo, hi = b[rank], b[rank + 1]
+    for clamp in (False, True):
+        P = o.canonical_scores(U, V)
+        if clamp:
+            P = np.where(P > 0, P, np.float32(0))
+        want = o.topk_stable(P, k)
+        for bound in ("force", False):
+            idx, sc = tdist.sharded_topk(torch.from_numpy(U), torch.from_numpy(V[lo:hi].copy()), r, k, clamp, lo,
+                                         exchange="nccl", bound=bound)
+            assert np.array_equal(idx.numpy(), want), (clamp, bound)
+            assert np.array_equal(sc.numpy(), np.take_along_axis(P, want.astype(np.int64), 1))
+
+
+def test_item_sharded_bounded_protocol_host_logic():
+    _spawn(_bounded_protocol)
