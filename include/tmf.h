@@ -131,6 +131,10 @@ TMF_API int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float* lo
 /* Adam step t=1 from zero moments (a new tf.keras.optimizers.Adam each epoch, matrix_factorization.py:176). */
 TMF_API int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream);
 
+/* Extension (not reference behaviour): Adam with persistent moments m, v (zero-initialised by the caller) and step count
+ * `step` >= 1 -- what a single long-lived tf.keras.optimizers.Adam would do; behind fit(optimizer="adam"). */
+TMF_API int tmf_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, int32_t step, tmf_stream_t stream);
+
 /* out[0] = sum(x[0..n)) accumulated in fp64, fixed order (reduce_mean numerator, :179). ws >= tmf_reduce_ws_bytes(). */
 TMF_API int tmf_reduce_sum(const float* x, int64_t n, float* out, void* ws, tmf_stream_t stream);
 

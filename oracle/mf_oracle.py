@@ -295,6 +295,19 @@ def adam_step1(w, g, lr):
 MSE, WMRB, KL = "mse", "wmrb", "kl"
 
 
+def adam_step(w, g, m, v, t, lr):
+    """Keras Adam with PERSISTENT moments (beta_1 0.9, beta_2 0.999, epsilon 1e-7) [TF-sem]: what one long-lived
+    ``tf.keras.optimizers.Adam`` would do.  NOT reference behaviour (the reference builds a new optimizer every epoch,
+    matrix_factorization.py:176 -> ``adam_step1``); oracle of the ``fit(optimizer="adam")`` extension.
+    Returns ``(w, m, v)`` after step ``t`` (>= 1)."""
+    dt = w.dtype.type
+    b1, b2, eps = dt(0.9), dt(0.999), dt(1e-7)
+    m = b1 * m + g * (dt(1) - b1)
+    v = b2 * v + (g * g) * (dt(1) - b2)
+    alpha = dt(lr) * np.sqrt(dt(1) - b2 ** dt(t)) / (dt(1) - b1 ** dt(t))
+    return (w - alpha * m / (np.sqrt(v) + eps)).astype(w.dtype), m, v
+
+
 def _loss_and_coefs(loss, rows, cols, vals, p, sample_scores, n_items, n_samples):
     if loss == MSE:
         return (vals.astype(p.dtype) - p) ** 2, mse_coef(vals, p), None

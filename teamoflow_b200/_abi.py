@@ -38,6 +38,7 @@ SIGNATURES = {
     "tmf_pair_dots": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p]),
     "tmf_kl_coef": (_i32, [_i64, _p, _p, _p, _p, _p, _p]),
     "tmf_adam1": (_i32, [_p, _p, _i64, _f32, _p]),
+    "tmf_adam": (_i32, [_p, _p, _p, _p, _i64, _f32, _i32, _p]),
     "tmf_reduce_sum": (_i32, [_p, _i64, _p, _p, _p]),
     "tmf_bias_add": (_i32, [_p, _i64, _i32, _i32, _p, _i32, _p]),
     "tmf_col_sum": (_i32, [_p, _i64, _i32, _i32, _p, _p, _sz, _p]),

@@ -535,6 +535,22 @@ __global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g,
   }
 }
 
+// Adam with persistent moments (extension behind fit(optimizer="adam"); Keras formula, epsilon 1e-7)
+__global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float alpha) {
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + gi * (1.0f - b1);
+    const float vi = b2 * v[i] + (gi * gi) * (1.0f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    w[i] = w[i] - __fdiv_rn(alpha * mi, sqrtf(vi) + eps);
+  }
+}
+
 __global__ void pair_dots_kernel(long long nnz, const int* __restrict__ rows, const int* __restrict__ cols,
                                  const float* __restrict__ Eu, const float* __restrict__ Ei, int ld, float* __restrict__ p) {
   // 8 lanes per pair, float4 strided over the row
@@ -897,6 +913,15 @@ extern "C" int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float*
 extern "C" int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream) {
   if (n == 0) return TMF_OK;
   adam1_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, as_stream(stream)>>>(w, g, n, lr);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_adam(float* w, const float* g, float* m, float* v, int64_t n, float lr, int32_t step, tmf_stream_t stream) {
+  TMF_REQUIRE(step >= 1, "tmf_adam: step counts from 1");
+  if (n == 0) return TMF_OK;
+  const float alpha = lr * sqrtf(1.0f - powf(0.999f, (float)step)) / (1.0f - powf(0.9f, (float)step));
+  adam_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, as_stream(stream)>>>(w, g, m, v, n, alpha);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }

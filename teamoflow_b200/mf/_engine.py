@@ -169,10 +169,21 @@ class Tower:
             return {"W": self.W, "b": self.b}
         return {"W": self.W, "Wr": self.Wr, "br": self.br}
 
-    def update(self, lr, skip=()):
+    def update(self, lr, skip=(), state=None):
+        """Reference behaviour (``state is None``): a brand-new Adam's first step (matrix_factorization.py:176).
+        ``state``: dict of persistent moments + step count (the ``optimizer="adam"`` extension)."""
+        if state is not None:
+            state["t"] = state.get("t", 0) + 1
         for k, w in self.trainables().items():
-            if k not in skip:
+            if k in skip:
+                continue
+            if state is None:
                 adam1(w, self.grads[k], lr)
+            else:
+                if k not in state:
+                    state[k] = (torch.zeros_like(w), torch.zeros_like(w))
+                m, v = state[k]
+                _abi.call("tmf_adam", _abi.ptr(w), _abi.ptr(self.grads[k]), _abi.ptr(m), _abi.ptr(v), w.numel(), float(lr), state["t"])
 
 
 # ----------------------------------------------------------------------------- interaction structure
@@ -191,26 +202,8 @@ class InteractionPlan:
         self.nnz = inter.nnz
         self.S = 0
         self.samp = None
-        keys = self.col_idx
-        if loss == WMRB:
-            if random_ind is None:
-                raise ValueError("WMRBLoss needs sampled items: construct the model with n_users, n_items and "
-                                 "generate_sample=True (or set model.random_ind)")
-            ri = to_device(random_ind, torch.int64)
-            if ri.dim() != 2 or ri.shape[0] != self.n_users:
-                raise ValueError(f"random_ind must be [n_users={self.n_users}, n_samples], got {tuple(ri.shape)}")
-            if ri.numel() and (int(ri.min()) < 0 or int(ri.max()) >= self.n_items):
-                raise ValueError("random_ind holds item ids outside [0, n_items)")
-            self.S = int(ri.shape[1])
-            if self.n_users * self.S + self.nnz >= 2 ** 31:
-                raise ValueError("nnz + n_users*n_samples must be < 2^31")
-            self.samp = ri.to(torch.int32).contiguous()
-            keys = torch.cat([self.col_idx, self.samp.reshape(-1)])
-        self.T = int(keys.numel())
-        self.t_ptr, self.t_src = build_transpose(keys, self.n_items)
-        self.t_user = torch.empty(max(self.T, 1), dtype=torch.int32, device=dev)
-        _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
-                  _abi.ptr(self.t_user))
+        self.t_user = None
+        self.set_samples(random_ind)
         self._build_work_list()
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.coef = torch.zeros(max(self.nnz + self.n_users * self.S, 1), dtype=torch.float32, device=dev)
@@ -221,6 +214,35 @@ class InteractionPlan:
         self.red_out = torch.zeros(1, dtype=torch.float32, device=dev)
         self.spmm_ws = None
         self.n_pos = int((self.vals > 0).sum()) if loss == WMRB else self.nnz
+
+    def set_samples(self, random_ind):
+        """(Re)build everything that depends on the sampled negatives: the int32 sample table and the item-major
+        list over interactions ++ samples.  Called once per fit (the reference samples once per model,
+        matrix_factorization.py:72-73) and again by the ``resample_every`` extension."""
+        dev = self.vals.device
+        keys = self.col_idx
+        if self.loss == WMRB:
+            if random_ind is None:
+                raise ValueError("WMRBLoss needs sampled items: construct the model with n_users, n_items and "
+                                 "generate_sample=True (or set model.random_ind)")
+            ri = to_device(random_ind, torch.int64)
+            if ri.dim() != 2 or ri.shape[0] != self.n_users:
+                raise ValueError(f"random_ind must be [n_users={self.n_users}, n_samples], got {tuple(ri.shape)}")
+            if ri.numel() and (int(ri.min()) < 0 or int(ri.max()) >= self.n_items):
+                raise ValueError("random_ind holds item ids outside [0, n_items)")
+            if self.S and int(ri.shape[1]) != self.S:
+                raise ValueError("the number of samples per user cannot change between resamplings")
+            self.S = int(ri.shape[1])
+            if self.n_users * self.S + self.nnz >= 2 ** 31:
+                raise ValueError("nnz + n_users*n_samples must be < 2^31")
+            self.samp = ri.to(torch.int32).contiguous()
+            keys = torch.cat([self.col_idx, self.samp.reshape(-1)])
+        self.T = int(keys.numel())
+        self.t_ptr, self.t_src = build_transpose(keys, self.n_items)
+        if self.t_user is None or self.t_user.numel() < max(self.T, 1):
+            self.t_user = torch.empty(max(self.T, 1), dtype=torch.int32, device=dev)
+        _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
+                  _abi.ptr(self.t_user))
 
     # users with more interactions than this are processed as several slices (load balance, tmf_user_pass)
     SPLIT = 4096
@@ -318,6 +340,7 @@ class TrainPlan:
     def __init__(self, user_tower: Tower, item_tower: Tower, inter_plan: InteractionPlan, r, comm=None):
         self.u, self.i, self.ip, self.r = user_tower, item_tower, inter_plan, int(r)
         self.comm = comm  # optional teamoflow_b200.mf.dist.GradientSync
+        self.opt_state = None  # ({}, {}) = persistent Adam moments per tower (extension; None = the reference's fresh Adam per step)
         if comm is not None:
             comm.attach(self)  # item-side gradient (and fusable weights) move into NVLink peer memory
 
@@ -338,6 +361,11 @@ class TrainPlan:
         return fused
 
     def step(self, lr):
+        if self.opt_state is not None:  # stateful Adam (extension): the exchange kernel's fused fresh-Adam step does not apply
+            self.forward_backward()
+            self.u.update(lr, state=self.opt_state[0])
+            self.i.update(lr, state=self.opt_state[1])
+            return
         fused = self.forward_backward(lr)
         self.u.update(lr)
         self.i.update(lr, skip=("W",) if fused else ())

@@ -160,20 +160,39 @@ class MatrixFactorization:
         self.item_trainable = self._trainable_list(ti)
         return self._plan
 
-    def fit(self, epochs, user_features, item_features, tf_interactions, lr=1e-2, comm=None, verbose=True):
+    def fit(self, epochs, user_features, item_features, tf_interactions, lr=1e-2, comm=None, verbose=True,
+            optimizer="fresh", resample_every=None, resample_seed=None):
         """Full-batch training, one gradient step per epoch (ref:96-187).
 
         Each epoch: embeddings -> scores of the observed (and sampled) pairs -> loss -> gradient of the
         SUMMED loss (ref:170-171) -> a brand-new Adam's first step on every trainable (ref:176).
-        ``comm`` (extension): a ``teamoflow_b200.mf.dist.GradientSync`` for user-sharded data parallelism.
+        Extensions (defaults = reference behaviour):
+          ``comm``            a ``teamoflow_b200.mf.dist.GradientSync`` for user-sharded data parallelism;
+          ``optimizer``       ``"fresh"`` = a new Adam every epoch like the reference; ``"adam"`` = ONE Adam whose moments
+                              and step count persist over the epochs of this fit (``tmf_adam``);
+          ``resample_every``  redraw the WMRB negatives every that many epochs with the device sampler (the reference
+                              samples once per model, ref:72-73); ``resample_seed`` makes the draws reproducible.  The new
+                              table replaces ``self.random_ind``; every table drawn is also kept in ``self._sample_log``.
         """
+        if optimizer not in ("fresh", "adam"):
+            raise ValueError("optimizer must be 'fresh' (reference behaviour) or 'adam'")
         plan = self._prepare(user_features, item_features, tf_interactions, comm=comm)
+        if optimizer == "adam":
+            plan.opt_state = ({}, {})
         if comm is not None:
             comm.broadcast_params(plan.u, plan.i)
         cumulative_time = 0
         self.loss_history = []
+        self._sample_log = []
         for epoch in range(epochs):
             start = t.default_timer()
+            if resample_every and epoch > 0 and epoch % int(resample_every) == 0 and plan.ip.loss == eng.WMRB:
+                seed = None if resample_seed is None else int(resample_seed) + epoch
+                if seed is None:
+                    seed = int(np.random.randint(0, 2 ** 62))
+                self.random_ind = random_sampler(plan.ip.n_items, plan.ip.n_users, plan.ip.S, seed=seed)
+                self._sample_log.append((epoch, self.random_ind))
+                plan.ip.set_samples(self.random_ind)
             plan.step(lr)
             report = (epoch + 1) % 25 == 0
             if report:
@@ -307,6 +326,50 @@ class MatrixFactorization:
         dict_results = {'User Embedding': self.user_embedding, 'Item Embedding': self.item_embedding,
                         'User Variables': self.user_trainable, 'Item Variables': self.item_trainable}
         return dict_config, dict_results
+
+    def save(self, path):
+        """Extension: write the fitted model to ``path`` -- constructor kwargs (so ``load`` can rebuild it,
+        unlike ``from_saved(save_model()[0])``, quirk 7), embeddings, trainables and the sampled negatives."""
+        config = {"n_components": self.n_components, "user_repr_graph": type(self.user_repr_graph).__name__,
+                  "item_repr_graph": type(self.item_repr_graph).__name__, "loss_graph": type(self.loss_graph).__name__,
+                  "user_weight_graph": type(self.user_weight_graph).__name__, "item_weight_graph": type(self.item_weight_graph).__name__,
+                  "n_users": self.n_users, "n_items": self.n_items, "n_samples": self.n_samples}
+        c = lambda x: None if x is None else x.detach().cpu()  # noqa: E731
+        state = {"user_embedding": c(getattr(self, "user_embedding", None)), "item_embedding": c(getattr(self, "item_embedding", None)),
+                 "user_trainable": None if self.user_trainable is None else [c(v) for v in self.user_trainable],
+                 "item_trainable": None if self.item_trainable is None else [c(v) for v in self.item_trainable],
+                 "random_ind": c(self.random_ind),
+                 "user_linear_bias": c(self.user_linear_bias), "item_linear_bias": c(self.item_linear_bias),
+                 "user_relu_weight": c(self.user_relu_weight), "user_relu_bias": c(self.user_relu_bias),
+                 "item_relu_weight": c(self.item_relu_weight), "item_relu_bias": c(self.item_relu_bias)}
+        torch.save({"format": "teamoflow_b200.mf/1", "config": config, "state": state}, path)
+
+    @classmethod
+    def load(cls, path, initializers=None):
+        """Rebuild a model written by ``save``.  Custom ``Initializer`` subclasses are not serialised: pass
+        ``initializers=(user_weight_graph, item_weight_graph)`` to restore them (default: ``NormalInitializer``)."""
+        from . import embedding_graphs as _E, initializer_graphs as _I, loss_graphs as _L
+        blob = torch.load(path, map_location="cpu", weights_only=True)
+        if blob.get("format") != "teamoflow_b200.mf/1":
+            raise ValueError("not a teamoflow_b200 model file")
+        cfg, st = dict(blob["config"]), blob["state"]
+        for key, mod in (("user_repr_graph", _E), ("item_repr_graph", _E), ("loss_graph", _L)):
+            cfg[key] = getattr(mod, cfg[key])()
+        for j, key in enumerate(("user_weight_graph", "item_weight_graph")):
+            given = None if initializers is None else initializers[j]
+            cfg[key] = given if given is not None else getattr(_I, cfg[key], _I.NormalInitializer)()
+        model = cls(**cfg)
+        r = model.n_components
+        g = lambda x: None if x is None else to_device(x, x.dtype)  # noqa: E731
+        if st["user_embedding"] is not None:
+            model.user_embedding = _public(eng.storage_of(g(st["user_embedding"])), r)
+            model.item_embedding = _public(eng.storage_of(g(st["item_embedding"])), r)
+        model.user_trainable = None if st["user_trainable"] is None else [g(v) for v in st["user_trainable"]]
+        model.item_trainable = None if st["item_trainable"] is None else [g(v) for v in st["item_trainable"]]
+        model.random_ind = g(st["random_ind"])
+        for key in ("user_linear_bias", "item_linear_bias", "user_relu_weight", "user_relu_bias", "item_relu_weight", "item_relu_bias"):
+            setattr(model, key, g(st[key]))
+        return model
 
     @classmethod
     def from_saved(cls, config):

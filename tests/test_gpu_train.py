@@ -468,3 +468,82 @@ def test_heavy_users_are_split_and_still_deterministic_and_exact():
         g1 = plan.u.grads["W"].clone()
         plan.forward_backward()
         assert torch.equal(g1, plan.u.grads["W"])
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) extensions (defaults stay reference behaviour)
+
+
+def _small_wmrb_model(seed=31, n_u=60, n_i=80, r=8, S=10, nnz=700):
+    E, I, L, eng, FeatureMatrix, SparseInteractions, MatrixFactorization = _mods()
+    rng, rows, cols, vals, samp = make_problem(n_u, n_i, r, nnz, S, seed, values=(1.0, 2.0, -1.0))
+    U0 = (rng.standard_normal((n_u, r)) * 0.3).astype(np.float32)
+    V0 = (rng.standard_normal((n_i, r)) * 0.3).astype(np.float32)
+    model = MatrixFactorization(r, loss_graph=L.WMRBLoss(), user_weight_graph=fixed_init(U0), item_weight_graph=fixed_init(V0),
+                                n_users=n_u, n_items=n_i, n_samples=S)
+    model.random_ind = torch.as_tensor(samp, device="cuda")
+    inter = SparseInteractions(np.stack([rows, cols], 1), vals, (n_u, n_i))
+    return model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S)
+
+
+def test_stateful_adam_extension_matches_oracle():
+    model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S) = _small_wmrb_model()
+    lr, epochs = 0.05, 3
+    model.fit(epochs, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=lr, verbose=False, optimizer="adam")
+    Xu, Xi = np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32)
+    pu, pi = {"W": U0.copy()}, {"W": V0.copy()}
+    mu, vu, mi, vi = (np.zeros_like(U0), np.zeros_like(U0), np.zeros_like(V0), np.zeros_like(V0))
+    for t in range(1, epochs + 1):
+        _, gu, gi, _, _ = o.train_step_sparse("wmrb", Xu, Xi, "linear", "linear", pu, pi, rows, cols, vals, samp, n_i, S, update=False)
+        pu["W"], mu, vu = o.adam_step(pu["W"], gu["W"], mu, vu, t, lr)
+        pi["W"], mi, vi = o.adam_step(pi["W"], gi["W"], mi, vi, t, lr)
+    for got, want in ((model.user_trainable[0], pu["W"]), (model.item_trainable[0], pi["W"])):
+        d = np.abs(cpu(got).astype(np.float64) - want)
+        assert (d <= 2 * lr * epochs).all() and (d > 5e-5).mean() < 0.01
+
+
+def test_fresh_optimizer_is_the_default_and_differs_from_stateful():
+    model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S) = _small_wmrb_model()
+    model.fit(3, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False)
+    fresh = cpu(model.item_trainable[0]).copy()
+    _, _, _, Ei_ref, _ = o.fit(3, "wmrb", np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32), "linear", "linear",
+                               {"W": U0.copy()}, {"W": V0.copy()}, rows, cols, vals, samp, n_i, S, lr=0.05, dense=False)[:5]
+    assert (np.abs(fresh - Ei_ref) > 5e-5).mean() < 0.02
+    model.fit(3, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False, optimizer="adam")
+    assert np.abs(cpu(model.item_trainable[0]) - fresh).max() > 1e-3
+
+
+def test_resample_every_extension_matches_oracle_with_the_drawn_tables():
+    model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S) = _small_wmrb_model(seed=32)
+    lr = 0.05
+    model.fit(4, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=lr, verbose=False, resample_every=2, resample_seed=99)
+    assert [e for e, _ in model._sample_log] == [2]
+    samp2 = cpu(model._sample_log[0][1])
+    assert samp2.shape == samp.shape and not np.array_equal(samp2, samp)
+    assert all(len(set(row)) == S and min(row) >= 0 and max(row) < n_i for row in samp2.tolist())  # without replacement
+    Xu, Xi = np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32)
+    pu, pi, _, _, _ = o.fit(2, "wmrb", Xu, Xi, "linear", "linear", {"W": U0.copy()}, {"W": V0.copy()}, rows, cols, vals, samp, n_i, S,
+                            lr=lr, dense=False)
+    pu, pi, _, _, _ = o.fit(2, "wmrb", Xu, Xi, "linear", "linear", pu, pi, rows, cols, vals, samp2, n_i, S, lr=lr, dense=False)
+    for got, want in ((model.user_trainable[0], pu["W"]), (model.item_trainable[0], pi["W"])):
+        d = np.abs(cpu(got).astype(np.float64) - want)
+        assert (d <= 2 * lr * 4).all() and (d > 5e-5).mean() < 0.02
+    # same seed, same draws
+    model.fit(4, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=lr, verbose=False, resample_every=2, resample_seed=99)
+    assert np.array_equal(cpu(model._sample_log[0][1]), samp2)
+
+
+def test_save_and_load_round_trip(tmp_path):
+    from teamoflow_b200.mf.matrix_factorization import MatrixFactorization
+    model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S) = _small_wmrb_model(seed=33)
+    model.fit(2, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False)
+    path = str(tmp_path / "model.pt")
+    model.save(path)
+    again = MatrixFactorization.load(path)
+    assert torch.equal(again.user_embedding, model.user_embedding) and torch.equal(again.item_embedding, model.item_embedding)
+    assert torch.equal(again.random_ind, model.random_ind) and again.n_samples == model.n_samples
+    assert type(again.loss_graph).__name__ == "WMRBLoss"
+    assert np.array_equal(again.retrieve_user_recs(k=7), model.retrieve_user_recs(k=7))
+    A = np.zeros((n_u, n_i), np.float32); A[rows, cols] = vals
+    assert torch.equal(again.recall_at_k(torch.as_tensor(A), k=5), model.recall_at_k(torch.as_tensor(A), k=5))
+    # and it can be trained again (weights are re-initialised by fit like the reference does)
+    again.fit(1, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False)

@@ -173,3 +173,30 @@ def test_dense_and_sparse_fit_agree_short_trajectory():
     b = o.fit(3, "wmrb", np.eye(30), np.eye(40), "linear", "linear", {"W": U0}, {"W": V0}, rows, cols,
               vals.astype(np.float64), samp, 40, 8, lr=0.1, dense=False)
     np.testing.assert_allclose(a[4], b[4], rtol=1e-9)
+
+
+def test_stateful_adam_matches_the_keras_formula_in_the_shim():
+    """oracle.adam_step (extension oracle) against the Keras-Adam stand-in used to run the reference source."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden", "tf_shim"))
+    try:
+        import tensorflow as tf  # the shim
+        assert tf.__version__.endswith("shim")
+        rng = np.random.default_rng(5)
+        w0 = rng.standard_normal((7, 3)).astype(np.float32)
+        var = tf.Variable(w0)
+        opt = tf.keras.optimizers.Adam(learning_rate=0.05)
+        w, m, v = w0.copy(), np.zeros_like(w0), np.zeros_like(w0)
+        for t in range(1, 5):
+            g = rng.standard_normal((7, 3)).astype(np.float32)
+            opt.apply_gradients([(torch.from_numpy(g), var)])
+            w, m, v = o.adam_step(w, g, m, v, t, 0.05)
+            np.testing.assert_allclose(var.detach().numpy(), w, rtol=1e-5, atol=1e-6)
+            if t == 1:  # the first step of a stateful Adam is the reference's per-epoch fresh step
+                np.testing.assert_allclose(w, o.adam_step1(w0, g, 0.05), rtol=2e-6, atol=2e-7)
+    finally:
+        sys.path.pop(0)
+        for mod in ("tensorflow", "tensorflow_probability"):
+            sys.modules.pop(mod, None)
