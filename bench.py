@@ -363,7 +363,7 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     return {"metric": "top-k scored user-item pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "config": {"workload": f"{n_u} users x {n_i} items rank-{r} top-{k} (raw scores), item-sharded x{world}", "k": k,
                        "exchange": (tdist.exchange_mode() + " (bounds all-gathered, lists merged over NVLink peer memory)") if world > 1 else "none"},
-            "dtype": "bf16 operands, fp32 accumulate in TMEM, fp64-accumulated rerank",
+            "dtype": "16-bit tensor-core operands (fp16 or bf16, chosen from the data), fp32 accumulate in TMEM, fp64-accumulated rerank",
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": None},
             "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,

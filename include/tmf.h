@@ -162,8 +162,9 @@ TMF_API int tmf_pack_bf16(const float* src, int64_t n, int32_t n_comp, int32_t l
                   int32_t k_pad, float* norms, tmf_stream_t stream);
 
 /* U.V^T (matrix_factorization.py:195) + per-row top-k (tf.math.top_k, :245,:429) as ONE kernel:
- * tcgen05 bf16 GEMM, accumulators in TMEM, fused threshold/candidate epilogue; then an fp32/fp64
- * canonical rerank so indices are exact.  Scores are never written to HBM.
+ * tcgen05 GEMM on 16-bit operands (fp16 or bf16, whichever rounds the given embeddings more accurately),
+ * accumulators in TMEM, fused threshold/candidate epilogue; then an fp32/fp64 canonical rerank so indices
+ * are exact.  Scores are never written to HBM.
  *   clamp != 0: scores <= 0 are +0.0 before ranking (recall_at_k path, :237).
  *   item_offset: global index of this GPU's first item (item-sharded scoring).
  *   out_idx[n_users, k] int32 (global ids), out_score[n_users, k] fp32 canonical scores.
@@ -188,6 +189,11 @@ TMF_API int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V
 TMF_API int tmf_score_topk_bounded(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                            int32_t k, int32_t clamp, int32_t item_offset, const float* row_bound, int32_t* out_idx,
                            float* out_score, void* ws, size_t ws_bytes, tmf_stream_t stream);
+
+/* Same with an explicit operand format: -1 = chosen from the data like tmf_score_topk does (fp16 where the embeddings fit
+ * its range and it rounds them more accurately than bf16), 0 = bf16, 1 = fp16. */
+TMF_API int tmf_score_dense_tc(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                       int32_t operand_format, float* P, void* ws, size_t ws_bytes, tmf_stream_t stream);
 
 /* merge G per-shard top-k lists ([G, n_users, k], each row sorted as tmf_score_topk writes it) -> [n_users, k],
  * comparator (score desc, idx asc); G <= 16. */

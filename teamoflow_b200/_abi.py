@@ -52,6 +52,7 @@ SIGNATURES = {
     "tmf_score_topk": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
     "tmf_score_topk_bounded": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "tmf_score_dense_bf16": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p, _sz, _p]),
+    "tmf_score_dense_tc": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "tmf_topk_merge": (_i32, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "tmf_predict_dense": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p]),
     "tmf_rank_rows_ws_bytes": (_sz, [_i64, _i64]),
@@ -75,7 +76,7 @@ call_count = 0
 launch_count = 0
 # kernels per ABI call where it is not 1 (memsets are not counted)
 KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5,
-                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 5, "tmf_score_topk_bounded": 5}
+                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 8, "tmf_score_topk_bounded": 8}
 
 
 class TmfError(RuntimeError):

@@ -9,6 +9,7 @@
 // list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -157,6 +158,8 @@ __device__ __forceinline__ void smem_inc(int* p) {
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+__device__ __forceinline__ bool use_fp16(const float* stats);  // operand format choice, defined with the pack kernels
+
 struct TopkParams {
   long long n_users, n_items;   // real sizes
   int ub0, n_ublocks;           // this launch covers user blocks [ub0, ub0 + n_ublocks)
@@ -170,6 +173,8 @@ struct TopkParams {
   int* ovf_rows;                // [n_users_pad] global rows handed to the exact path
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
+  const float* fmt_stats;       // operand statistics (see use_fp16); NULL with force_fmt >= 0
+  int force_fmt;                // -1 = by fmt_stats, 0 = bf16, 1 = fp16
   const float* row_bound;       // optional [n_users]: lower bounds of the rows' k-th best TRUE score (cross-GPU exchange), raw mode only
   unsigned long long* prof;     // optional [8] cycle counters (env TMF_TOPK_PROF=1): where the warps wait
   int dbg;                      // profiling aid (env TMF_TOPK_DEBUG): 1 = no appends, 2 = no filtering, 3 = no TMEM reads
@@ -748,6 +753,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
+      const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
+      const uint32_t idesc = f16 ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
         mbar_wait(smem_u32(a_full), a_phase);
         a_phase ^= 1;
@@ -767,7 +775,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), kIdesc,
+              tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
                               (uint32_t)((kb | k) != 0));
             }
             tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
@@ -1283,28 +1291,95 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(const RerankParams p, c
   }
 }
 
+// ------------------------------------------------------------------ operand format
+// The tensor-core operands are 16-bit: bf16 (8 significant bits, fp32's exponent range) or fp16 (11 significant bits,
+// normal range 6e-5 .. 65504).  Where the embeddings fit fp16's range its rounding residuals -- and with them the
+// data-derived error bound E, the survivor counts of the epilogue and the rerank's candidate lists -- are ~8x smaller.
+// operand_stats_kernel measures both roundings on the actual data; use_fp16() picks the format with the smaller
+// relative residual (bf16 whenever a component would overflow fp16).  stats: [0] sum v^2, [1] sum (v - fp16(v))^2,
+// [2] sum (v - bf16(v))^2, [3] max|v| (as int bits) for U; [4..7] the same for V.  Either choice is exact (E follows the
+// chosen rounding); the float atomics only make a borderline CHOICE run-dependent, never a result.
+__device__ __forceinline__ bool use_fp16(const float* stats) {
+  if (stats == nullptr) return false;
+  const float mx = fmaxf(__int_as_float(__float_as_int(stats[3])), __int_as_float(__float_as_int(stats[7])));
+  if (!(mx < 60000.f)) return false;
+  const float su = fmaxf(stats[0], 1e-30f), sv = fmaxf(stats[4], 1e-30f);
+  const float e16 = sqrtf(stats[1] / su) + sqrtf(stats[5] / sv);
+  const float ebf = sqrtf(stats[2] / su) + sqrtf(stats[6] / sv);
+  return e16 < ebf;
+}
+
+__global__ void __launch_bounds__(256) operand_stats_kernel(const float* __restrict__ src, long long n, int r, int ld, float* __restrict__ stats) {
+  float ss = 0.f, s16 = 0.f, sbf = 0.f, mx = 0.f;
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {  // one warp per row
+    const float4* p4 = reinterpret_cast<const float4*>(src + row * ld);
+    for (int c4 = lane; c4 < (ld >> 2); c4 += 32) {  // pad columns [r, ld) are zero: they add nothing
+      const float4 q = __ldg(p4 + c4);
+      const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = vv[j];
+        const float d16 = v - __half2float(__float2half_rn(v));
+        const float dbf = v - __bfloat162float(__float2bfloat16_rn(v));
+        ss = fmaf(v, v, ss);
+        s16 = fmaf(d16, d16, s16);
+        sbf = fmaf(dbf, dbf, sbf);
+        mx = fmaxf(mx, fabsf(v));
+      }
+    }
+  }
+  (void)r;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    s16 += __shfl_xor_sync(0xffffffffu, s16, o);
+    sbf += __shfl_xor_sync(0xffffffffu, sbf, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(stats + 0, ss);
+    atomicAdd(stats + 1, s16);
+    atomicAdd(stats + 2, sbf);
+    atomicMax(reinterpret_cast<int*>(stats) + 3, __float_as_int(mx));  // non-negative floats order like ints (inf/NaN sort high)
+  }
+}
+
 // ------------------------------------------------------------------ operand packing
 // one warp per row: fp32 [n, ld] -> bf16 [n_pad, k_pad] (zero padded); per row the l2 norms of the row, of its bf16
 // image and of the rounding residual; optional global maxima of the row norm and the residual norm
 __global__ void pack_bf16_kernel(const float* __restrict__ src, long long n, int r, int ld, __nv_bfloat16* __restrict__ dst,
                                  long long n_pad, int k_pad, float* __restrict__ norms, float* __restrict__ norms_bf,
-                                 float* __restrict__ norms_res, int* __restrict__ max_bits, int nan_pad) {
+                                 float* __restrict__ norms_res, int* __restrict__ max_bits, int nan_pad,
+                                 const float* __restrict__ fmt_stats, int force_fmt) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_pad) return;
+  const bool f16 = force_fmt >= 0 ? force_fmt == 1 : use_fp16(fmt_stats);
+  unsigned short* dst16 = reinterpret_cast<unsigned short*>(dst);
   float ss = 0.f, sb = 0.f, sd = 0.f;
   for (int c = lane; c < k_pad; c += 32) {
     float v = 0.f;
     if (row < n && c < r) v = src[row * ld + c];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float vb = __bfloat162float(h);
+    unsigned short bits;
+    float vb;
+    if (f16) {
+      const __half h = __float2half_rn(v);
+      bits = __half_as_ushort(h);
+      vb = __half2float(h);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      bits = __bfloat16_as_ushort(h);
+      vb = __bfloat162float(h);
+    }
     const float d = v - vb;  // exact
     ss = fmaf(v, v, ss);
     sb = fmaf(vb, vb, sb);
     sd = fmaf(d, d, sd);
     // padded ITEM rows are NaN: their scores are NaN in every accumulator row, which fmaxf ignores and every
     // >= test rejects -- the epilogue needs no per-column bounds checks
-    dst[row * k_pad + c] = (nan_pad && row >= n) ? __ushort_as_bfloat16((unsigned short)0x7FC0) : h;
+    dst16[row * k_pad + c] = (nan_pad && row >= n) ? (unsigned short)(f16 ? 0x7E00 : 0x7FC0) : bits;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1408,7 +1483,7 @@ extern "C" int tmf_pack_bf16(const float* src, int64_t n, int32_t n_comp, int32_
   TMF_REQUIRE(n_pad >= n && k_pad >= n_comp && n_comp <= ld, "tmf_pack_bf16: bad shape");
   if (n_pad == 0) return TMF_OK;
   pack_bf16_kernel<<<(unsigned)cdiv(n_pad * 32, 256), 256, 0, as_stream(stream)>>>(src, n, n_comp, ld, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                                                n_pad, k_pad, norms, nullptr, nullptr, nullptr, 0);
+                                                                                n_pad, k_pad, norms, nullptr, nullptr, nullptr, 0, nullptr, 0);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }
@@ -1420,7 +1495,7 @@ extern "C" size_t tmf_score_topk_ws_bytes(int64_t n_users, int64_t n_items, int3
 
 static int score_topk_impl(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                            int32_t k, int32_t clamp, int32_t item_offset, int32_t* out_idx, float* out_score, void* ws,
-                           size_t ws_bytes, tmf_stream_t stream, float* dump, const float* row_bound = nullptr) {
+                           size_t ws_bytes, tmf_stream_t stream, float* dump, const float* row_bound = nullptr, int force_fmt = -1) {
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && n_comp > 0 && n_comp <= ld, "tmf_score_topk: bad shape");
   TMF_REQUIRE(n_comp <= MAX_KB * BK, "tmf_score_topk: n_components up to %d supported", MAX_KB * BK);
   TMF_REQUIRE(k >= 1 && k <= 128 && k <= n_items, "tmf_score_topk: need 1 <= k <= min(128, n_items) (k=%d)", k);
@@ -1446,10 +1521,21 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   TMF_CUDA(cudaMemsetAsync(vmax_bits, 0, 8, st));
   TMF_CUDA(cudaMemsetAsync(ovfc, 0, 4, st));
+  if (force_fmt < 0) {
+    const char* e = getenv("TMF_TOPK_FMT");  // A/B aid: "bf16" / "f16"
+    if (e) force_fmt = (e[0] == 'f' || e[0] == 'h') ? 1 : 0;
+  }
+  float* fmt_stats = reinterpret_cast<float*>(w + L.off_vmax + 16);  // 8 floats inside the 256-byte scalar block
+  if (force_fmt < 0) {
+    TMF_CUDA(cudaMemsetAsync(fmt_stats, 0, 32, st));
+    const int sgrid = 8 * kNumSMs;
+    operand_stats_kernel<<<sgrid, 256, 0, st>>>(U, n_users, n_comp, ld, fmt_stats);
+    operand_stats_kernel<<<sgrid, 256, 0, st>>>(V, n_items, n_comp, ld, fmt_stats + 4);
+  }
   pack_bf16_kernel<<<(unsigned)cdiv(L.nu_pad * 32, 256), 256, 0, st>>>(U, n_users, n_comp, ld, Ub, L.nu_pad, L.k_pad, nullptr, unorm, ures,
-                                                                       nullptr, 0);
+                                                                       nullptr, 0, fmt_stats, force_fmt);
   pack_bf16_kernel<<<(unsigned)cdiv(L.ni_pad * 32, 256), 256, 0, st>>>(V, n_items, n_comp, ld, Vb, L.ni_pad, L.k_pad, vnorm, nullptr, nullptr,
-                                                                       vmax_bits, 1);
+                                                                       vmax_bits, 1, fmt_stats, force_fmt);
   row_error_kernel<<<(unsigned)cdiv(L.nu_pad, 256), 256, 0, st>>>(unorm, ures, vmax_bits, L.k_pad, erow, L.nu_pad);
   TMF_LAUNCH_CHECK();
 
@@ -1467,6 +1553,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
   p.dump = dump; p.dump_ld = n_items;
   p.row_bound = row_bound;
+  p.fmt_stats = fmt_stats; p.force_fmt = force_fmt;
   { const char* e = getenv("TMF_TOPK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.prof = nullptr;
   if (getenv("TMF_TOPK_PROF")) {
@@ -1537,5 +1624,12 @@ extern "C" int tmf_score_topk_bounded(const float* U, int64_t n_users, const flo
 extern "C" int tmf_score_dense_bf16(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                                     float* P, void* ws, size_t ws_bytes, tmf_stream_t stream) {
   TMF_REQUIRE(P != nullptr, "tmf_score_dense_bf16: null output");
-  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, 1, 0, 0, nullptr, nullptr, ws, ws_bytes, stream, P);
+  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, 1, 0, 0, nullptr, nullptr, ws, ws_bytes, stream, P, nullptr, 0);
+}
+
+extern "C" int tmf_score_dense_tc(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
+                                  int32_t operand_format, float* P, void* ws, size_t ws_bytes, tmf_stream_t stream) {
+  TMF_REQUIRE(P != nullptr, "tmf_score_dense_tc: null output");
+  TMF_REQUIRE(operand_format >= -1 && operand_format <= 1, "tmf_score_dense_tc: operand_format is -1 (auto), 0 (bf16) or 1 (fp16)");
+  return score_topk_impl(U, n_users, V, n_items, n_comp, ld, 1, 0, 0, nullptr, nullptr, ws, ws_bytes, stream, P, nullptr, operand_format);
 }

@@ -189,28 +189,35 @@ def test_retrieve_user_recs_all_modes():
         assert np.array_equal(got, o.retrieve_user_recs(P, user=user, k=k))
 
 
+@pytest.mark.parametrize("fmt", [0, 1])
 @pytest.mark.parametrize("n_u,n_i,r", [(128, 256, 64), (200, 700, 128), (130, 300, 10), (64, 513, 200)])
-def test_tensor_core_scores_within_stated_error_bound(n_u, n_i, r):
-    """The raw tcgen05 bf16 GEMM scores obey |s~ - s| <= |du||v| + |u~||dv| + accumulation slack, with u~ = bf16(u),
-    du = u - u~ (the premise of the exact top-k; the kernel uses the same bound with the slab maxima of |v|, |dv|)."""
+def test_tensor_core_scores_within_stated_error_bound(n_u, n_i, r, fmt):
+    """The raw tcgen05 GEMM scores obey |s~ - s| <= |du||v| + |u~||dv| + accumulation slack, with u~ = the 16-bit rounding
+    of u in the operand format (0 = bf16, 1 = fp16), du = u - u~ (the premise of the exact top-k; the kernel uses the same
+    bound with the slab maxima of |v|, |dv|)."""
     from teamoflow_b200 import _abi
     from teamoflow_b200.mf._engine import new_storage
     rng = np.random.default_rng(r)
     U = (rng.standard_normal((n_u, r)) * rng.uniform(0.1, 3.0, (n_u, 1))).astype(np.float32)
     V = (rng.standard_normal((n_i, r)) * rng.uniform(0.1, 3.0, (n_i, 1))).astype(np.float32)
-    if n_u >= 200:  # adversarial rows: every component just below a bf16 rounding boundary, all products positive
-        U[:8] = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -20) * (2.0 ** rng.integers(-1, 2, (8, 1))).astype(np.float32)
-        V[:8] = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -20)
+    half_ulp = 2.0 ** -8 if fmt == 0 else 2.0 ** -11
+    if n_u >= 200:  # adversarial rows: every component just below a rounding boundary of the format, all products positive
+        U[:8] = np.float32(1.0 + half_ulp - 2.0 ** -20) * (2.0 ** rng.integers(-1, 2, (8, 1))).astype(np.float32)
+        V[:8] = np.float32(1.0 + half_ulp - 2.0 ** -20)
     Us = new_storage(n_u, r, torch.as_tensor(U, device="cuda")); Vs = new_storage(n_i, r, torch.as_tensor(V, device="cuda"))
     P = torch.full((n_u, n_i), float("nan"), device="cuda")
     ws_bytes = _abi.query("tmf_score_topk_ws_bytes", n_u, n_i, r, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
-    _abi.call("tmf_score_dense_bf16", _abi.ptr(Us), n_u, _abi.ptr(Vs), n_i, r, Us.shape[1], _abi.ptr(P), _abi.ptr(ws), ws_bytes)
+    _abi.call("tmf_score_dense_tc", _abi.ptr(Us), n_u, _abi.ptr(Vs), n_i, r, Us.shape[1], fmt, _abi.ptr(P), _abi.ptr(ws), ws_bytes)
+    if fmt == 0:  # the older entry point is the bf16 case
+        P0 = torch.full((n_u, n_i), float("nan"), device="cuda")
+        _abi.call("tmf_score_dense_bf16", _abi.ptr(Us), n_u, _abi.ptr(Vs), n_i, r, Us.shape[1], _abi.ptr(P0), _abi.ptr(ws), ws_bytes)
+        assert torch.equal(P, P0)
     torch.cuda.synchronize()
     got = cpu(P).astype(np.float64)
     exact = U.astype(np.float64) @ V.astype(np.float64).T
-    Ub = torch.as_tensor(U).bfloat16().float().numpy().astype(np.float64)
-    Vb = torch.as_tensor(V).bfloat16().float().numpy().astype(np.float64)
+    rnd = (lambda X: torch.as_tensor(X).bfloat16().float().numpy()) if fmt == 0 else (lambda X: torch.as_tensor(X).half().float().numpy())
+    Ub, Vb = rnd(U).astype(np.float64), rnd(V).astype(np.float64)
     nrm = lambda X: np.linalg.norm(X, axis=1)  # noqa: E731
     k_pad = (r + 63) // 64 * 64
     bound = (nrm(U - Ub)[:, None] * nrm(V.astype(np.float64))[None, :] + nrm(Ub)[:, None] * nrm(V - Vb)[None, :]
@@ -218,11 +225,36 @@ def test_tensor_core_scores_within_stated_error_bound(n_u, n_i, r):
     assert np.isfinite(got).all()
     err = np.abs(got - exact)
     assert (err <= bound + 1e-30).all(), f"max err/bound = {(err / bound).max():.3f}"
-    # and it really is a bf16-operand product, not something sloppier: typical error well inside the bound
-    assert np.median(err / bound) < 0.25
-    if n_u >= 200:  # the adversarial block really exceeds the naive 2^-8 |u||v| figure: the bound must come from the data
-        naive = (1.05 / 256) * nrm(U.astype(np.float64))[:8, None] * nrm(V.astype(np.float64))[None, :8]
+    # and it really is a product of operands rounded to that format, not something sloppier
+    assert np.median(err / bound) < 0.3
+    if n_u >= 200:  # the adversarial block really exceeds the naive one-half-ulp figure: the bound must come from the data
+        naive = 1.05 * half_ulp * nrm(U.astype(np.float64))[:8, None] * nrm(V.astype(np.float64))[None, :8]
         assert (err[:8, :8] > naive).all()
+
+
+def test_operand_format_follows_the_data():
+    """fp16 operands where they round the embeddings better, bf16 where a component would overflow fp16 or sits in its
+    subnormal range -- and the top-k is exact either way."""
+    from teamoflow_b200 import _abi
+    from teamoflow_b200.mf._engine import new_storage
+    rng = np.random.default_rng(8)
+    n_u, n_i, r = 128, 256, 64
+    base_u = rng.standard_normal((n_u, r)).astype(np.float32)
+    base_v = rng.standard_normal((n_i, r)).astype(np.float32)
+    for scale, want in ((0.1, "f16"), (1e5, "bf16"), (1e-7, "bf16")):
+        U, V = base_u * np.float32(scale), base_v * np.float32(scale if scale < 1 else 1.0)
+        Us = new_storage(n_u, r, torch.as_tensor(U, device="cuda")); Vs = new_storage(n_i, r, torch.as_tensor(V, device="cuda"))
+        ws_bytes = _abi.query("tmf_score_topk_ws_bytes", n_u, n_i, r, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        P = {}
+        for fmt in (-1, 0, 1):
+            P[fmt] = torch.full((n_u, n_i), float("nan"), device="cuda")
+            _abi.call("tmf_score_dense_tc", _abi.ptr(Us), n_u, _abi.ptr(Vs), n_i, r, Us.shape[1], fmt, _abi.ptr(P[fmt]), _abi.ptr(ws), ws_bytes)
+        torch.cuda.synchronize()
+        assert torch.equal(P[-1], P[1] if want == "f16" else P[0]), (scale, want)
+        idx, sc = fused_topk(U, V, 10, False)
+        widx, wsc = oracle_topk(U, V, 10, False)
+        assert np.array_equal(idx, widx) and np.array_equal(sc, wsc)
 
 
 def test_topk_exact_with_adversarial_bf16_rounding():
