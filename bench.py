@@ -40,6 +40,9 @@ WORKLOADS = {
                desc="ML-100K-shaped synthetic: 943 x 1682, 100k interactions (ratings>=4 positive), rank 32, WMRB S=336"),
     "c1": dict(n_u=1000, n_i=1000, nnz=10_000, r=10, S=0, mu=None, mi=None,
                desc="toy 1k x 1k, density 0.01, rank 10, MSE"),
+    # BASELINE.json configs[3]: ONE 10M x 2M problem, user-sharded over the ranks (strong scaling; per-rank sizes = total / world)
+    "c4": dict(n_u=10_000_000, n_i=2_000_000, nnz=500_000_000, r=128, S=32, mu=None, mi=None, strong=True,
+               desc="10M users x 2M items, 500M interactions, rank 128, WMRB S=32, identity features, user-sharded data parallel"),
     "c4mini": dict(n_u=1_250_000, n_i=2_000_000, nnz=62_500_000, r=128, S=32, mu=None, mi=None,
                    desc="1/8 user shard of the 10M x 2M, 500M-interaction rank-128 WMRB S=32 problem"),
 }
@@ -168,11 +171,13 @@ class Workload:
         from teamoflow_b200.mf import initializer_graphs as I, loss_graphs as L
         from teamoflow_b200.mf.matrix_factorization import MatrixFactorization
         from teamoflow_b200.mf.utils import random_sampler
-        self.w = w = WORKLOADS[name]
+        self.w = w = dict(WORKLOADS[name])
+        if w.get("strong"):  # one fixed problem split over the ranks
+            w["n_u"], w["nnz"] = w["n_u"] // world, w["nnz"] // world
         self.name, self.rank, self.world = name, rank, world
         dev = torch.device("cuda", torch.cuda.current_device())
         n_u, n_i, r, S = w["n_u"], w["n_i"], w["r"], w["S"]
-        seed = 20240 + {"c1": 1, "c2": 2, "c3": 3, "c4mini": 4}[name]
+        seed = 20240 + {"c1": 1, "c2": 2, "c3": 3, "c4mini": 4, "c4": 4}[name]
         t0 = time.time()
         rows, cols = gen_interactions(n_u, n_i, w["nnz"], seed * 1000 + rank, dev)
         self.nnz = int(rows.numel())
@@ -384,7 +389,7 @@ def cpu_reference_step(wl_name, budget_s=20.0, n_sub=None):
     w = WORKLOADS[wl_name]
     n_i, r, S = w["n_i"], w["r"], w["S"]
     if n_sub is None:
-        n_sub = {"c3": 1024, "c2": 943, "c1": 1000, "c4mini": 64}[wl_name]
+        n_sub = {"c3": 1024, "c2": 943, "c1": 1000, "c4mini": 64, "c4": 64}[wl_name]
     n_sub = min(n_sub, w["n_u"])
     rng = np.random.default_rng(7)
     per_user = max(1, w["nnz"] // w["n_u"])
@@ -480,6 +485,7 @@ def main():
         return
 
     wl = Workload(args.workload, rank, world)
+    w = wl.w  # per-rank sizes (differs from WORKLOADS[...] for strong-scaling workloads)
     comm = None
     if world > 1:
         comm = tdist.GradientSync(shared_user_rows=w["n_u"] if w["mu"] else None)
@@ -548,7 +554,7 @@ def main():
                        f"{float(dt):.3f} s total, final loss {final_loss:.5f}"}
 
     out = {"metric": metric, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": w["desc"], "n_users_per_gpu": w["n_u"], "n_items": w["n_i"], "nnz_per_gpu": wl.nnz, "rank": w["r"],
                       "n_samples": w["S"], "parallelism": f"user-sharded dp{world}" if world > 1 else "single GPU",
