@@ -117,6 +117,19 @@ def main():
                 same, msg = False, f"ERROR {e}"
             print(f"[rank {rank}] sharded top-k clamp={clamp} exchange={exchange} bound={bound}: {msg}", flush=True)
             ok = ok and same
+    # ---- ragged shapes: user count not divisible by the ranks, slabs smaller than k (padded lists), grid-valued ties
+    for nu3, ni3, r3, k3 in ((1001, 40 * world + 3, 16, 50), (257, 997, 24, 20)):
+        g3 = torch.Generator(device="cuda"); g3.manual_seed(6)
+        U3 = new_storage(nu3, r3); U3[:, :r3] = torch.randint(-4, 5, (nu3, r3), generator=g3, device="cuda").float() / 8
+        V3 = new_storage(ni3, r3); V3[:, :r3] = torch.randint(-4, 5, (ni3, r3), generator=g3, device="cuda").float() / 8
+        ib3 = tdist.shard_bounds(ni3, world)
+        for clamp in (False, True):
+            idx1, sc1 = score_topk(U3, V3, r3, k3, clamp)
+            for exchange, bound in (("peer", "force"), ("nccl", "force"), ("auto", True)):
+                idx, sc = tdist.sharded_topk(U3, V3[ib3[rank]:ib3[rank + 1]].contiguous(), r3, k3, clamp, ib3[rank], exchange=exchange, bound=bound)
+                same = bool(torch.equal(idx, idx1) and torch.equal(sc, sc1))
+                print(f"[rank {rank}] ragged {nu3}x{ni3} k={k3} clamp={clamp} exchange={exchange} bound={bound}: {'exact' if same else 'MISMATCH'}", flush=True)
+                ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
