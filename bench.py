@@ -258,6 +258,14 @@ def profile_phases(plan, lr, reps=3):
 # ------------------------------------------------------------------------------------------- top-k bench
 
 
+def _topk_traffic(n_u, n_i, world):
+    """DRAM bytes per launch of the dominant top-k kernel from the committed ncu capture (only for the captured shape)."""
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if world == 1 and n_u == 1_000_000 and n_i == 1_000_000 and os.path.exists(tpath):
+        return json.load(open(tpath)).get("score_topk_kernel")
+    return None
+
+
 def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     from teamoflow_b200 import _abi
     from teamoflow_b200.mf import dist as tdist
@@ -372,7 +380,8 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
                        "exchange": (tdist.exchange_mode() + " (bounds all-gathered, lists merged over NVLink peer memory)") if world > 1 else "none"},
             "dtype": "16-bit tensor-core operands (fp16 or bf16, chosen from the data), fp32 accumulate in TMEM, fp64-accumulated rerank",
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": None},
+                         "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": _topk_traffic(n_u, n_i, world),
+                         "traffic_note": "DRAM bytes of one score_topk_kernel launch (262,144 users x 1M items) from the committed ncu --set full capture"},
             "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
                     "d2h_bytes_per_step": out.numel() * 4},
             "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded, "recall_path": recall,
