@@ -67,6 +67,36 @@ __device__ __forceinline__ void fma4(float4& acc, float c, const float4& r) {
   acc.w = fmaf(c, r.w, acc.w);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2, two IEEE fp32 results per issue slot)
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  float2 r;
+  asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};"
+      " fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd; }"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; callers guarantee a normal x
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// 16-byte global -> shared asynchronous copy (LDGSTS: no register staging); both addresses 16-byte aligned
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void add4(float4& acc, const float4& r) {
   acc.x += r.x;
   acc.y += r.y;

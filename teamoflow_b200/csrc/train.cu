@@ -19,7 +19,7 @@ namespace tmf {
 // =====================================================================================
 
 struct UserPassParams {
-  int n_users, n_items, ld, n_comp, n_samples, s_pad, cache_rows;
+  int n_users, n_items, ld, n_comp, n_samples, s_pad;
   long long nnz;
   const int* row_ptr;
   const int* col_idx;
@@ -51,6 +51,16 @@ __device__ __forceinline__ void load_row(const float* __restrict__ base, long lo
   }
 }
 
+// Item-row gather for the hot loops: per-lane base pointers with the lane's column CLAMPED into the row (lanes past the
+// row's end re-read its last 16 bytes; their user-row entries are zero and their results are never stored), so a row
+// address is one 32x32+64-bit multiply-add and the load needs neither a predicate nor a zero fill.
+template <int VPL>
+__device__ __forceinline__ void load_item(const char* const (&lane_base)[VPL], int row, unsigned ld_bytes, float4 (&x)[VPL]) {
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+    x[v] = __ldg(reinterpret_cast<const float4*>(lane_base[v] + (unsigned long long)(unsigned)row * ld_bytes));
+}
+
 template <int VPL>
 __device__ __forceinline__ float dotv(const float4 (&a)[VPL], const float4 (&b)[VPL]) {
   float s = dot4(a[0], b[0]);
@@ -59,7 +69,7 @@ __device__ __forceinline__ float dotv(const float4 (&a)[VPL], const float4 (&b)[
   return s;
 }
 
-constexpr int kUserPassThreads = 256;
+constexpr int kUserPassThreads = 32;
 
 // full-warp shuffles (constant mask, sub-warp width): every loop below is warp-uniform so that no variable-mask
 // convergence checks (MATCH/REDUX/BRA.DIV, ~6 instructions per shuffle group) are generated
@@ -70,17 +80,22 @@ __device__ __forceinline__ float gsum(float v) {
   return v;
 }
 
+// One WARP per work item (a CTA is one warp, up to 32 of them resident per SM): the phases of a user are separated by
+// warp-level synchronisation only, and many users per SM are in flight in different phases.  (The first version gave a
+// user to a 256-thread CTA: 4 CTAs per SM, five block barriers per user and shared-memory reductions over 16 row groups --
+// 2.93 ms per C3 epoch against 1.9 ms for this layout.)
 // JPL > 0 : each lane keeps JPL sample scores and JPL partial G sums in registers (S <= LPR*JPL)
 // JPL == 0: MSE (no samples)
 // JPL < 0 : generic WMRB, per-group G partials in shared memory
 template <int LPR, int VPL, int JPL, int LOSS>
-__global__ void __launch_bounds__(kUserPassThreads, (JPL >= 0 && JPL <= 8 && VPL == 1) ? 4 : 2)
+__global__ void __launch_bounds__(kUserPassThreads, (JPL >= 0 && JPL <= 8 && VPL == 1) ? 32 : 16)
 user_pass_kernel(const UserPassParams p) {
   constexpr int NT = kUserPassThreads;
+  static_assert(NT == 32, "one warp per work item");
   constexpr int NG = NT / LPR;
-  constexpr int JR = JPL > 0 ? JPL : 1;
+  constexpr int JH = JPL > 0 ? JPL / 2 : 1;
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
-  __shared__ int s_next;
   const int tid = threadIdx.x;
   const int g = tid / LPR;
   const int lg = tid % LPR;
@@ -88,16 +103,16 @@ user_pass_kernel(const UserPassParams p) {
   const int nv = ld >> 2;
   const int S = p.n_samples;
   float* sS = smem;                     // [s_pad]  sample scores, later final G_j
-  float* sG = sS + p.s_pad;             // [NG][s_pad] per-group partial G
-  float* sAcc = sG + (LOSS == TMF_LOSS_WMRB ? NG * p.s_pad : 0);  // [NG][ld]
-  float* sRows = sAcc + NG * ld;        // [S][ld] optional cache of the sampled item rows
+  float* sG = sS + p.s_pad;             // [NG][s_pad] per-group partial G (generic path only)
 
+  // work items come from an atomic counter; the NEXT item is claimed while the current one is processed
+  int next = 0;
+  if (tid == 0) next = atomicAdd(p.counter, 1);
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_next = atomicAdd(p.counter, 1);
-    __syncthreads();
-    const int t_work = s_next;
+    __syncwarp();  // shared-memory reuse across work items
+    const int t_work = __shfl_sync(FULL, next, 0);
     if (t_work >= p.n_work) break;
+    if (tid == 0) next = atomicAdd(p.counter, 1);
     // a work item is a whole user or, for very heavy users, one slice of its interactions (load balance: a user
     // with millions of interactions would otherwise be one CTA's serial tail)
     const int u = p.work_user ? p.work_user[t_work] : t_work;
@@ -113,10 +128,14 @@ user_pass_kernel(const UserPassParams p) {
     }
 
     float4 eu[VPL];
-    load_row<LPR, VPL>(p.Eu, u, ld, nv, lg, eu);
+    load_row<LPR, VPL>(p.Eu, u, ld, nv, lg, eu);  // zero past the row's end
+    const char* ei_lane[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) ei_lane[v] = reinterpret_cast<const char*>(p.Ei) + 16 * min(lg + LPR * v, nv - 1);
+    const unsigned ld_bytes = 4u * (unsigned)ld;
 
-    float sj[JR];
-    float gj[JR];
+    float2 sj2[JH];  // this lane's sample scores, two per register pair (FADD2 / FFMA2 operands)
+    float2 gj2[JH];  // ... and its partial G sums
     if constexpr (LOSS == TMF_LOSS_WMRB) {
       const int* su = p.samp + (long long)u * S;
       const int n_sit = (S + NG * 4 - 1) / (NG * 4);
@@ -127,33 +146,26 @@ user_pass_kernel(const UserPassParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) idx[q] = (j0 + q < S) ? su[j0 + q] : 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) load_row<LPR, VPL>(p.Ei, idx[q], ld, nv, lg, row[q]);
+        for (int q = 0; q < 4; ++q) load_item<VPL>(ei_lane, idx[q], ld_bytes, row[q]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = j0 + q;
           const float s = gsum<LPR>(dotv<VPL>(eu, row[q]));
-          if (j < S) {
-            if (lg == 0) sS[j] = s;
-            if (p.cache_rows) {
-#pragma unroll
-              for (int v = 0; v < VPL; ++v) {
-                const int col = lg + LPR * v;
-                if (col < nv) reinterpret_cast<float4*>(sRows + (long long)j * ld)[col] = row[q][v];
-              }
-            }
-          }
+          if (j < S && lg == 0) sS[j] = s;
         }
       }
       if constexpr (JPL < 0) {
         for (int j = lg; j < S; j += LPR) sG[g * p.s_pad + j] = 0.f;
       }
-      __syncthreads();
+      __syncwarp();
       if constexpr (JPL > 0) {
+        // padding slots hold a large negative FINITE score: their hinge is negative, so the indicator is 0 and
+        // 0 * h stays a (signed) zero in the FFMA2 below (an infinity would turn it into NaN)
 #pragma unroll
-        for (int t = 0; t < JPL; ++t) {
-          const int j = lg + LPR * t;
-          sj[t] = (j < S) ? sS[j] : -INFINITY;
-          gj[t] = 0.f;
+        for (int t = 0; t < JH; ++t) {
+          const int j0 = lg + LPR * (2 * t), j1 = lg + LPR * (2 * t + 1);
+          sj2[t] = make_float2((j0 < S) ? sS[j0] : -1e30f, (j1 < S) ? sS[j1] : -1e30f);
+          gj2[t] = make_float2(0.f, 0.f);
         }
       }
     }
@@ -162,62 +174,51 @@ user_pass_kernel(const UserPassParams p) {
 #pragma unroll
     for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    // ---- interactions of this user, strided over the NG row groups; warp-uniform trip count, next row prefetched.
-    // Each lane parks the (loss argument, coefficient) of ONE of every LPR consecutive iterations, so the ~30-instruction
-    // logf and the two stores run once per LPR interactions instead of once per interaction.
-    const int n_it = (b - a + NG - 1) / NG;
-    int k = a + g;
-    float4 row_n[VPL];
-    float v_n = 0.f;
-    {
-      const int kc = min(k, b - 1);
-      v_n = (k < b) ? p.val[kc] : 0.f;
-      load_row<LPR, VPL>(p.Ei, p.col_idx[kc], ld, nv, lg, row_n);
-    }
-    float keep_d = 1.0f, keep_c = 0.f;  // parked: 1 + m (0 when the interaction carries no WMRB loss) and c
-    int keep_k = -1;
-    for (int it = 0; it < n_it; ++it, k += NG) {
-      float4 row[VPL];
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) row[v] = row_n[v];
-      const float a_k = v_n;
+    // ---- interactions of this user, strided over the NG row groups; warp-uniform trip count.  One interaction per
+    // row group and iteration: score, S hinge terms (each lane owns JPL of them, evaluated two at a time with packed
+    // fp32x2 instructions), dL/dscore, and acc += c * row while the row is still in registers.  Lane 0 of the group
+    // stores (1 + m, c); the logarithm is applied by a coalesced in-place pass after the loop.
+    auto process = [&](const float4 (&row)[VPL], const float a_k, const int k) {
       const bool active = k < b;
-      {
-        const int kn = k + NG;
-        const int kc = min(kn, b - 1);
-        v_n = (kn < b) ? p.val[kc] : 0.f;
-        load_row<LPR, VPL>(p.Ei, p.col_idx[kc], ld, nv, lg, row_n);
-      }
       const float pk = gsum<LPR>(dotv<VPL>(eu, row));
       float c = 0.f, d = 0.f;
       if constexpr (LOSS == TMF_LOSS_MSE) {
         const float df = a_k - pk;  // loss_graphs.py:52
-        d = df;
+        d = df * df;
         c = active ? -2.0f * df : 0.f;
       } else {
         const float base = __fsub_rn(1.0f, pk);
         const bool pos = active && a_k > 0.f;  // loss_graphs.py:74
-        float sum = 0.f, cnt = 0.f;
+        float sum, cnt;
         if constexpr (JPL > 0) {
-          bool ind[JPL];
+          const float2 base2 = make_float2(base, base);
+          float2 ind2[JH];
+          float2 sum2 = make_float2(0.f, 0.f), cnt2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int t = 0; t < JPL; ++t) {
-            const float h = __fadd_rn(base, sj[t]);   // (1 - p) + s, loss_graphs.py:84
-            sum += fmaxf(h, 0.f);                      // tf.maximum(h, 0)
-            ind[t] = h >= 0.f;                         // its gradient goes to h when h >= 0
-            cnt += ind[t] ? 1.f : 0.f;
+          for (int t = 0; t < JH; ++t) {
+            const float2 h2 = fadd2(base2, sj2[t]);             // (1 - p) + s, loss_graphs.py:84
+            ind2[t] = make_float2(h2.x >= 0.f ? 1.f : 0.f,      // tf.maximum(h, 0): value h and gradient 1 when h >= 0
+                                  h2.y >= 0.f ? 1.f : 0.f);
+            sum2 = ffma2(ind2[t], h2, sum2);                    // 1 * h + sum rounds once, like the plain add
+            cnt2 = fadd2(cnt2, ind2[t]);
           }
-          sum = gsum<LPR>(sum);
-          cnt = gsum<LPR>(cnt);
-          const float m = p.scale * sum;                 // :86
-          d = __fadd_rn(1.0f, m);
-          const float w = pos ? __fdividef(p.scale, d) : 0.f;
-          c = -w * cnt;
+          float2 sc = make_float2(sum2.x + sum2.y, cnt2.x + cnt2.y);
 #pragma unroll
-          for (int t = 0; t < JPL; ++t)
-            if (ind[t]) gj[t] += w;
-          if (!pos) d = 0.f;
+          for (int o = LPR / 2; o > 0; o >>= 1)
+            sc = fadd2(sc, make_float2(__shfl_xor_sync(0xffffffffu, sc.x, o, LPR), __shfl_xor_sync(0xffffffffu, sc.y, o, LPR)));
+          sum = sc.x;
+          cnt = sc.y;
+          const float m = p.scale * sum;                 // :86
+          d = __fadd_rn(1.0f, m);                        // >= 1: m is a sum of non-negative terms
+          const float w = pos ? p.scale * rcp_approx(d) : 0.f;
+          c = -w * cnt;
+          const float2 w2 = make_float2(w, w);
+#pragma unroll
+          for (int t = 0; t < JH; ++t) gj2[t] = ffma2(ind2[t], w2, gj2[t]);
+          if (!pos) d = 1.0f;                            // log(1) = 0: no loss for non-positive interactions
         } else {
+          sum = 0.f;
+          cnt = 0.f;
           for (int j = lg; j < S; j += LPR) {
             const float h = __fadd_rn(base, sS[j]);
             sum += fmaxf(h, 0.f);
@@ -235,77 +236,103 @@ user_pass_kernel(const UserPassParams p) {
               if (h >= 0.f) sG[g * p.s_pad + j] += w;
             }
           }
-          if (!pos) d = 0.f;
+          if (!pos) d = 1.0f;
         }
       }
 #pragma unroll
       for (int v = 0; v < VPL; ++v) fma4(acc[v], c, row[v]);
-      if ((it & (LPR - 1)) == lg) {
-        keep_d = d;
-        keep_c = c;
-        keep_k = active ? k : -1;
+      if (lg == 0 && active) {
+        p.loss_out[k] = d;
+        p.coef_out[k] = c;
       }
-      if ((it & (LPR - 1)) == LPR - 1 || it == n_it - 1) {  // warp-uniform: flush the parked results
-        if (keep_k >= 0) {
-          float l;
-          if constexpr (LOSS == TMF_LOSS_MSE) l = keep_d * keep_d;
-          else l = keep_d > 0.f ? logf(keep_d) : 0.f;   // log(1 + m), :88
-          p.loss_out[keep_k] = l;
-          p.coef_out[keep_k] = keep_c;
+    };
+    // Two-stage software pipeline: (item id, value) of an interaction are fetched two iterations ahead, its row one
+    // iteration ahead, so neither the id -> row dependency nor the row's L2 latency sits on the critical path.
+    // Indices past the slice are clamped (a tail iteration re-reads the last row and is masked by `active`).
+    auto fetch_idx = [&](int& idx, float& a_k, const int k) {
+      const int kc = min(k, b - 1);
+      idx = p.col_idx[kc];
+      a_k = p.val[kc];
+    };
+    {
+      const int n_it = (b - a + NG - 1) / NG;
+      int k = a + g;
+      float4 row_a[VPL], row_b[VPL];  // two row buffers (no register copies)
+      int i_a, i_b;
+      float v_a, v_b;
+      fetch_idx(i_a, v_a, k);
+      fetch_idx(i_b, v_b, k + NG);
+      load_item<VPL>(ei_lane, i_a, ld_bytes, row_a);
+      for (int it = 0; it < n_it; it += 2, k += 2 * NG) {
+        load_item<VPL>(ei_lane, i_b, ld_bytes, row_b);
+        const float va = v_a;
+        fetch_idx(i_a, v_a, k + 2 * NG);
+        process(row_a, va, k);
+        if (it + 1 < n_it) {  // warp-uniform
+          load_item<VPL>(ei_lane, i_a, ld_bytes, row_a);
+          const float vb = v_b;
+          fetch_idx(i_b, v_b, k + 3 * NG);
+          process(row_b, vb, k + NG);
         }
-        keep_k = -1;
       }
     }
 
     if constexpr (LOSS == TMF_LOSS_WMRB) {
+      __syncwarp();  // every lane's (1 + m) stores are visible to the warp; sS (sample scores) is no longer read
+      for (int k = a + tid; k < b; k += NT) p.loss_out[k] = logf(p.loss_out[k]);  // log(1 + m), loss_graphs.py:88
       if constexpr (JPL > 0) {
+        // G_j = sum of the row groups' partial sums (xor tree over the groups: fixed order => deterministic)
 #pragma unroll
-        for (int t = 0; t < JPL; ++t) {
-          const int j = lg + LPR * t;
-          if (j < S) sG[g * p.s_pad + j] = gj[t];
+        for (int t = 0; t < JH; ++t) {
+#pragma unroll
+          for (int o = LPR; o < 32; o <<= 1) {
+            gj2[t].x += __shfl_xor_sync(FULL, gj2[t].x, o);
+            gj2[t].y += __shfl_xor_sync(FULL, gj2[t].y, o);
+          }
+          if (g == 0) {
+            const int j0 = lg + LPR * (2 * t), j1 = lg + LPR * (2 * t + 1);
+            float* dst = slot < 0 ? p.coef_out + p.nnz + (long long)u * S   // whole user
+                                  : p.part_G + (long long)slot * p.s_pad;   // slice: summed by the fix-up kernel
+            if (j0 < S) { dst[j0] = gj2[t].x; sS[j0] = gj2[t].x; }
+            if (j1 < S) { dst[j1] = gj2[t].y; sS[j1] = gj2[t].y; }
+          }
+        }
+      } else {
+        for (int j = tid; j < S; j += NT) {  // fixed group order => deterministic
+          float G = sG[j];
+          for (int gg = 1; gg < NG; ++gg) G += sG[gg * p.s_pad + j];
+          if (slot < 0) p.coef_out[p.nnz + (long long)u * S + j] = G;
+          else p.part_G[(long long)slot * p.s_pad + j] = G;
+          sS[j] = G;
         }
       }
-      __syncthreads();
-      for (int j = tid; j < S; j += NT) {  // fixed group order => deterministic
-        float G = sG[j];
-        for (int gg = 1; gg < NG; ++gg) G += sG[gg * p.s_pad + j];
-        if (slot < 0) p.coef_out[p.nnz + (long long)u * S + j] = G;
-        else p.part_G[(long long)slot * p.s_pad + j] = G;   // summed over the user's slices by the fix-up kernel
-        sS[j] = G;
-      }
-      __syncthreads();
+      __syncwarp();
       const int* su = p.samp + (long long)u * S;
 #pragma unroll 4
       for (int j = (slot < 0 ? g : S); j < S; j += NG) {  // split users: the sample term is added once, in the fix-up
         const float G = sS[j];
         float4 row[VPL];
-        if (p.cache_rows) {
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            const int col = lg + LPR * v;
-            row[v] = (col < nv) ? reinterpret_cast<const float4*>(sRows + (long long)j * ld)[col]
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        } else {
-          load_row<LPR, VPL>(p.Ei, su[j], ld, nv, lg, row);
-        }
+        load_item<VPL>(ei_lane, su[j], ld_bytes, row);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) fma4(acc[v], G, row[v]);
       }
     }
 
-    // ---- dE_u[u] = sum over groups (fixed order)
+    // ---- dE_u[u] = sum over the row groups (xor tree: fixed order)
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        acc[v].x += __shfl_xor_sync(FULL, acc[v].x, o);
+        acc[v].y += __shfl_xor_sync(FULL, acc[v].y, o);
+        acc[v].z += __shfl_xor_sync(FULL, acc[v].z, o);
+        acc[v].w += __shfl_xor_sync(FULL, acc[v].w, o);
+      }
       const int col = lg + LPR * v;
-      if (col < nv) reinterpret_cast<float4*>(sAcc + g * ld)[col] = acc[v];
-    }
-    __syncthreads();
-    for (int c = tid; c < ld; c += NT) {
-      float s = sAcc[c];
-      for (int gg = 1; gg < NG; ++gg) s += sAcc[gg * ld + c];
-      if (slot < 0) p.dEu[(long long)u * ld + c] = s;
-      else p.part_E[(long long)slot * ld + c] = s;
+      if (g == 0 && col < nv) {
+        float* dst = slot < 0 ? p.dEu + (long long)u * ld : p.part_E + (long long)slot * ld;
+        reinterpret_cast<float4*>(dst)[col] = acc[v];
+      }
     }
   }
 }
@@ -351,12 +378,9 @@ template <int LPR, int VPL, int JPL, int LOSS>
 static int launch_user_pass(const UserPassParams& p, cudaStream_t st) {
   constexpr int NG = kUserPassThreads / LPR;
   auto kern = user_pass_kernel<LPR, VPL, JPL, LOSS>;
-  size_t base = (size_t)NG * p.ld * sizeof(float);
-  if (LOSS == TMF_LOSS_WMRB) base += (size_t)(1 + NG) * p.s_pad * sizeof(float);
+  size_t smem = 0;
+  if (LOSS == TMF_LOSS_WMRB) smem = (size_t)(1 + (JPL < 0 ? NG : 0)) * p.s_pad * sizeof(float);
   UserPassParams q = p;
-  size_t rows = (LOSS == TMF_LOSS_WMRB) ? (size_t)p.n_samples * p.ld * sizeof(float) : 0;
-  q.cache_rows = (LOSS == TMF_LOSS_WMRB) && (base + rows <= 56 * 1024);
-  size_t smem = base + (q.cache_rows ? rows : 0);
   TMF_REQUIRE(smem <= 200 * 1024, "tmf_user_pass: n_samples=%d too large for shared memory (%zu B)", p.n_samples, smem);
   if (smem > 48 * 1024) TMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 1;

@@ -245,7 +245,7 @@ class InteractionPlan:
                   _abi.ptr(self.t_user))
 
     # users with more interactions than this are processed as several slices (load balance, tmf_user_pass)
-    SPLIT = 4096
+    SPLIT = 1024
 
     def _build_work_list(self):
         """Work items of the user pass: whole users, or SPLIT-sized slices of very heavy users, heaviest first."""
