@@ -442,53 +442,87 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_seg_kernel(const SpmmParams
     if ((long long)p.seg_ptr[mid] <= cs) lo = mid; else hi = mid - 1;
   }
   int s = lo;
-  long long e = cs;
-  while (e < ce) {
-    long long sb = p.seg_ptr[s + 1];
-    while (sb <= e) { ++s; sb = p.seg_ptr[s + 1]; }  // skip empty segments
-    const long long sa = p.seg_ptr[s];
-    const long long pe = min(sb, ce);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    while (e < pe) {
-      const int nb = (int)min((long long)LPR, pe - e);
-      int my_i = 0;
-      float my_c = 0.f;
-      if (lg < nb) {
-        my_i = p.idx[e + lg];
-        my_c = p.coef ? p.coef[p.cpos ? p.cpos[e + lg] : (e + lg)] : 1.0f;
-      }
-      int t = 0;
-      for (; t + 4 <= nb; t += 4) {  // 4 independent row loads in flight, FMAs in entry order
-        const int i0 = __shfl_sync(gm, my_i, t + 0, LPR), i1 = __shfl_sync(gm, my_i, t + 1, LPR);
-        const int i2 = __shfl_sync(gm, my_i, t + 2, LPR), i3 = __shfl_sync(gm, my_i, t + 3, LPR);
-        const float c0 = __shfl_sync(gm, my_c, t + 0, LPR), c1 = __shfl_sync(gm, my_c, t + 1, LPR);
-        const float c2 = __shfl_sync(gm, my_c, t + 2, LPR), c3 = __shfl_sync(gm, my_c, t + 3, LPR);
-        if (active) {
-          const float4 r0 = ldg4(p.src + (long long)i0 * p.ld_src + 4 * col);
-          const float4 r1 = ldg4(p.src + (long long)i1 * p.ld_src + 4 * col);
-          const float4 r2 = ldg4(p.src + (long long)i2 * p.ld_src + 4 * col);
-          const float4 r3 = ldg4(p.src + (long long)i3 * p.ld_src + 4 * col);
-          fma4(acc, c0, r0);
-          fma4(acc, c1, r1);
-          fma4(acc, c2, r2);
-          fma4(acc, c3, r3);
+  long long sb = p.seg_ptr[s + 1];
+  while (sb <= cs) { ++s; sb = p.seg_ptr[s + 1]; }  // skip empty segments
+  long long sa = p.seg_ptr[s];
+  const float* src_lane = p.src + 4 * min(col, p.nv - 1);  // clamped column: inactive lanes re-read a valid one, never store
+  const unsigned long long ld_src = (unsigned long long)p.ld_src;
+
+  // Entries are fetched a batch of LPR ahead (lane t of the group holds entry base + t: index and coefficient), so the
+  // index -> coefficient -> row dependency of the NEXT batch resolves while the rows of the current one are gathered;
+  // rows are gathered eight at a time.  Sums run in entry order: bitwise deterministic.
+  auto fetch = [&](long long base, int& my_i, float& my_c) {
+    const long long e = base + lg;
+    my_i = 0;
+    my_c = 0.f;
+    if (e < ce) {
+      my_i = p.idx[e];
+      my_c = p.coef ? p.coef[p.cpos ? p.cpos[e] : e] : 1.0f;
+    }
+  };
+  int nxt_i;
+  float nxt_c;
+  fetch(cs, nxt_i, nxt_c);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long base = cs; base < ce; base += LPR) {
+    const int my_i = nxt_i;
+    const float my_c = nxt_c;
+    fetch(base + LPR, nxt_i, nxt_c);
+    const int nb = (int)min((long long)LPR, ce - base);
+    int t = 0;
+    while (t < nb) {
+      const int te = (int)min((long long)nb, sb - base);  // entries of this batch that belong to segment s
+      for (; t + 8 <= te; t += 8) {
+        int i[8];
+        float c[8];
+        float4 r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          i[q] = __shfl_sync(gm, my_i, t + q, LPR);
+          c[q] = __shfl_sync(gm, my_c, t + q, LPR);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = ldg4(src_lane + (unsigned long long)(unsigned)i[q] * ld_src);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) fma4(acc, c[q], r[q]);
       }
-      for (; t < nb; ++t) {
+      if (t + 4 <= te) {
+        int i[4];
+        float c[4];
+        float4 r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          i[q] = __shfl_sync(gm, my_i, t + q, LPR);
+          c[q] = __shfl_sync(gm, my_c, t + q, LPR);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = ldg4(src_lane + (unsigned long long)(unsigned)i[q] * ld_src);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fma4(acc, c[q], r[q]);
+        t += 4;
+      }
+      for (; t < te; ++t) {
         const int i0 = __shfl_sync(gm, my_i, t, LPR);
         const float c0 = __shfl_sync(gm, my_c, t, LPR);
-        if (active) fma4(acc, c0, ldg4(p.src + (long long)i0 * p.ld_src + 4 * col));
+        fma4(acc, c0, ldg4(src_lane + (unsigned long long)(unsigned)i0 * ld_src));
       }
-      e += nb;
+      if (base + t == sb || base + t == ce) {  // segment (or this chunk's part of it) complete
+        if (active) {
+          float* dst;
+          if (sa >= cs && sb <= ce) dst = p.out + (long long)s * p.ld_out;
+          else if (sa < cs) dst = p.part_first + gid * p.ld_out;
+          else dst = p.part_carry + gid * p.ld_out;
+          reinterpret_cast<float4*>(dst)[col] = acc;
+        }
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base + t < ce) {
+          ++s;
+          sb = p.seg_ptr[s + 1];
+          while (sb <= base + t) { ++s; sb = p.seg_ptr[s + 1]; }  // skip empty segments
+          sa = p.seg_ptr[s];
+        }
+      }
     }
-    if (active) {
-      float* dst;
-      if (sa >= cs && sb <= ce) dst = p.out + (long long)s * p.ld_out;
-      else if (sa < cs) dst = p.part_first + gid * p.ld_out;
-      else dst = p.part_carry + gid * p.ld_out;
-      reinterpret_cast<float4*>(dst)[col] = acc;
-    }
-    ++s;
   }
 }
 

@@ -448,7 +448,8 @@ def test_heavy_users_are_split_and_still_deterministic_and_exact():
     E, I, L, eng, FM, SI, MF = _mods()
     n_u, n_i, r, S = 6, 9000, 16, 20
     rng = np.random.default_rng(21)
-    lens = [8999, 5000, 4097, 4096, 3, 0]
+    SP = eng.InteractionPlan.SPLIT
+    lens = [2 * SP + 807, SP + 904, SP + 1, SP, 3, 0]  # 3, 2, 2, 1, 1, 0 slices
     rows = np.concatenate([np.full(n, u) for u, n in enumerate(lens)])
     cols = np.concatenate([np.sort(rng.choice(n_i, n, replace=False)) for n in lens]).astype(np.int64)
     vals = rng.choice(np.array([1.0, 2.0, -1.0], np.float32), rows.size)
