@@ -547,22 +547,26 @@ def main():
     e2e = None
     if True:
         from teamoflow_b200.mf.matrix_factorization import MatrixFactorization  # noqa: F401
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        model.fit(args.steps, xu, xi, wl.interactions_host(), lr=wl.lr, comm=comm, verbose=False)
-        final_loss = model._plan.ip.mean_loss() if comm is None else comm.mean_loss(model._plan.ip)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        dt = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+        dts = []
+        for _ in range(3):  # three complete fit() calls from the host buffers; the median is reported
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.fit(args.steps, xu, xi, wl.interactions_host(), lr=wl.lr, comm=comm, verbose=False)
+            final_loss = model._plan.ip.mean_loss() if comm is None else comm.mean_loss(model._plan.ip)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            dti = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                torch.distributed.all_reduce(dti, op=torch.distributed.ReduceOp.MAX)
+            dts.append(float(dti))
+        dt = sorted(dts)[1]
         e2e = {"value": world * wl.nnz * args.steps / float(dt), "unit": "interactions/s",
                "h2d_bytes_per_step": wl.h2d_bytes() / args.steps, "d2h_bytes_per_step": 4.0 / args.steps,
                "note": f"one MatrixFactorization.fit({args.steps} epochs) from pinned host COO + host CSR features, incl. H2D, "
                        f"CSR/item-major structure build, weight init, {args.steps} epochs, D2H of the mean loss; "
-                       f"{float(dt):.3f} s total, final loss {final_loss:.5f}"}
+                       f"median of 3 calls ({', '.join('%.3f' % x for x in dts)} s), final loss {final_loss:.5f}"}
 
     out = {"metric": metric, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None, "dtype": "f32",

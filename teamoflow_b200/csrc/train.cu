@@ -94,6 +94,12 @@ user_pass_kernel(const UserPassParams p) {
   static_assert(NT == 32, "one warp per work item");
   constexpr int NG = NT / LPR;
   constexpr int JH = JPL > 0 ? JPL / 2 : 1;
+#ifdef TMF_V_PD2
+  constexpr int PD = 2, SB = 4;
+#else
+  constexpr int PD = (JPL >= 0 && JPL <= 4 && VPL == 1) ? 4 : 2;   // row buffers of the interaction loop
+  constexpr int SB = (JPL >= 0 && JPL <= 4 && VPL == 1) ? 8 : 4;   // sample rows gathered at once per group
+#endif
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
@@ -134,21 +140,55 @@ user_pass_kernel(const UserPassParams p) {
     for (int v = 0; v < VPL; ++v) ei_lane[v] = reinterpret_cast<const char*>(p.Ei) + 16 * min(lg + LPR * v, nv - 1);
     const unsigned ld_bytes = 4u * (unsigned)ld;
 
+    // When many samples force the hinge layout's LPR above the row width (S > 16 * row lanes), the two phases that only
+    // gather sample rows work in narrower sub-groups of SW lanes (the narrowest power of two >= 4 covering a row), so
+    // 32 / SW rows are gathered per load instruction instead of one.
+    // (The dispatcher only widens LPR when S / LPR > 16, which lands in the JPL = 16 or generic variants: the others
+    // do not carry this path and keep their registers.)
+    constexpr bool NARROW_OK = (JPL == 16 || JPL < 0) && VPL == 1 && LPR > 4;
+    int SW = LPR;
+    if constexpr (NARROW_OK) {
+      while (SW > 4 && (SW >> 1) >= nv) SW >>= 1;
+    }
+    const bool narrow = NARROW_OK && SW < LPR;  // warp-uniform
+    const int sl = tid & (SW - 1), sg = tid / SW, NSG = 32 / SW;
+    const char* ei_sub = reinterpret_cast<const char*>(p.Ei) + 16 * min(sl, nv - 1);
+
     float2 sj2[JH];  // this lane's sample scores, two per register pair (FADD2 / FFMA2 operands)
     float2 gj2[JH];  // ... and its partial G sums
     if constexpr (LOSS == TMF_LOSS_WMRB) {
       const int* su = p.samp + (long long)u * S;
-      const int n_sit = (S + NG * 4 - 1) / (NG * 4);
-      for (int it = 0; it < n_sit; ++it) {  // 4 independent row gathers in flight per group; warp-uniform trip count
-        const int j0 = (it * NG + g) * 4;
-        int idx[4];
-        float4 row[4][VPL];
+      if (NARROW_OK && narrow) {
+        const float4 eus = (sl < nv) ? ldg4(p.Eu + (long long)u * ld + 4 * sl) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n_sit = (S + NSG * 4 - 1) / (NSG * 4);
+        for (int it = 0; it < n_sit; ++it) {
+          const int j0 = (it * NSG + sg) * 4;
+          int idx[4];
+          float4 row[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) idx[q] = (j0 + q < S) ? su[j0 + q] : 0;
+          for (int q = 0; q < 4; ++q) idx[q] = (j0 + q < S) ? su[j0 + q] : 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) load_item<VPL>(ei_lane, idx[q], ld_bytes, row[q]);
+          for (int q = 0; q < 4; ++q)
+            row[q] = __ldg(reinterpret_cast<const float4*>(ei_sub + (unsigned long long)(unsigned)idx[q] * ld_bytes));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 4; ++q) {
+            float sc = dot4(eus, row[q]);
+            for (int o = SW >> 1; o > 0; o >>= 1) sc += __shfl_xor_sync(FULL, sc, o);
+            if (j0 + q < S && sl == 0) sS[j0 + q] = sc;
+          }
+        }
+      }
+      const int n_sit = narrow ? 0 : (S + NG * SB - 1) / (NG * SB);
+      for (int it = 0; it < n_sit; ++it) {  // SB independent row gathers in flight per group; warp-uniform trip count
+        const int j0 = (it * NG + g) * SB;
+        int idx[SB];
+        float4 row[SB][VPL];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) idx[q] = (j0 + q < S) ? su[j0 + q] : 0;
+#pragma unroll
+        for (int q = 0; q < SB; ++q) load_item<VPL>(ei_lane, idx[q], ld_bytes, row[q]);
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
           const int j = j0 + q;
           const float s = gsum<LPR>(dotv<VPL>(eu, row[q]));
           if (j < S && lg == 0) sS[j] = s;
@@ -246,9 +286,12 @@ user_pass_kernel(const UserPassParams p) {
         p.coef_out[k] = c;
       }
     };
-    // Two-stage software pipeline: (item id, value) of an interaction are fetched two iterations ahead, its row one
-    // iteration ahead, so neither the id -> row dependency nor the row's L2 latency sits on the critical path.
-    // Indices past the slice are clamped (a tail iteration re-reads the last row and is masked by `active`).
+    // Software pipeline over PD row buffers: (item id, value) of an interaction are fetched PD iterations ahead, its row
+    // PD - 1 iterations ahead, so neither the id -> row dependency nor the row's L2 / HBM latency sits on the critical
+    // path (PD = 4 where the registers allow it: with a 1 GB item table the rows come from HBM and one row in flight per
+    // warp would leave the memory system idle).  Iteration i uses buffer i % PD; the loop is unrolled PD times so the
+    // buffers are addressed statically (no register copies).  Indices past the slice are clamped (a tail iteration
+    // re-reads the last row and is masked by `active`).
     auto fetch_idx = [&](int& idx, float& a_k, const int k) {
       const int kc = min(k, b - 1);
       idx = p.col_idx[kc];
@@ -257,22 +300,23 @@ user_pass_kernel(const UserPassParams p) {
     {
       const int n_it = (b - a + NG - 1) / NG;
       int k = a + g;
-      float4 row_a[VPL], row_b[VPL];  // two row buffers (no register copies)
-      int i_a, i_b;
-      float v_a, v_b;
-      fetch_idx(i_a, v_a, k);
-      fetch_idx(i_b, v_b, k + NG);
-      load_item<VPL>(ei_lane, i_a, ld_bytes, row_a);
-      for (int it = 0; it < n_it; it += 2, k += 2 * NG) {
-        load_item<VPL>(ei_lane, i_b, ld_bytes, row_b);
-        const float va = v_a;
-        fetch_idx(i_a, v_a, k + 2 * NG);
-        process(row_a, va, k);
-        if (it + 1 < n_it) {  // warp-uniform
-          load_item<VPL>(ei_lane, i_a, ld_bytes, row_a);
-          const float vb = v_b;
-          fetch_idx(i_b, v_b, k + 3 * NG);
-          process(row_b, vb, k + NG);
+      float4 rows[PD][VPL];
+      int ids[PD];
+      float vs[PD];
+#pragma unroll
+      for (int q = 0; q < PD; ++q) fetch_idx(ids[q], vs[q], k + q * NG);
+#pragma unroll
+      for (int q = 0; q < PD - 1; ++q) load_item<VPL>(ei_lane, ids[q], ld_bytes, rows[q]);
+      for (int it = 0; it < n_it; it += PD, k += PD * NG) {
+#pragma unroll
+        for (int q = 0; q < PD; ++q) {
+          if (q == 0 || it + q < n_it) {  // warp-uniform
+            const int qn = (q + PD - 1) % PD;                       // buffer of iteration it + q + PD - 1
+            load_item<VPL>(ei_lane, ids[qn], ld_bytes, rows[qn]);
+            const float v = vs[q];
+            fetch_idx(ids[q], vs[q], k + (q + PD) * NG);
+            process(rows[q], v, k + q * NG);
+          }
         }
       }
     }
@@ -308,13 +352,27 @@ user_pass_kernel(const UserPassParams p) {
       }
       __syncwarp();
       const int* su = p.samp + (long long)u * S;
+      if (NARROW_OK && narrow) {
+        float4 accg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-      for (int j = (slot < 0 ? g : S); j < S; j += NG) {  // split users: the sample term is added once, in the fix-up
-        const float G = sS[j];
-        float4 row[VPL];
-        load_item<VPL>(ei_lane, su[j], ld_bytes, row);
+        for (int j = (slot < 0 ? sg : S); j < S; j += NSG)
+          fma4(accg, sS[j], __ldg(reinterpret_cast<const float4*>(ei_sub + (unsigned long long)(unsigned)su[j] * ld_bytes)));
+        for (int o = SW; o < 32; o <<= 1) {  // over the sub-groups (xor tree: fixed order)
+          accg.x += __shfl_xor_sync(FULL, accg.x, o);
+          accg.y += __shfl_xor_sync(FULL, accg.y, o);
+          accg.z += __shfl_xor_sync(FULL, accg.z, o);
+          accg.w += __shfl_xor_sync(FULL, accg.w, o);
+        }
+        if (g == 0 && lg < SW) add4(acc[0], accg);  // lane lg < SW owns column lg in both layouts
+      } else {
+#pragma unroll 4
+        for (int j = (slot < 0 ? g : S); j < S; j += NG) {  // split users: the sample term is added once, in the fix-up
+          const float G = sS[j];
+          float4 row[VPL];
+          load_item<VPL>(ei_lane, su[j], ld_bytes, row);
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) fma4(acc[v], G, row[v]);
+          for (int v = 0; v < VPL; ++v) fma4(acc[v], G, row[v]);
+        }
       }
     }
 
@@ -344,7 +402,11 @@ __global__ void __launch_bounds__(256) user_fixup_kernel(const UserPassParams p,
   extern __shared__ __align__(16) float fsm[];
   float* sG = fsm;            // [s_pad]
   float* sE = sG + p.s_pad;   // [ld]
+  float* sP = sE + p.ld;      // [256 / nvp][ld] partial sample terms
   const int tid = threadIdx.x;
+  const int nv = p.ld >> 2;
+  int nvp = 4;
+  while (nvp < nv) nvp <<= 1;  // <= 64 (ld <= 256)
   for (int w = blockIdx.x; w < n_split; w += gridDim.x) {
     const int u = split_user[w], first = split_first[w], nseg = split_nseg[w];
     const int S = p.n_samples;
@@ -363,13 +425,23 @@ __global__ void __launch_bounds__(256) user_fixup_kernel(const UserPassParams p,
       sE[c] = s;
     }
     __syncthreads();
-    for (int c = tid; c < p.ld; c += 256) {
-      float s = sE[c];
-      if (loss == TMF_LOSS_WMRB) {
-        const int* su = p.samp + (long long)u * S;
-        for (int j = 0; j < S; ++j) s = fmaf(sG[j], p.Ei[(long long)su[j] * p.ld + c], s);
+    if (loss == TMF_LOSS_WMRB) {  // sample term: the 256 threads form NP sub-groups of nvp lanes, sub-group jp takes samples jp, jp + NP, ...
+      const int* su = p.samp + (long long)u * S;
+      const int c4 = tid & (nvp - 1), jp = tid / nvp, NP = 256 / nvp;
+      float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < nv) {
+#pragma unroll 4
+        for (int j = jp; j < S; j += NP) fma4(a4, sG[j], ldg4(p.Ei + (long long)su[j] * p.ld + 4 * c4));
+        reinterpret_cast<float4*>(sP + jp * p.ld)[c4] = a4;
       }
-      p.dEu[(long long)u * p.ld + c] = s;
+      __syncthreads();
+      for (int c = tid; c < p.ld; c += 256) {
+        float s = sE[c];
+        for (int q = 0; q < NP; ++q) s += sP[q * p.ld + c];  // fixed order
+        p.dEu[(long long)u * p.ld + c] = s;
+      }
+    } else {
+      for (int c = tid; c < p.ld; c += 256) p.dEu[(long long)u * p.ld + c] = sE[c];
     }
   }
 }
@@ -398,6 +470,7 @@ template <int LPR, int VPL>
 static int dispatch_user_pass_j(const UserPassParams& p, int loss, cudaStream_t st) {
   if (loss == TMF_LOSS_MSE) return launch_user_pass<LPR, VPL, 0, TMF_LOSS_MSE>(p, st);
   const int jpl = (p.n_samples + LPR - 1) / LPR;
+  if (jpl <= 2) return launch_user_pass<LPR, VPL, 2, TMF_LOSS_WMRB>(p, st);
   if (jpl <= 4) return launch_user_pass<LPR, VPL, 4, TMF_LOSS_WMRB>(p, st);
   if (jpl <= 8) return launch_user_pass<LPR, VPL, 8, TMF_LOSS_WMRB>(p, st);
   if (jpl <= 16) return launch_user_pass<LPR, VPL, 16, TMF_LOSS_WMRB>(p, st);
@@ -1061,8 +1134,8 @@ extern "C" int tmf_user_pass_fixup(int32_t loss, int32_t n_split, const int32_t*
   p.ld = ld; p.n_samples = loss == TMF_LOSS_WMRB ? n_samples : 0; p.s_pad = (p.n_samples + 3) & ~3; p.nnz = nnz;
   p.Ei = Ei; p.samp = samp; p.part_G = const_cast<float*>(part_G); p.part_E = const_cast<float*>(part_E);
   p.coef_out = coef_out; p.dEu = dEu;
-  const size_t smem = (size_t)(p.s_pad + ld) * sizeof(float);
-  TMF_REQUIRE(smem <= 48 * 1024, "tmf_user_pass_fixup: n_samples too large");
+  const size_t smem = (size_t)(p.s_pad + ld + 1024) * sizeof(float);  // (256 / nvp) partial rows of ld floats <= 1024 floats
+  TMF_REQUIRE(smem <= 48 * 1024 && ld <= 256, "tmf_user_pass_fixup: n_samples too large");
   user_fixup_kernel<<<std::min(n_split, 148 * 4), 256, smem, as_stream(stream)>>>(p, loss, n_split, split_user, split_first, split_nseg);
   TMF_LAUNCH_CHECK();
   return TMF_OK;

@@ -244,20 +244,28 @@ class InteractionPlan:
         _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
                   _abi.ptr(self.t_user))
 
-    # users with more interactions than this are processed as several slices (load balance, tmf_user_pass)
+    # users with more interactions than the slice length are processed as several slices (load balance: tmf_user_pass gives
+    # a work item to ONE warp).  1024 on large problems; shorter -- down to 32 -- when the whole problem would otherwise
+    # not fill the machine's ~9.5k resident warp slots (a 943-user problem's heaviest user must not be one warp's tail).
     SPLIT = 1024
+    SPLIT_MIN = 32
+    TARGET_ITEMS = 148 * 32 * 2
+
+    def slice_len(self):
+        return int(min(self.SPLIT, max(self.SPLIT_MIN, self.nnz // self.TARGET_ITEMS)))
 
     def _build_work_list(self):
-        """Work items of the user pass: whole users, or SPLIT-sized slices of very heavy users, heaviest first."""
+        """Work items of the user pass: whole users, or slice_len()-sized slices of very heavy users, heaviest first."""
         dev = self.vals.device
+        SPLIT = self.slice_len()
         rp = self.row_ptr.to(torch.int64)
         lens = rp[1:] - rp[:-1]
-        nseg = torch.clamp((lens + self.SPLIT - 1) // self.SPLIT, min=1)
+        nseg = torch.clamp((lens + SPLIT - 1) // SPLIT, min=1)
         first_seg = torch.cumsum(nseg, 0) - nseg
         w_user = torch.repeat_interleave(torch.arange(self.n_users, device=dev), nseg)
         seg = torch.arange(w_user.numel(), device=dev) - first_seg[w_user]
-        w_a = rp[w_user] + seg * self.SPLIT
-        w_b = torch.minimum(w_a + self.SPLIT, rp[w_user + 1])
+        w_a = rp[w_user] + seg * SPLIT
+        w_b = torch.minimum(w_a + SPLIT, rp[w_user + 1])
         split = nseg[w_user] > 1
         slot = torch.cumsum(split.to(torch.int64), 0) - 1
         w_slot = torch.where(split, slot, torch.full_like(slot, -1))

@@ -449,6 +449,7 @@ def test_heavy_users_are_split_and_still_deterministic_and_exact():
     n_u, n_i, r, S = 6, 9000, 16, 20
     rng = np.random.default_rng(21)
     SP = eng.InteractionPlan.SPLIT
+    eng.InteractionPlan.SPLIT_MIN, keep_min = SP, eng.InteractionPlan.SPLIT_MIN  # fixed slice length for this test
     lens = [2 * SP + 807, SP + 904, SP + 1, SP, 3, 0]  # 3, 2, 2, 1, 1, 0 slices
     rows = np.concatenate([np.full(n, u) for u, n in enumerate(lens)])
     cols = np.concatenate([np.sort(rng.choice(n_i, n, replace=False)) for n in lens]).astype(np.int64)
@@ -469,6 +470,7 @@ def test_heavy_users_are_split_and_still_deterministic_and_exact():
         g1 = plan.u.grads["W"].clone()
         plan.forward_backward()
         assert torch.equal(g1, plan.u.grads["W"])
+    eng.InteractionPlan.SPLIT_MIN = keep_min
 
 
 # ------------------------------------------------------------------ SURVEY 8(f) extensions (defaults stay reference behaviour)
