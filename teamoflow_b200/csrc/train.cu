@@ -650,23 +650,36 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
 // elementwise / reductions
 // =====================================================================================
 
-__global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g, long long n, float lr) {
+__device__ __forceinline__ float adam1_step(float w, float gi, float alpha) {
   // Keras Adam, step 1 from zero moments, un-simplified m/v/alpha form in fp32
   const float one_m_b1 = 1.0f - 0.9f;
   const float one_m_b2 = 1.0f - 0.999f;
-  const float alpha = lr * sqrtf(one_m_b2) / one_m_b1;
   const float eps = 1e-7f;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) {
-    const float gi = g[i];
-    const float m = gi * one_m_b1;
-    const float v = (gi * gi) * one_m_b2;
-    w[i] = w[i] - __fdiv_rn(alpha * m, sqrtf(v) + eps);
-  }
+  const float m = gi * one_m_b1;
+  const float v = (gi * gi) * one_m_b2;
+  return w - __fdiv_rn(alpha * m, sqrtf(v) + eps);
 }
 
-// Adam with persistent moments (extension behind fit(optimizer="adam"); Keras formula, epsilon 1e-7)
+// 128-bit accesses over the 16-byte aligned body (n4 float4 groups), scalar tail
+__global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g, long long n, float lr, int vec) {
+  const float alpha = lr * sqrtf(1.0f - 0.999f) / (1.0f - 0.9f);
+  const long long n4 = vec ? (n >> 2) : 0;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float4* w4 = reinterpret_cast<float4*>(w);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long q = i; q < n4; q += stride) {
+    const float4 gv = __ldcs(g4 + q);  // the gradient is dead after this read
+    float4 wv = w4[q];
+    wv.x = adam1_step(wv.x, gv.x, alpha);
+    wv.y = adam1_step(wv.y, gv.y, alpha);
+    wv.z = adam1_step(wv.z, gv.z, alpha);
+    wv.w = adam1_step(wv.w, gv.w, alpha);
+    w4[q] = wv;
+  }
+  for (long long q = 4 * n4 + i; q < n; q += stride) w[q] = adam1_step(w[q], g[q], alpha);
+}
+
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float alpha) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-7f;
@@ -1043,7 +1056,8 @@ extern "C" int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float*
 
 extern "C" int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream) {
   if (n == 0) return TMF_OK;
-  adam1_kernel<<<(unsigned)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, as_stream(stream)>>>(w, g, n, lr);
+  const int vec = aligned16(w) && aligned16(g);  // views at odd offsets take the scalar path
+  adam1_kernel<<<(unsigned)std::min<long long>(cdiv(cdiv(n, vec ? 4 : 1), 256), 148 * 16), 256, 0, as_stream(stream)>>>(w, g, n, lr, vec);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }
