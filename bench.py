@@ -507,8 +507,9 @@ def main():
     plan = model._prepare(xu, xi, wl.interactions_host(), comm=comm)
     if comm is not None:
         comm.broadcast_params(plan.u, plan.i)
-    for _ in range(args.warmup):
-        plan.step(wl.lr)
+    # warm-up through the same entry point as the timed loop (TrainPlan.run = the body of fit()'s epoch loop: first step
+    # eager, the rest replayed from ONE captured CUDA graph of a step); the capture happens here
+    plan.run(max(args.warmup, 3), wl.lr)
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
@@ -516,8 +517,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
-        for _ in range(args.steps):
-            plan.step(wl.lr)
+        plan.run(args.steps, wl.lr)
         e1.record()
         if world > 1:
             torch.distributed.barrier()

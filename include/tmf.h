@@ -234,8 +234,10 @@ TMF_API int tmf_ipc_export(const void* dev_ptr, void* handle_host);
 TMF_API int tmf_ipc_open(const void* handle_host, void** out);
 TMF_API int tmf_ipc_close(void* p);
 
-/* Stream-ordered barrier between the ranks: pads_host[g] = rank g's pad (>= TMF_MAX_PEERS uint32, zero-initialised,
- * in peer memory); every rank calls it with the same, strictly increasing `epoch` (>= 1).  Work enqueued before the
+/* Stream-ordered barrier between the ranks: pads_host[g] = rank g's pad (256 bytes, zero-initialised, in peer
+ * memory: uint32 arrival slots [0, TMF_MAX_PEERS) + a private epoch counter at byte 128); every rank calls it with the
+ * same, strictly increasing `epoch` (>= 1), or with epoch = 0 = "the next value of the device-side counter" (no
+ * per-call argument: replayable from a CUDA graph; do not mix the two forms on one pad).  Work enqueued before the
  * barrier on any rank is visible to work enqueued after it on every rank.  A peer missing for 20 s traps. */
 TMF_API int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, tmf_stream_t stream);
 

@@ -37,8 +37,22 @@ __device__ __forceinline__ float key2f_desc(uint32_t k) {
 // ------------------------------------------------------------------ flag barrier
 // pads.p[g] = rank g's pad: kMaxPeers uint32 slots, slot s is written by rank s only.  Epochs only grow.
 // A peer that never arrives (crashed rank) trips the timeout and traps instead of hanging the GPU.
+// epoch == 0: the epoch is the next value of a counter kept in the rank's own pad (word kEpochWord, touched by this rank
+// only).  Every rank issues the same sequence of barriers, so the counters agree -- and the launch carries no
+// per-call argument, which makes it replayable from a CUDA graph.
+constexpr int kEpochWord = 32;  // byte 128 of the 256-byte pad; the arrival slots use words [0, kMaxPeers)
 __global__ void peer_barrier_kernel(PeerPtrs pads, int world, int rank, uint32_t epoch, unsigned long long timeout_ns) {
   const int t = threadIdx.x;
+  if (epoch == 0) {
+    uint32_t e = 0;
+    if (t == 0) {
+      uint32_t* ctr = reinterpret_cast<uint32_t*>(pads.p[rank]) + kEpochWord;
+      e = *ctr + 1u;
+      if (e == 0) e = 1u;
+      *ctr = e;
+    }
+    epoch = __shfl_sync(0xffffffffu, e, 0);
+  }
   if (t >= world) return;
   __threadfence_system();
   uint32_t* remote = reinterpret_cast<uint32_t*>(pads.p[t]) + rank;

@@ -368,6 +368,57 @@ class TrainPlan:
             self.comm.sync_shared_grads(self.u, self.i)
         return fused
 
+    # ---- epoch loop.  One step is ~15-25 short launches; on small problems (and on every multi-GPU step, where the
+    # exchange adds barrier / reduce / NCCL launches) the host's launch path, not the GPU, sets the pace.  The loop
+    # therefore runs its first step eagerly (allocates every workspace, warms NCCL up) and replays ONE captured CUDA graph
+    # of a step for the rest.  Everything a step launches is stream-ordered with fixed arguments (the peer barrier takes
+    # its epoch from a device-side counter), so a replay is bit-identical to an eager step.
+    USE_CUDA_GRAPH = True
+
+    def run(self, n_steps, lr, graph=None):
+        """``n_steps`` training steps (the body of the reference's epoch loop, matrix_factorization.py:129-180)."""
+        n_steps = int(n_steps)
+        use = self.USE_CUDA_GRAPH if graph is None else bool(graph)
+        if not use or self.opt_state is not None or n_steps < 3:
+            for _ in range(n_steps):
+                self.step(lr)
+            return
+        self.step(lr)
+        g = self._captured_step(lr)
+        if g is None:
+            for _ in range(n_steps - 1):
+                self.step(lr)
+            return
+        for _ in range(n_steps - 1):
+            g.replay()
+        _abi.launch_count += self._graph_launches * (n_steps - 1)
+
+    def invalidate_graph(self):
+        """Drop the captured step (its buffers changed: new negatives, new optimizer state)."""
+        self._graph = None
+
+    def _captured_step(self, lr):
+        if getattr(self, "_graph", None) is not None and self._graph_lr == float(lr):
+            return self._graph
+        g = torch.cuda.CUDAGraph()
+        l0, c0 = _abi.launch_count, _abi.call_count
+        try:
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.step(lr)
+        except Exception as e:  # capture refused (e.g. a collective that cannot be captured): eager loop, say so once
+            import sys
+            print(f"[teamoflow_b200] CUDA graph capture of the training step failed ({type(e).__name__}: {e}); "
+                  "running the epoch loop eagerly", file=sys.stderr)
+            torch.cuda.synchronize()
+            TrainPlan.USE_CUDA_GRAPH = False
+            self._graph = None
+            return None
+        self._graph_launches = _abi.launch_count - l0
+        _abi.launch_count, _abi.call_count = l0, c0  # captured, not launched
+        self._graph, self._graph_lr = g, float(lr)
+        return g
+
     def step(self, lr):
         if self.opt_state is not None:  # stateful Adam (extension): the exchange kernel's fused fresh-Adam step does not apply
             self.forward_backward()

@@ -229,8 +229,9 @@ class PeerArena:
     def barrier(self):
         """Stream-ordered barrier over the group (no host synchronisation)."""
         from .. import _abi
-        self.epoch += 1
-        _abi.call("tmf_peer_barrier", self._pads, self.world, self.rank, self.epoch)
+        # epoch 0 = "next value of the device-side counter in this rank's pad": no per-call argument, so the launch can
+        # be replayed from a CUDA graph (TrainPlan.run)
+        _abi.call("tmf_peer_barrier", self._pads, self.world, self.rank, 0)
 
     def close(self):
         from .. import _abi

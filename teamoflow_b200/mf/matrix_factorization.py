@@ -184,6 +184,7 @@ class MatrixFactorization:
         cumulative_time = 0
         self.loss_history = []
         self._sample_log = []
+        span_left = 0
         for epoch in range(epochs):
             start = t.default_timer()
             if resample_every and epoch > 0 and epoch % int(resample_every) == 0 and plan.ip.loss == eng.WMRB:
@@ -193,7 +194,15 @@ class MatrixFactorization:
                 self.random_ind = random_sampler(plan.ip.n_items, plan.ip.n_users, plan.ip.S, seed=seed)
                 self._sample_log.append((epoch, self.random_ind))
                 plan.ip.set_samples(self.random_ind)
-            plan.step(lr)
+                plan.invalidate_graph()
+            if span_left == 0:
+                # epochs up to the next loss report / resampling point run as one span (TrainPlan.run: first step
+                # eager, the rest replayed from a CUDA graph of the step)
+                span_left = min(25 - epoch % 25, epochs - epoch)
+                if resample_every and plan.ip.loss == eng.WMRB:
+                    span_left = min(span_left, int(resample_every) - epoch % int(resample_every))
+                plan.run(span_left, lr)
+            span_left -= 1
             report = (epoch + 1) % 25 == 0
             if report:
                 torch.cuda.synchronize()

@@ -504,6 +504,29 @@ def test_stateful_adam_extension_matches_oracle():
         assert (d <= 2 * lr * epochs).all() and (d > 5e-5).mean() < 0.01
 
 
+def test_cuda_graph_epoch_loop_is_bitwise_the_eager_loop():
+    """fit() replays ONE captured CUDA graph of a step after the first epoch (TrainPlan.run); the trajectory must be the
+    eager loop's bit for bit, for every loss / tower combination the step can launch."""
+    E, I, L, eng, FM, SI, MF = _mods()
+    n_u, n_i, r, S = 50, 70, 8, 12
+    for loss, kinds in (("wmrb", ("linear", "linear")), ("mse", ("biased", "relu")), ("kl", ("relu", "biased"))):
+        rng, rows, cols, vals, samp = make_problem(n_u, n_i, r, 600, S, 41, values=(1.0, 2.0, -1.0))
+        pu, pi = params_for(kinds[0], n_u, r, rng, 0.5), params_for(kinds[1], n_i, r, rng, 0.5)
+        out = []
+        for use_graph in (True, False):
+            m = build_model(loss, kinds, pu, pi, r, n_u, n_i, S, samp)
+            keep = eng.TrainPlan.USE_CUDA_GRAPH
+            eng.TrainPlan.USE_CUDA_GRAPH = use_graph
+            try:
+                m.fit(7, FM.eye(n_u), FM.eye(n_i), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)), lr=0.05, verbose=False)
+            finally:
+                eng.TrainPlan.USE_CUDA_GRAPH = keep
+            assert (getattr(m._plan, "_graph", None) is not None) == use_graph
+            out.append([w.clone() for w in m.user_trainable + m.item_trainable] + [m.user_embedding.clone(), m.item_embedding.clone()])
+        for a, b in zip(*out):
+            assert torch.equal(a, b)
+
+
 def test_fresh_optimizer_is_the_default_and_differs_from_stateful():
     model, inter, FeatureMatrix, (rows, cols, vals, samp, U0, V0, n_u, n_i, r, S) = _small_wmrb_model()
     model.fit(3, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False)
