@@ -600,7 +600,23 @@ def main():
     if rank == 0:
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # The captured step graphs hold NCCL work (the all-reduce of the shared user-side gradients).  Drop them while the
+        # communicator is alive, then leave WITHOUT tearing the process group down: destroy_process_group() after graph
+        # capture blocked forever in the first 2-GPU run of the graph path (the JSON line was already out).  Every rank
+        # has finished (barrier + synchronize), so the OS reclaims the rest.
+        for pl in (plan, getattr(model, "_plan", None)):
+            if pl is not None:
+                pl.invalidate_graph()
+        del plan
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        out_stream.flush()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

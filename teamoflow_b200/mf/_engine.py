@@ -13,6 +13,8 @@ are 16-byte aligned for 128-bit loads; the public tensors are the ``[:, :r]`` vi
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -373,7 +375,7 @@ class TrainPlan:
     # therefore runs its first step eagerly (allocates every workspace, warms NCCL up) and replays ONE captured CUDA graph
     # of a step for the rest.  Everything a step launches is stream-ordered with fixed arguments (the peer barrier takes
     # its epoch from a device-side counter), so a replay is bit-identical to an eager step.
-    USE_CUDA_GRAPH = True
+    USE_CUDA_GRAPH = os.environ.get("TMF_CUDA_GRAPH", "1") != "0"   # TMF_CUDA_GRAPH=0: eager epoch loop
 
     def run(self, n_steps, lr, graph=None):
         """``n_steps`` training steps (the body of the reference's epoch loop, matrix_factorization.py:129-180)."""
@@ -392,6 +394,7 @@ class TrainPlan:
         for _ in range(n_steps - 1):
             g.replay()
         _abi.launch_count += self._graph_launches * (n_steps - 1)
+        self.graph_replays = getattr(self, "graph_replays", 0) + n_steps - 1
 
     def invalidate_graph(self):
         """Drop the captured step (its buffers changed: new negatives, new optimizer state)."""

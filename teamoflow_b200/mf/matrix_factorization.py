@@ -213,6 +213,7 @@ class MatrixFactorization:
                 self.loss_history.append((epoch + 1, loss_one_epoch))
                 if verbose:
                     print(f'Epoch {epoch + 1} Complete | Loss {loss_one_epoch} | Runtime {cumulative_time:.5} s')
+        plan.invalidate_graph()  # the captured step does not outlive fit (with comm it holds NCCL work)
         if comm is not None and hasattr(comm, "detach"):
             comm.detach(plan)
         # ref:186-187 -- embeddings recomputed from the final weights
