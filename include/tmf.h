@@ -107,6 +107,8 @@ TMF_API int tmf_spmm_seg(int32_t n_seg, const int32_t* seg_ptr, int64_t n_entrie
  *   user's interactions, slot); slot = -1 for whole users, otherwise the row of part_G [n_slots, ceil4(S)] /
  *   part_E [n_slots, ld] that receives the slice's partial sums (very heavy users are split for load balance and
  *   finished by tmf_user_pass_fixup).  Items should be listed heaviest first.  counter: one int32 work counter.
+ *   A work item is processed by ONE warp (up to 32 resident per SM), so slices should be short enough that the whole
+ *   list fills ~9.5k warp slots (InteractionPlan.slice_len: 32 ... 1024 interactions).
  */
 TMF_API int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int64_t nnz, const int32_t* row_ptr, const int32_t* col_idx,
                   const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
@@ -128,7 +130,8 @@ TMF_API int tmf_pair_dots(int64_t nnz, const int32_t* rows, const int32_t* cols,
 TMF_API int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float* loss_out, float* coef_out, void* ws,
                 tmf_stream_t stream);
 
-/* Adam step t=1 from zero moments (a new tf.keras.optimizers.Adam each epoch, matrix_factorization.py:176). */
+/* Adam step t=1 from zero moments (a new tf.keras.optimizers.Adam each epoch, matrix_factorization.py:176).
+ * 128-bit accesses when w and g are 16-byte aligned, scalar otherwise; same bits either way. */
 TMF_API int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream);
 
 /* Extension (not reference behaviour): Adam with persistent moments m, v (zero-initialised by the caller) and step count

@@ -91,6 +91,19 @@ __device__ __forceinline__ float rcp_approx(float x) {  // MUFU.RCP, 1 ulp; call
   return r;
 }
 
+// Keras Adam, step 1 from zero moments (a NEW optimizer every epoch, matrix_factorization.py:176), in the un-simplified
+// m / v / alpha form in fp32.  One definition for the stand-alone update (tmf_adam1) and the update fused into
+// the multi-GPU gradient exchange (tmf_peer_reduce_push): replicas must receive identical bits.
+__device__ __forceinline__ float adam1_alpha(float lr) { return lr * sqrtf(1.0f - 0.999f) / (1.0f - 0.9f); }
+__device__ __forceinline__ float adam1_apply(float w, float g, float alpha) {
+  const float one_m_b1 = 1.0f - 0.9f;
+  const float one_m_b2 = 1.0f - 0.999f;
+  const float eps = 1e-7f;
+  const float m = g * one_m_b1;
+  const float v = (g * g) * one_m_b2;
+  return w - __fdiv_rn(alpha * m, sqrtf(v) + eps);
+}
+
 // 16-byte global -> shared asynchronous copy (LDGSTS: no register staging); both addresses 16-byte aligned
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");

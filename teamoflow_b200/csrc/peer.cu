@@ -132,16 +132,7 @@ topk_merge_lists_kernel(PeerPtrs idx_in, PeerPtrs sc_in, int G, long long row_lo
 //   lr <  0 : the sum is stored into dst of every peer                       (all-reduce)
 //   lr >= 0 : w <- adam1(w, sum) for the slice, new rows stored to every peer (all-reduce fused with the update)
 // One float4 per thread per trip; the loads of the G partials are issued together.
-__device__ __forceinline__ float adam1_update(float w, float g, float lr) {
-  // Keras Adam, t = 1, zero moments (matrix_factorization.py:176): the same fp32 operation sequence as adam1_kernel
-  const float one_m_b1 = 1.0f - 0.9f;
-  const float one_m_b2 = 1.0f - 0.999f;
-  const float alpha = lr * sqrtf(one_m_b2) / one_m_b1;
-  const float eps = 1e-7f;
-  const float m = g * one_m_b1;
-  const float v = (g * g) * one_m_b2;
-  return w - __fdiv_rn(alpha * m, sqrtf(v) + eps);
-}
+__device__ __forceinline__ float adam1_update(float w, float g, float lr) { return adam1_apply(w, g, adam1_alpha(lr)); }
 
 template <int G>
 __global__ void __launch_bounds__(256) peer_reduce_push_kernel(PeerPtrs part, PeerPtrs dst, long long off4, long long n4,

@@ -650,19 +650,9 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
 // elementwise / reductions
 // =====================================================================================
 
-__device__ __forceinline__ float adam1_step(float w, float gi, float alpha) {
-  // Keras Adam, step 1 from zero moments, un-simplified m/v/alpha form in fp32
-  const float one_m_b1 = 1.0f - 0.9f;
-  const float one_m_b2 = 1.0f - 0.999f;
-  const float eps = 1e-7f;
-  const float m = gi * one_m_b1;
-  const float v = (gi * gi) * one_m_b2;
-  return w - __fdiv_rn(alpha * m, sqrtf(v) + eps);
-}
-
 // 128-bit accesses over the 16-byte aligned body (n4 float4 groups), scalar tail
 __global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g, long long n, float lr, int vec) {
-  const float alpha = lr * sqrtf(1.0f - 0.999f) / (1.0f - 0.9f);
+  const float alpha = adam1_alpha(lr);
   const long long n4 = vec ? (n >> 2) : 0;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -671,13 +661,13 @@ __global__ void adam1_kernel(float* __restrict__ w, const float* __restrict__ g,
   for (long long q = i; q < n4; q += stride) {
     const float4 gv = __ldcs(g4 + q);  // the gradient is dead after this read
     float4 wv = w4[q];
-    wv.x = adam1_step(wv.x, gv.x, alpha);
-    wv.y = adam1_step(wv.y, gv.y, alpha);
-    wv.z = adam1_step(wv.z, gv.z, alpha);
-    wv.w = adam1_step(wv.w, gv.w, alpha);
+    wv.x = adam1_apply(wv.x, gv.x, alpha);
+    wv.y = adam1_apply(wv.y, gv.y, alpha);
+    wv.z = adam1_apply(wv.z, gv.z, alpha);
+    wv.w = adam1_apply(wv.w, gv.w, alpha);
     w4[q] = wv;
   }
-  for (long long q = 4 * n4 + i; q < n; q += stride) w[q] = adam1_step(w[q], g[q], alpha);
+  for (long long q = 4 * n4 + i; q < n; q += stride) w[q] = adam1_apply(w[q], g[q], alpha);
 }
 
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
