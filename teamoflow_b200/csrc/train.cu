@@ -94,12 +94,8 @@ user_pass_kernel(const UserPassParams p) {
   static_assert(NT == 32, "one warp per work item");
   constexpr int NG = NT / LPR;
   constexpr int JH = JPL > 0 ? JPL / 2 : 1;
-#ifdef TMF_V_PD2
-  constexpr int PD = 2, SB = 4;
-#else
   constexpr int PD = (JPL >= 0 && JPL <= 4 && VPL == 1) ? 4 : 2;   // row buffers of the interaction loop
   constexpr int SB = (JPL >= 0 && JPL <= 4 && VPL == 1) ? 8 : 4;   // sample rows gathered at once per group
-#endif
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
