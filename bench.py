@@ -579,7 +579,12 @@ def main():
                       "loss_after": loss_now},
            "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
                         "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                        "alg_bytes_per_launch": phase_bytes[dom], "ms_per_launch": phases[dom]},
+                        "alg_bytes_per_launch": phase_bytes[dom], "ms_per_launch": phases[dom],
+                        "note": "achieved = SURVEY-8d ALGORITHMIC bytes (every embedding-row gather counted as HBM bytes) / "
+                                "CUDA-event time; `traffic` = DRAM bytes of one launch from the committed ncu capture. Where the "
+                                "gathered table fits the 126 MB L2 (C3: 6.9 MB item table) traffic << algorithmic bytes, the "
+                                "fraction can exceed 1 and the kernel's real bound is instruction issue + L1/L2 gather latency "
+                                "(profiles/r01_summary.md v8: 67.7 % issue-active)"},
            "step_roofline": {"alg_bytes_per_step": wl.bytes["total"], "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": step_gbs / hbm_peak},
            "phases_ms": phases, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches}
