@@ -6,7 +6,7 @@ free -g | head -2
 if [ "$N" = "1" ]; then
   timeout 1200 python bench.py --workload c4 --steps 10 --warmup 3 --topk none --no-cpu-baseline > gpurun_out/bench_c4_1gpu.json 2> gpurun_out/bench_c4_1gpu.err; echo "exit $?"
 else
-  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --workload c4 --steps 10 --warmup 3 --topk none --no-cpu-baseline > gpurun_out/bench_c4_${N}gpu.json 2> gpurun_out/bench_c4_${N}gpu.err; echo "exit $?"
+  timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --workload c4 --steps 10 --warmup 3 --topk none --no-cpu-baseline > gpurun_out/bench_c4_${N}gpu.json 2> gpurun_out/bench_c4_${N}gpu.err; echo "exit $?"
 fi
 python - <<PY
 import json
