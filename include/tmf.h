@@ -130,6 +130,15 @@ TMF_API int tmf_pair_dots(int64_t nnz, const int32_t* rows, const int32_t* cols,
 TMF_API int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float* loss_out, float* coef_out, void* ws,
                 tmf_stream_t stream);
 
+/* The same loss under user sharding: the two groups' moments (tf.nn.moments, loss_graphs.py:116,118) are
+ * global, so each rank first reduces ITS interactions to six additive fp64 sums
+ *     moments_out[6] = {n+, sum p+, sum p+^2, n-, sum p-, sum p-^2}          (tmf_kl_moments)
+ * the host sums them over the ranks (one 48-byte all-reduce), and tmf_kl_coef_from_moments derives the global means /
+ * variances, the scalar loss and this rank's d loss / d p[k].  ws >= tmf_reduce_ws_bytes() for both. */
+TMF_API int tmf_kl_moments(int64_t nnz, const float* p, const float* val, double* moments_out, void* ws, tmf_stream_t stream);
+TMF_API int tmf_kl_coef_from_moments(int64_t nnz, const float* p, const float* val, const double* moments, float* loss_out,
+                             float* coef_out, void* ws, tmf_stream_t stream);
+
 /* Adam step t=1 from zero moments (a new tf.keras.optimizers.Adam each epoch, matrix_factorization.py:176).
  * 128-bit accesses when w and g are 16-byte aligned, scalar otherwise; same bits either way. */
 TMF_API int tmf_adam1(float* w, const float* g, int64_t n, float lr, tmf_stream_t stream);
@@ -212,6 +221,18 @@ TMF_API size_t tmf_rank_rows_ws_bytes(int64_t n_rows, int64_t n_cols);
 TMF_API int tmf_rank_rows(const float* P, int64_t n_rows, int64_t n_cols, int32_t clamp, int32_t* out_idx, void* ws,
                   size_t ws_bytes, tmf_stream_t stream);
 
+/* predict(A)'s second output (matrix_factorization.py:197-198: gather_nd(P, where(A == 0)) flattened row-major) from the
+ * CSR (a_ptr, a_idx: sorted columns) of the NON-ZERO cells of A -- no dense A.  out has n_users*n_items - nnz entries. */
+TMF_API int tmf_gather_unobserved(const float* P, int64_t n_users, int64_t n_items, const int32_t* a_ptr, const int32_t* a_idx,
+                          float* out, tmf_stream_t stream);
+
+/* Masked top-k (new-build: the reference does not exclude seen items, A.7): keeps, in order, the first k entries
+ * of each row of cand_idx [n_users, kc] (the top-kc list of tmf_score_topk) that are not stored in row u of the CSR; rows with
+ * fewer than k survivors get short_rows[u] = 1 (the caller ranks those rows exactly).  out_score may be NULL. */
+TMF_API int tmf_filter_seen(const int32_t* cand_idx, const float* cand_score, int64_t n_users, int32_t kc, int32_t k,
+                    const int32_t* a_ptr, const int32_t* a_idx, int32_t* out_idx, float* out_score, int32_t* short_rows,
+                    tmf_stream_t stream);
+
 /* hits[u] = #{i in topk[u] : A[u,i] != 0}, relevant[u] = #{i : A[u,i] > 0} for CSR A (:248-254). */
 TMF_API int tmf_metrics_hits(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
                      const float* a_val, float* hits, float* relevant, tmf_stream_t stream);
@@ -241,8 +262,11 @@ TMF_API int tmf_ipc_close(void* p);
  * memory: uint32 arrival slots [0, TMF_MAX_PEERS) + a private epoch counter at byte 128); every rank calls it with the
  * same, strictly increasing `epoch` (>= 1), or with epoch = 0 = "the next value of the device-side counter" (no
  * per-call argument: replayable from a CUDA graph; do not mix the two forms on one pad).  Work enqueued before the
- * barrier on any rank is visible to work enqueued after it on every rank.  A peer missing for 20 s traps. */
-TMF_API int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, tmf_stream_t stream);
+ * barrier on any rank is visible to work enqueued after it on every rank.  A peer missing for `timeout_ms`
+ * (0 = the default, 120 s) does NOT trap: the waiting rank stores 1 + (the missing rank) into the uint32 at byte 132 of
+ * its own pad (sticky) and leaves the barrier; the host reads that word at its next synchronisation point and raises. */
+TMF_API int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, uint32_t timeout_ms,
+                     tmf_stream_t stream);
 
 /* all-to-all + merge + all-gather of item-sharded top-k lists in one kernel: for rows [row_lo, row_lo + n_rows) read
  * the `world` per-slab lists idx_host[g] / score_host[g] ([n_users, k] each, in rank g's memory), merge them like

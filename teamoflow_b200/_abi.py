@@ -37,6 +37,8 @@ SIGNATURES = {
     "tmf_user_pass_fixup": (_i32, [_i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p, _p]),
     "tmf_pair_dots": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p]),
     "tmf_kl_coef": (_i32, [_i64, _p, _p, _p, _p, _p, _p]),
+    "tmf_kl_moments": (_i32, [_i64, _p, _p, _p, _p, _p]),
+    "tmf_kl_coef_from_moments": (_i32, [_i64, _p, _p, _p, _p, _p, _p, _p]),
     "tmf_adam1": (_i32, [_p, _p, _i64, _f32, _p]),
     "tmf_adam": (_i32, [_p, _p, _p, _p, _i64, _f32, _i32, _p]),
     "tmf_reduce_sum": (_i32, [_p, _i64, _p, _p, _p]),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "tmf_predict_dense": (_i32, [_p, _i64, _p, _i64, _i32, _i32, _p, _p]),
     "tmf_rank_rows_ws_bytes": (_sz, [_i64, _i64]),
     "tmf_rank_rows": (_i32, [_p, _i64, _i64, _i32, _p, _p, _sz, _p]),
+    "tmf_gather_unobserved": (_i32, [_p, _i64, _i64, _p, _p, _p, _p]),
+    "tmf_filter_seen": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
     "tmf_metrics_hits": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "tmf_dcg": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tmf_idcg": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p]),
@@ -65,7 +69,7 @@ SIGNATURES = {
     "tmf_ipc_export": (_i32, [_p, _p]),
     "tmf_ipc_open": (_i32, [_p, _p]),
     "tmf_ipc_close": (_i32, [_p]),
-    "tmf_peer_barrier": (_i32, [_p, _i32, _i32, C.c_uint32, _p]),
+    "tmf_peer_barrier": (_i32, [_p, _i32, _i32, C.c_uint32, C.c_uint32, _p]),
     "tmf_topk_merge_peer": (_i32, [_p, _p, _i32, _i64, _i64, _i32, _p, _p, _i32, _p]),
     "tmf_peer_reduce_push": (_i32, [_p, _p, _i32, _i32, _i64, _i64, _f32, _p]),
 }
@@ -75,7 +79,7 @@ _lib = None
 call_count = 0
 launch_count = 0
 # kernels per ABI call where it is not 1 (memsets are not counted)
-KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5,
+KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5, "tmf_kl_moments": 2, "tmf_kl_coef_from_moments": 2,
                     "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 8, "tmf_score_topk_bounded": 8}
 
 

@@ -36,11 +36,15 @@ __device__ __forceinline__ float key2f_desc(uint32_t k) {
 
 // ------------------------------------------------------------------ flag barrier
 // pads.p[g] = rank g's pad: kMaxPeers uint32 slots, slot s is written by rank s only.  Epochs only grow.
-// A peer that never arrives (crashed rank) trips the timeout and traps instead of hanging the GPU.
+// A peer that never arrives (crashed rank) trips the timeout: the waiting rank sets the error word of its OWN pad
+// (kErrWord, sticky, read by the host at its next synchronisation point -- dist.PeerArena.check()) and leaves the barrier
+// instead of hanging the GPU or killing the CUDA context with a trap (a benign host stall on one rank -- GC, a blocked
+// print, graph instantiation -- must not take the other ranks' contexts down).
 // epoch == 0: the epoch is the next value of a counter kept in the rank's own pad (word kEpochWord, touched by this rank
 // only).  Every rank issues the same sequence of barriers, so the counters agree -- and the launch carries no
 // per-call argument, which makes it replayable from a CUDA graph.
 constexpr int kEpochWord = 32;  // byte 128 of the 256-byte pad; the arrival slots use words [0, kMaxPeers)
+constexpr int kErrWord = 33;    // byte 132: set to 1 + (rank that was missing) when a wait timed out
 __global__ void peer_barrier_kernel(PeerPtrs pads, int world, int rank, uint32_t epoch, unsigned long long timeout_ns) {
   const int t = threadIdx.x;
   if (epoch == 0) {
@@ -65,7 +69,10 @@ __global__ void peer_barrier_kernel(PeerPtrs pads, int world, int rank, uint32_t
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
     if ((int32_t)(v - epoch) >= 0) break;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > timeout_ns) __trap();
+    if (t1 - t0 > timeout_ns) {
+      atomicMax(reinterpret_cast<uint32_t*>(pads.p[rank]) + kErrWord, (uint32_t)(1 + t));
+      break;
+    }
     __nanosleep(200);
   }
 }
@@ -206,11 +213,13 @@ extern "C" int tmf_ipc_close(void* p) {
   return TMF_OK;
 }
 
-extern "C" int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, tmf_stream_t stream) {
+extern "C" int tmf_peer_barrier(const void* const* pads_host, int32_t world, int32_t rank, uint32_t epoch, uint32_t timeout_ms,
+                                tmf_stream_t stream) {
   TMF_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "tmf_peer_barrier: bad world/rank");
   PeerPtrs pads;
   fill_ptrs(pads, pads_host, world);
-  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pads, world, rank, epoch, 20ull * 1000ull * 1000ull * 1000ull);
+  const unsigned long long ms = timeout_ms ? timeout_ms : 120000u;  // 0 = default (2 minutes)
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pads, world, rank, epoch, ms * 1000ull * 1000ull);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }

@@ -3,10 +3,14 @@
 // per-row running threshold and appends the few survivors to a candidate list; an fp64-accumulated
 // rerank of the candidates then makes the returned indices exact (ties -> lower item id).
 //
-// Exactness argument (DESIGN.md "top-k"): the bf16 GEMM score s~ of a pair differs from the canonical
-// score s by at most e = 2^-8 * 1.05 * |u| * |v|.  With t~ the k-th largest s~ seen so far in a row,
-// every item of the final top-k satisfies s~ >= t~ - 2E (E = e with |v| := max |v|), so the candidate
-// list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
+// Exactness argument (DESIGN.md "top-k"): with u~ = fl16(u), du = u - u~ (both known exactly) the tensor-core
+// score s~ of a pair differs from the canonical score s by at most E = |du| max|v| + |u~| max|dv| + accumulation
+// slack (row_error_kernel; rigorous, computed from the data -- the worst case for bf16 is 2^-7 |u||v|).  With t~ a
+// lower bound of the k-th largest s~ seen so far in a row, every item of the final top-k satisfies s~ >= t~ - 2E,
+// so the candidate list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
+//
+// Developer switches (TMF_TOPK_DEBUG / TMF_TOPK_FMT / TMF_TOPK_PROF environment variables) exist only in builds
+// compiled with -DTMF_DEVTOOLS (scripts/build_variant.sh); the product library reads no environment variable.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -43,6 +47,12 @@ constexpr int MAX_KB = 4;                  // n_components <= 256
 // ACC_UNIT: slack per accumulated k-step for the fp32 accumulation inside the tensor core, relative to |u~||v~|.
 constexpr float ACC_UNIT = 2.4e-7f;
 constexpr float NORM_SLACK = 1.0001f;  // rounding of the fp32 norm arithmetic itself
+
+#ifdef TMF_DEVTOOLS
+#define TMF_DBG(p) ((p).dbg)
+#else
+#define TMF_DBG(p) 0
+#endif
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -282,7 +292,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int 
     }
     return;
   }
-  if (p.dbg == 2 || p.dbg == 3) return;
+  if (TMF_DBG(p) == 2 || TMF_DBG(p) == 3) return;
   const int id0 = p.item_offset + col0;
   if (!warp_inited) {  // warp-uniform: no threshold yet, keep everything (coalesced per lane, no queue)
     if (valid) {
@@ -342,7 +352,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowStat
 #pragma unroll
   for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (4096u << g) : 0u;
   unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
-  if (p.dbg == 1) gmask = 0;
+  if (TMF_DBG(p) == 1) gmask = 0;
   const int id0 = p.item_offset + col0;
   while (gmask) {  // warp-uniform
     const int g = __ffs(gmask) - 1;
@@ -837,9 +847,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         tcgen05_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
         const bool tail_tile = (nt + 1) * BN > n_items;
-        if (!DUMP && warp_inited && p.dbg < 2) {
+        if (!DUMP && warp_inited && TMF_DBG(p) < 2) {
           epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, p);
-        } else if (p.dbg < 3) {
+        } else if (TMF_DBG(p) < 3) {
           uint32_t ra[32], rb[32];
           tmem_ld32(t_base, ra);
 #pragma unroll 1
@@ -1521,10 +1531,12 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   TMF_CUDA(cudaMemsetAsync(vmax_bits, 0, 8, st));
   TMF_CUDA(cudaMemsetAsync(ovfc, 0, 4, st));
+#ifdef TMF_DEVTOOLS
   if (force_fmt < 0) {
     const char* e = getenv("TMF_TOPK_FMT");  // A/B aid: "bf16" / "f16"
     if (e) force_fmt = (e[0] == 'f' || e[0] == 'h') ? 1 : 0;
   }
+#endif
   float* fmt_stats = reinterpret_cast<float*>(w + L.off_vmax + 16);  // 8 floats inside the 256-byte scalar block
   if (force_fmt < 0) {
     TMF_CUDA(cudaMemsetAsync(fmt_stats, 0, 32, st));
@@ -1554,12 +1566,15 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.dump = dump; p.dump_ld = n_items;
   p.row_bound = row_bound;
   p.fmt_stats = fmt_stats; p.force_fmt = force_fmt;
-  { const char* e = getenv("TMF_TOPK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = 0;
   p.prof = nullptr;
+#ifdef TMF_DEVTOOLS
+  { const char* e = getenv("TMF_TOPK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   if (getenv("TMF_TOPK_PROF")) {
     p.prof = reinterpret_cast<unsigned long long*>(w + L.off_vmax + 64);
     TMF_CUDA(cudaMemsetAsync(p.prof, 0, 192, st));
   }
+#endif
 
   RerankParams q{};
   q.n_users = n_users; q.n_items = n_items; q.k = k; q.clamp = p.clamp; q.item_offset = item_offset; q.r = n_comp; q.ld = ld;

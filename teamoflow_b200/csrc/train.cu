@@ -724,11 +724,12 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* out)
 // MODE 0: sum(x)            MODE 1: sum(x^2)
 // MODE 2: KL first moments  {cnt+, sum+, cnt-, sum-}
 // MODE 3: KL second moments {ssd+, ssd-} around stats[0]=mu+, stats[1]=mu-
+// MODE 4: KL raw moments    {cnt+, sum+, sumsq+, cnt-, sum-, sumsq-}  (additive over user shards: data-parallel KL)
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads) reduce_partial_kernel(const float* __restrict__ x, const float* __restrict__ val,
                                                                     long long n, const double* __restrict__ stats,
                                                                     double* __restrict__ partial) {
-  constexpr int NV = MODE == 2 ? 4 : (MODE == 3 ? 2 : 1);
+  constexpr int NV = MODE == 2 ? 4 : (MODE == 3 ? 2 : (MODE == 4 ? 6 : 1));
   double v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = 0.0;
@@ -744,6 +745,9 @@ __global__ void __launch_bounds__(kRedThreads) reduce_partial_kernel(const float
     if (MODE == 3) {
       if (val[i] > 0.f) { const double d = xi - stats[0]; v[0] += d * d; } else { const double d = xi - stats[1]; v[1] += d * d; }
     }
+    if (MODE == 4) {
+      if (val[i] > 0.f) { v[0] += 1.0; v[1] += xi; v[2] += xi * xi; } else { v[3] += 1.0; v[4] += xi; v[5] += xi * xi; }
+    }
   }
   block_reduce_store<NV>(v, partial + (long long)blockIdx.x * NV);
 }
@@ -751,17 +755,18 @@ __global__ void __launch_bounds__(kRedThreads) reduce_partial_kernel(const float
 // FIN 0: out_f[0] = sum                      FIN 1: scale = rsqrt(max(sum, 1e-12)) -> stats[0]
 // FIN 2: KL means -> stats[0..3] = {mu+, mu-, n+, n-}
 // FIN 3: KL finish: stats[4..] = {s, z, phi}; out_f[0] = loss
+// FIN 4: KL raw moments -> stats[0..5] (the six sums, nothing derived)
 template <int FIN>
 __global__ void __launch_bounds__(kRedThreads) reduce_final_kernel(const double* __restrict__ partial, int n_blocks,
                                                                   double* __restrict__ stats, float* __restrict__ out_f) {
-  constexpr int NV = FIN == 2 ? 4 : (FIN == 3 ? 2 : 1);
+  constexpr int NV = FIN == 2 ? 4 : (FIN == 3 ? 2 : (FIN == 4 ? 6 : 1));
   double v[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] = 0.0;
   for (int b = threadIdx.x; b < n_blocks; b += kRedThreads)
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] += partial[(long long)b * NV + i];
-  __shared__ double res[4];
+  __shared__ double res[6];
   block_reduce_store<NV>(v, res);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -772,6 +777,10 @@ __global__ void __launch_bounds__(kRedThreads) reduce_final_kernel(const double*
       stats[1] = (double)(float)(res[3] / res[2]);
       stats[2] = res[0];
       stats[3] = res[2];
+    }
+    if (FIN == 4) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) stats[i] = res[i];
     }
     if (FIN == 3) {
       const float vp = (float)(res[0] / stats[2]);  // population variance
@@ -785,6 +794,23 @@ __global__ void __launch_bounds__(kRedThreads) reduce_final_kernel(const double*
       out_f[0] = 1.0f - 0.5f * erfcf(-z * 0.7071067811865476f);  // 1 - ndtr(z), loss_graphs.py:120-122
     }
   }
+}
+
+// Global KL statistics from the six (summed-over-ranks) raw moments m = {n+, S+, Q+, n-, S-, Q-}: means rounded to fp32
+// like tf.nn.moments, population variances about those means (Q - 2 mu S + n mu^2, fp64), then s, z, phi and the loss
+// exactly as FIN 3 derives them on one GPU.
+__global__ void kl_from_moments_kernel(const double* __restrict__ m, double* __restrict__ stats, float* __restrict__ out_f) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double np_ = m[0], nn_ = m[3];
+  const double mp = (double)(float)(m[1] / np_), mn = (double)(float)(m[4] / nn_);
+  const float vp = (float)((m[2] - 2.0 * mp * m[1] + np_ * mp * mp) / np_);
+  const float vn = (float)((m[5] - 2.0 * mn * m[4] + nn_ * mn * mn) / nn_);
+  const float s = sqrtf(vp + vn);
+  const float z = ((float)mp - (float)mn) / s;
+  const float phi = expf(-0.5f * z * z) * 0.3989422804014327f;
+  stats[0] = mp; stats[1] = mn; stats[2] = np_; stats[3] = nn_;
+  stats[4] = s; stats[5] = z; stats[6] = phi;
+  out_f[0] = 1.0f - 0.5f * erfcf(-z * 0.7071067811865476f);
 }
 
 __global__ void kl_coef_kernel(long long nnz, const float* __restrict__ p, const float* __restrict__ val,
@@ -1035,6 +1061,28 @@ extern "C" int tmf_kl_coef(int64_t nnz, const float* p, const float* val, float*
   reduce_final_kernel<2><<<1, kRedThreads, 0, st>>>(partial, nb, stats, nullptr);
   reduce_partial_kernel<3><<<nb, kRedThreads, 0, st>>>(p, val, nnz, stats, partial);
   reduce_final_kernel<3><<<1, kRedThreads, 0, st>>>(partial, nb, stats, loss_out);
+  if (nnz > 0) kl_coef_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, st>>>(nnz, p, val, stats, coef_out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_kl_moments(int64_t nnz, const float* p, const float* val, double* moments_out, void* ws, tmf_stream_t stream) {
+  TMF_REQUIRE(ws && moments_out && (nnz == 0 || (p && val)), "tmf_kl_moments: null");
+  double* partial = reinterpret_cast<double*>(ws) + 16;
+  const int nb = red_blocks(nnz);
+  cudaStream_t st = as_stream(stream);
+  reduce_partial_kernel<4><<<nb, kRedThreads, 0, st>>>(p, val, nnz, nullptr, partial);
+  reduce_final_kernel<4><<<1, kRedThreads, 0, st>>>(partial, nb, moments_out, nullptr);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_kl_coef_from_moments(int64_t nnz, const float* p, const float* val, const double* moments, float* loss_out,
+                                        float* coef_out, void* ws, tmf_stream_t stream) {
+  TMF_REQUIRE(ws && moments && loss_out && coef_out && (nnz == 0 || (p && val)), "tmf_kl_coef_from_moments: null");
+  double* stats = reinterpret_cast<double*>(ws);
+  cudaStream_t st = as_stream(stream);
+  kl_from_moments_kernel<<<1, 32, 0, st>>>(moments, stats, loss_out);
   if (nnz > 0) kl_coef_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, st>>>(nnz, p, val, stats, coef_out);
   TMF_LAUNCH_CHECK();
   return TMF_OK;

@@ -205,6 +205,8 @@ class InteractionPlan:
         self.S = 0
         self.samp = None
         self.t_user = None
+        self.comm = None        # set by TrainPlan under user sharding (KL needs the global moments)
+        self.kl_moments = None
         self.set_samples(random_ind)
         self._build_work_list()
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -305,8 +307,17 @@ class InteractionPlan:
         else:
             _abi.call("tmf_pair_dots", self.nnz, _abi.ptr(self.coo_rows), _abi.ptr(self.col_idx), _abi.ptr(Eu),
                       _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.p))
-            _abi.call("tmf_kl_coef", self.nnz, _abi.ptr(self.p), _abi.ptr(self.vals), _abi.ptr(self.kl_loss),
-                      _abi.ptr(self.coef), _abi.ptr(self.red_ws))
+            if self.comm is None:
+                _abi.call("tmf_kl_coef", self.nnz, _abi.ptr(self.p), _abi.ptr(self.vals), _abi.ptr(self.kl_loss),
+                          _abi.ptr(self.coef), _abi.ptr(self.red_ws))
+            else:  # user-sharded: the two groups' moments are global (loss_graphs.py:116,118) -> one 48-byte all-reduce
+                if self.kl_moments is None:
+                    self.kl_moments = torch.zeros(6, dtype=torch.float64, device=self.vals.device)
+                _abi.call("tmf_kl_moments", self.nnz, _abi.ptr(self.p), _abi.ptr(self.vals), _abi.ptr(self.kl_moments),
+                          _abi.ptr(self.red_ws))
+                self.comm.allreduce_kl_moments(self.kl_moments)
+                _abi.call("tmf_kl_coef_from_moments", self.nnz, _abi.ptr(self.p), _abi.ptr(self.vals), _abi.ptr(self.kl_moments),
+                          _abi.ptr(self.kl_loss), _abi.ptr(self.coef), _abi.ptr(self.red_ws))
             self.spmm_ws = self._spmm_ws(dEu.shape[1])
             spmm(self.n_users, self.row_ptr, self.nnz, self.col_idx, None, self.coef, Ei, r, out=dEu, ws=self.spmm_ws)
 
@@ -346,28 +357,101 @@ class InteractionPlan:
         return float(self.red_out.item()) / self.n_pos
 
 
+class BatchedInteractions:
+    """Mini-batch mode (extension; the reference is full-batch, matrix_factorization.py:128): the users are cut
+    into contiguous blocks of ``batch_size`` users, each with its own ``InteractionPlan`` (CSR slab, item-major list of
+    its interactions ++ its users' negatives) built once per fit.  One epoch = one optimizer step per block, in order;
+    a block's step sees only its users' interactions, so every other user's gradient row is exactly zero."""
+
+    def __init__(self, inter: SparseInteractions, loss, random_ind, batch_size):
+        if loss == KL:
+            raise NotImplementedError("mini-batch mode is defined for the per-interaction losses (MSE, WMRB)")
+        self.loss = loss
+        self.n_users, self.n_items = inter.dense_shape
+        B = int(batch_size)
+        if B < 1:
+            raise ValueError("batch_size must be >= 1 (users per mini-batch)")
+        row_ptr, col_idx, vals, coo_rows, perm = inter.csr()
+        self.perm = perm
+        self.nnz = inter.nnz
+        self.vals_sorted = vals
+        rp = row_ptr.cpu().numpy()
+        ri = None if random_ind is None else to_device(random_ind, torch.int64)
+        self.bounds, self.plans = [], []
+        for lo in range(0, self.n_users, B):
+            hi = min(lo + B, self.n_users)
+            a, b = int(rp[lo]), int(rp[hi])
+            idx = torch.stack([coo_rows[a:b].to(torch.int64) - lo, col_idx[a:b].to(torch.int64)], 1)
+            sub = SparseInteractions(idx, vals[a:b], (hi - lo, self.n_items))
+            self.plans.append(InteractionPlan(sub, loss, None if ri is None else ri[lo:hi]))
+            self.bounds.append((lo, hi, a, b))
+        self.S = self.plans[0].S if self.plans else 0
+        self.n_pos = sum(p.n_pos for p in self.plans)
+        self.vals = vals
+
+    def set_samples(self, random_ind):
+        ri = to_device(random_ind, torch.int64)
+        for (lo, hi, _, _), p in zip(self.bounds, self.plans):
+            p.set_samples(ri[lo:hi])
+
+    def loss_vector(self):
+        """Per-interaction losses in stored order, each taken at the step of its own mini-batch."""
+        lk = torch.cat([p.loss_k[:p.nnz] for p in self.plans]) if self.plans else torch.zeros(0, device=self.vals.device)
+        vals = self.vals_sorted
+        if self.perm is not None:
+            out = torch.empty_like(lk); out[self.perm] = lk
+            v = torch.empty_like(vals); v[self.perm] = vals
+            lk, vals = out, v
+        return lk[vals > 0] if self.loss == WMRB else lk
+
+    def mean_loss(self):
+        if self.n_pos == 0:
+            return float("nan")
+        tot = 0.0
+        for p in self.plans:
+            if p.n_pos:
+                tot += p.mean_loss() * p.n_pos
+        return tot / self.n_pos
+
+
 class TrainPlan:
-    def __init__(self, user_tower: Tower, item_tower: Tower, inter_plan: InteractionPlan, r, comm=None):
+    def __init__(self, user_tower: Tower, item_tower: Tower, inter_plan, r, comm=None):
         self.u, self.i, self.ip, self.r = user_tower, item_tower, inter_plan, int(r)
+        self.batched = isinstance(inter_plan, BatchedInteractions)
+        if self.batched and comm is not None and comm.world_size > 1:
+            import torch.distributed as dist
+            nb = torch.tensor([len(inter_plan.plans), -len(inter_plan.plans)], device=inter_plan.vals.device)
+            dist.all_reduce(nb, op=dist.ReduceOp.MAX, group=comm.group)
+            if int(nb[0]) != -int(nb[1]):
+                raise ValueError("mini-batch mode under user sharding needs the same number of mini-batches on every rank "
+                                 "(every step is a collective): choose batch_size so that ceil(n_local_users / batch_size) agrees")
         self.comm = comm  # optional teamoflow_b200.mf.dist.GradientSync
         self.opt_state = None  # ({}, {}) = persistent Adam moments per tower (extension; None = the reference's fresh Adam per step)
+        if not self.batched:
+            inter_plan.comm = comm if (comm is not None and comm.world_size > 1) else None  # KL: global moments
         if comm is not None:
             comm.attach(self)  # item-side gradient (and fusable weights) move into NVLink peer memory
 
-    def forward_backward(self, lr=None):
+    def forward_backward(self, lr=None, batch=None):
         """One forward + backward.  With ``lr`` (training step) the multi-GPU exchange may fuse the Adam update of the
-        item weights into its reduction kernel; returns True when it did."""
+        item weights into its reduction kernel; returns True when it did.  ``batch``: index of the mini-batch (mini-batch
+        mode only): gradients of that block of users' interactions alone."""
         Eu = self.u.forward()
         Ei = self.i.forward()
-        self.ip.user_pass(Eu, Ei, self.r, self.u.dE)
-        self.ip.item_pass(Eu, self.r, self.i.dE)
+        if self.batched:
+            lo, hi, _, _ = self.ip.bounds[batch]
+            bp = self.ip.plans[batch]
+            self.u.dE.zero_()  # users outside the block: zero gradient rows (a fresh Adam step of g = 0 moves nothing)
+            bp.user_pass(Eu[lo:hi], Ei, self.r, self.u.dE[lo:hi])
+            bp.item_pass(Eu[lo:hi], self.r, self.i.dE)
+        else:
+            self.ip.user_pass(Eu, Ei, self.r, self.u.dE)
+            self.ip.item_pass(Eu, self.r, self.i.dE)
+        self.u.backward()  # local (needs dE_u only): its shared slices join the item-gradient exchange below
         fused = False
         if self.comm is not None:
-            fused = self.comm.sync_item_grad(self.i.dE, lr=lr, tower=self.i)
-        self.u.backward()
+            fused = self.comm.sync_grads(self, lr=lr)
         self.i.backward()
-        if self.comm is not None:
-            self.comm.sync_shared_grads(self.u, self.i)
         return fused
 
     # ---- epoch loop.  One step is ~15-25 short launches; on small problems (and on every multi-GPU step, where the
@@ -381,6 +465,10 @@ class TrainPlan:
         """``n_steps`` training steps (the body of the reference's epoch loop, matrix_factorization.py:129-180)."""
         n_steps = int(n_steps)
         use = self.USE_CUDA_GRAPH if graph is None else bool(graph)
+        if self.batched:  # one epoch = len(plans) different steps: eager
+            use = False
+        if getattr(self, "_graph_failed", False):  # a capture of THIS plan's step was refused: stay eager (other plans may still capture)
+            use = False
         if not use or self.opt_state is not None or n_steps < 3:
             for _ in range(n_steps):
                 self.step(lr)
@@ -414,7 +502,7 @@ class TrainPlan:
             print(f"[teamoflow_b200] CUDA graph capture of the training step failed ({type(e).__name__}: {e}); "
                   "running the epoch loop eagerly", file=sys.stderr)
             torch.cuda.synchronize()
-            TrainPlan.USE_CUDA_GRAPH = False
+            self._graph_failed = True
             self._graph = None
             return None
         self._graph_launches = _abi.launch_count - l0
@@ -423,11 +511,13 @@ class TrainPlan:
         return g
 
     def step(self, lr):
-        if self.opt_state is not None:  # stateful Adam (extension): the exchange kernel's fused fresh-Adam step does not apply
-            self.forward_backward()
-            self.u.update(lr, state=self.opt_state[0])
-            self.i.update(lr, state=self.opt_state[1])
-            return
-        fused = self.forward_backward(lr)
-        self.u.update(lr)
-        self.i.update(lr, skip=("W",) if fused else ())
+        """One epoch: a single full-batch step (the reference), or one step per mini-batch in mini-batch mode."""
+        for batch in (range(len(self.ip.plans)) if self.batched else (None,)):
+            if self.opt_state is not None:  # stateful Adam (extension): the exchange kernel's fused fresh-Adam step does not apply
+                self.forward_backward(batch=batch)
+                self.u.update(lr, state=self.opt_state[0])
+                self.i.update(lr, state=self.opt_state[1])
+                continue
+            fused = self.forward_backward(lr, batch=batch)
+            self.u.update(lr)
+            self.i.update(lr, skip=("W",) if fused else ())

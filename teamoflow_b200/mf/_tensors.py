@@ -83,6 +83,15 @@ class SparseInteractions:
         if self._csr is None:
             n_u, n_i = self.dense_shape
             rows64, cols64 = self.indices[:, 0], self.indices[:, 1]
+            if rows64.numel():
+                # ids outside dense_shape (e.g. 1-based MovieLens ids) would make the kernels gather rows past the end of
+                # the embedding tables; the reference's gather_nd raises there too (matrix_factorization.py:154)
+                lo_r, hi_r = torch.aminmax(rows64)
+                lo_c, hi_c = torch.aminmax(cols64)
+                lo_r, hi_r, lo_c, hi_c = torch.stack([lo_r, hi_r, lo_c, hi_c]).tolist()
+                if lo_r < 0 or lo_c < 0 or hi_r >= n_u or hi_c >= n_i:
+                    raise ValueError(f"interaction indices out of range for dense_shape {self.dense_shape}: rows in "
+                                     f"[{lo_r}, {hi_r}], cols in [{lo_c}, {hi_c}] (are the ids 1-based?)")
             key = rows64 * n_i + cols64
             perm = None
             if key.numel() > 1 and not bool((key[1:] >= key[:-1]).all()):

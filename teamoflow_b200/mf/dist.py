@@ -15,6 +15,8 @@ The reference has no distribution at all; this is the new-build desi
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -42,10 +44,16 @@ def balanced_user_bounds(row_lengths, world_size):
 
 
 class GradientSync:
-    """All-reduce hooks used by ``TrainPlan`` for user-sharded data-parallel training.
+    """Gradient exchange used by ``TrainPlan`` for user-sharded data-parallel training.
 
     ``shared_user_rows``: first row of ``W_u`` (or ``W_r`` for ReLU) that is shared by all ranks
     (side-feature rows after the rank-local identity block); ``None`` = no shared rows.
+
+    Peer path (default on GPUs): the item-side gradient lives in the NVLink peer arena and is summed by
+    ``tmf_peer_reduce_push`` (Adam step fused in for an identity-feature Linear item tower); the small gradients of
+    the shared user-side parameters are staged into the same arena and summed by a second launch between the SAME
+    two flag barriers -- a training step holds no NCCL work, so its captured CUDA graph is plain kernel launches.
+    Fallback (``peer=False`` or CUDA IPC refused): NCCL all-reduces.
     """
 
     def __init__(self, group=None, shared_user_rows=None, peer=True):
@@ -54,12 +62,11 @@ class GradientSync:
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bytes_reduced = 0
-        # peer=True: the item-side gradient is reduced by tmf_peer_reduce_push over NVLink peer memory (and, for an
-        # identity-feature Linear item tower, the Adam step is fused into the same kernel); False / IPC unavailable: NCCL
         self.peer = bool(peer) and self.world_size > 1 and torch.cuda.is_available()
         self._ar = None
-        self._dE = self._W = None
-        self._dE_off = self._W_off = None
+        self._plan = None
+        self._dE = self._W = self._stage = None
+        self._dE_off = self._W_off = self._stage_off = None
         self._rows = None
 
     def _allreduce(self, t):
@@ -67,21 +74,31 @@ class GradientSync:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.bytes_reduced += t.numel() * t.element_size()
 
+    # ---- peer arena life cycle
+
     def attach(self, plan):
-        """Move the item tower's gradient buffer (and, when the update can be fused, its weights) into peer memory.
-        Collective; called by ``TrainPlan``.  The arena is cached per group: one attached plan at a time."""
+        """Move the item tower's gradient buffer (and, when the update can be fused, its weights) into peer memory and
+        reserve the staging block of the shared user-side gradients.  Collective; called by ``TrainPlan``.  The arena
+        is cached per group: one attached plan at a time."""
         if not self.peer:
             return
         it = plan.i
         a256 = lambda n: (int(n) + 255) // 256 * 256  # noqa: E731
         fuse = it.kind == "linear" and it.X.identity
-        n_dE, n_W = a256(it.dE.numel() * 4), (a256(it.W.numel() * 4) if fuse else 0)
-        ar = peer_arena(n_dE + n_W, self.group, tag="grad")
+        tr = plan.u.trainables()
+        n_sh = sum(int((tr[k][start:] if start else tr[k]).numel()) for k, start in self._shared_slices(plan.u))
+        n_sh4 = (n_sh + 3) // 4  # float4 units, zero padded
+        n_dE, n_W, n_st = a256(it.dE.numel() * 4), (a256(it.W.numel() * 4) if fuse else 0), a256(n_sh4 * 16)
+        ar = peer_arena(n_dE + n_W + n_st, self.group, tag="grad")
         if ar is None:
             self.peer = False
             return
-        self._ar = ar
-        self._dE_off, self._W_off = 0, (n_dE if fuse else None)
+        for other in list(ar.views):  # a plan attached earlier (previous fit) gives the arena up first
+            if other is not self or other._plan is not plan:
+                other._arena_closing(ar)
+        self._ar, self._plan = ar, plan
+        ar.views = [self]
+        self._dE_off, self._W_off, self._stage_off = 0, (n_dE if fuse else None), n_dE + n_W
         self._dE = ar.local(0, tuple(it.dE.shape), torch.float32)
         self._dE.zero_()
         it.dE = self._dE
@@ -89,17 +106,69 @@ class GradientSync:
             self._W = ar.local(n_dE, tuple(it.W.shape), torch.float32)
             self._W.copy_(it.W)
             it.W = it.E = self._W
+        self._stage = None
+        if n_sh4:
+            self._stage = ar.local(self._stage_off, (n_sh4 * 4,), torch.float32)
+            self._stage.zero_()
+            self._stage_bounds = shard_bounds(n_sh4, self.world_size)
         self._rows = shard_bounds(it.dE.shape[0], self.world_size)
 
-    def detach(self, plan):
-        """End of fit: weights that live in the (shared, reusable) arena are copied out."""
-        it = plan.i
-        if self._W is not None and it.W.data_ptr() == self._W.data_ptr():
-            it.W = it.W.clone()
-            it.E = it.W
-        self._W = None
+    def _arena_closing(self, arena):
+        """The arena is about to be freed or handed to another plan: tensors of the attached plan move out of it."""
+        plan = self._plan
+        if plan is not None and self._ar is arena:
+            it = plan.i
+            if self._dE is not None and it.dE.data_ptr() == self._dE.data_ptr():
+                it.dE = it.dE.clone()
+            if self._W is not None and it.W.data_ptr() == self._W.data_ptr():
+                alias = it.E.data_ptr() == it.W.data_ptr()
+                it.W = it.W.clone()
+                if alias:
+                    it.E = it.W
+            if hasattr(plan, "invalidate_graph"):
+                plan.invalidate_graph()  # a captured step addresses the arena
+        if arena is not None and self in arena.views:
+            arena.views.remove(self)
+        self._ar = self._plan = None
+        self._dE = self._W = self._stage = None
 
-    def sync_item_grad(self, dEi, lr=None, tower=None):
+    def detach(self, plan):
+        """End of fit: the plan's tensors leave the (shared, reusable) arena; barrier time-outs surface here."""
+        ar = self._ar
+        if ar is not None:
+            ar.check()
+        if self._plan is plan:
+            self._arena_closing(ar)
+
+    # ---- the exchange of one step
+
+    def sync_grads(self, plan, lr=None):
+        """Everything a step exchanges, after the item-major pass and the USER tower's backward: ``dE_i`` (summed; with
+        ``lr`` the Adam step of an identity Linear item tower is fused in -> returns True and the caller skips that
+        update) and the shared user-side gradients (summed in place)."""
+        if self.world_size == 1:
+            return False
+        slices = self._shared_slices(plan.u)
+        peer = self._ar is not None and self._dE is not None and plan.i.dE.data_ptr() == self._dE.data_ptr()
+        if not peer:
+            self._allreduce(plan.i.dE)
+            self.sync_shared_grads(plan.u, plan.i)
+            return False
+        views = []
+        if self._stage is not None:
+            off = 0
+            for key, start in slices:
+                g = plan.u.grads[key]
+                g = (g[start:] if start else g).reshape(-1)
+                self._stage[off:off + g.numel()].copy_(g)
+                views.append((g, off))
+                off += g.numel()
+        fused = self.sync_item_grad(plan.i.dE, lr=lr, tower=plan.i, _with_stage=True)
+        for g, off in views:
+            g.copy_(self._stage[off:off + g.numel()])
+        return fused
+
+    def sync_item_grad(self, dEi, lr=None, tower=None, _with_stage=False):
         """Sum ``dE_i`` over the ranks (in place).  Returns True when the Adam step of ``tower.W`` was fused in
         (then ``dEi`` keeps the LOCAL partial and the caller must skip that update)."""
         if self.world_size == 1:
@@ -111,11 +180,17 @@ class GradientSync:
         ar, ld = self._ar, dEi.shape[1]
         lo, hi = self._rows[self.rank], self._rows[self.rank + 1]
         fused = (lr is not None and self._W is not None and tower is not None and tower.W.data_ptr() == self._W.data_ptr())
-        ar.barrier()  # every rank's partial is complete
+        ar.barrier()  # every rank's partials (and staged shared gradients) are complete
         _abi.call("tmf_peer_reduce_push", ar.ptrs(self._dE_off), ar.ptrs(self._W_off if fused else self._dE_off), self.world_size,
                   self.rank, lo * ld, (hi - lo) * ld, float(lr) if fused else -1.0)
-        ar.barrier()  # every rank's slice has landed everywhere; partial buffers may be rewritten
         self.bytes_reduced += dEi.numel() * 4
+        if _with_stage and self._stage is not None:
+            a, b = self._stage_bounds[self.rank], self._stage_bounds[self.rank + 1]
+            if b > a:
+                _abi.call("tmf_peer_reduce_push", ar.ptrs(self._stage_off), ar.ptrs(self._stage_off), self.world_size, self.rank,
+                          4 * a, 4 * (b - a), -1.0)
+            self.bytes_reduced += self._stage.numel() * 4
+        ar.barrier()  # every rank's slices have landed everywhere; partial buffers may be rewritten
         return fused
 
     def _shared_slices(self, u):
@@ -136,10 +211,15 @@ class GradientSync:
         return out
 
     def sync_shared_grads(self, u, i):
+        """NCCL form of the shared user-side gradient exchange (the peer path stages them, see ``sync_grads``)."""
         # the item tower's gradients are functions of the already-reduced dE_i: nothing to do there
         for key, start in self._shared_slices(u):
             g = u.grads[key]
             self._allreduce(g[start:] if start else g)
+
+    def allreduce_kl_moments(self, moments):
+        """KL under user sharding: the six additive fp64 sums of ``tmf_kl_moments`` (48 bytes) summed over the ranks."""
+        self._allreduce(moments)
 
     def broadcast_params(self, u, i):
         """Make replicated parameters identical at the start of fit (rank 0 wins)."""
@@ -154,8 +234,10 @@ class GradientSync:
 
     def mean_loss(self, ip):
         from . import _engine as eng
+        if self._ar is not None:
+            self._ar.check()
         if ip.loss == eng.KL:
-            raise NotImplementedError("KL's global moments are not sharded; run KL on one GPU")
+            return ip.mean_loss()  # the scalar is already global: every rank derived it from the summed moments
         local = ip.mean_loss()
         t = torch.tensor([0.0 if ip.n_pos == 0 else local * ip.n_pos, float(ip.n_pos)], dtype=torch.float64,
                          device=ip.vals.device)
@@ -184,41 +266,105 @@ class _DevMem:
 class PeerArena:
     """A block of this rank's HBM that every rank of the group can address directly over NVLink (CUDA IPC
     mappings of plain ``cudaMalloc`` memory, ``tmf_peer_alloc`` / ``tmf_ipc_*``), plus the flag pad of the
-    stream-ordered barrier (``tmf_peer_barrier``).  Collective: every rank constructs it with the same size."""
+    stream-ordered barrier (``tmf_peer_barrier``).  Collective: every rank constructs it with the same size.
+
+    Construction is collective-safe: the ranks agree (all-reduce MIN) after the local allocation + export and again
+    after mapping the peers' handles, so a rank that fails (out of memory, IPC refused) never leaves the others
+    inside a different collective; whatever the ranks that succeeded had built is released again and ``PeerArena.create``
+    returns ``None`` on every rank."""
 
     PAD_BYTES = 256
+    ERR_WORD = 33  # uint32 index inside the pad: 1 + missing rank after a barrier timeout (csrc/peer.cu kErrWord)
 
-    def __init__(self, nbytes, group=None):
+    def __init__(self):
+        raise TypeError("use PeerArena.create(nbytes, group)")
+
+    @classmethod
+    def create(cls, nbytes, group=None):
         import ctypes as C
+        import sys
         from .. import _abi
+        self = object.__new__(cls)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.nbytes = (int(nbytes) + 255) // 256 * 256
-        total = self.PAD_BYTES + self.nbytes
-        base = C.c_void_p()
-        _abi.call_nostream("tmf_peer_alloc", total, C.byref(base))
-        self._base = base.value
-        handle = C.create_string_buffer(64)
-        _abi.call_nostream("tmf_ipc_export", C.c_void_p(self._base), handle)
+        self.closed = False
+        self.views = []  # GradientSync instances whose plans hold tensors inside this arena (told before it is freed)
+        self._base = None
+        self.bases = []
+        self.timeout_ms = int(float(os.environ.get("TMF_PEER_TIMEOUT_S", "0")) * 1000)  # 0 = library default (120 s)
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def agree(ok):
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag) == 1
+
+        def report(stage, e):
+            print(f"[teamoflow_b200] peer memory unavailable on rank {self.rank} ({stage}: {type(e).__name__}: {e}); "
+                  "falling back to the NCCL exchange", file=sys.stderr, flush=True)
+
+        # ---- stage 1: local allocation + export
+        handle, ok = C.create_string_buffer(64), True
+        try:
+            base = C.c_void_p()
+            _abi.call_nostream("tmf_peer_alloc", self.PAD_BYTES + self.nbytes, C.byref(base))
+            self._base = base.value
+            _abi.call_nostream("tmf_ipc_export", C.c_void_p(self._base), handle)
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            report("allocate/export", e)
+        if not agree(ok):
+            self._release()
+            return None
+        # ---- stage 2: exchange the handles (every rank reaches this point) and map the peers' arenas
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=group)
-        self.bases = []
-        for g, h in enumerate(handles):
-            if g == self.rank:
-                self.bases.append(self._base)
-            else:
-                p = C.c_void_p()
-                _abi.call_nostream("tmf_ipc_open", C.create_string_buffer(h, 64), C.byref(p))
-                self.bases.append(p.value)
-        self.epoch = 0
-        self._mem = torch.as_tensor(_DevMem(self._base + self.PAD_BYTES, self.nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+        self.bases = [None] * self.world
+        try:
+            for g, h in enumerate(handles):
+                if g == self.rank:
+                    self.bases[g] = self._base
+                else:
+                    ptr = C.c_void_p()
+                    _abi.call_nostream("tmf_ipc_open", C.create_string_buffer(h, 64), C.byref(ptr))
+                    self.bases[g] = ptr.value
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            report("map peers", e)
+        if not agree(ok):
+            self._release()
+            return None
+        self._pad = torch.as_tensor(_DevMem(self._base, self.PAD_BYTES), device=dev).view(torch.int32)
+        self._mem = torch.as_tensor(_DevMem(self._base + self.PAD_BYTES, self.nbytes), device=dev)
         self._pads = (C.c_void_p * self.world)(*self.bases)
+        return self
+
+    def _release(self):
+        """Undo whatever this rank built (no collective inside)."""
+        import ctypes as C
+        from .. import _abi
+        for g, b in enumerate(self.bases):
+            if g != self.rank and b is not None:
+                try:
+                    _abi.call_nostream("tmf_ipc_close", C.c_void_p(b))
+                except Exception:  # noqa: BLE001
+                    pass
+        self.bases = []
+        self._mem = self._pad = None
+        if self._base is not None:
+            try:
+                _abi.call_nostream("tmf_peer_free", C.c_void_p(self._base))
+            except Exception:  # noqa: BLE001
+                pass
+            self._base = None
+        self.closed = True
 
     def local(self, offset, shape, dtype):
         """Tensor view of this rank's arena at byte ``offset`` (256-byte aligned offsets)."""
         n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
-        assert offset % 256 == 0 and offset + n <= self.nbytes
+        assert not self.closed and offset % 256 == 0 and offset + n <= self.nbytes
         return self._mem[offset:offset + n].view(dtype).reshape(shape)
 
     def ptrs(self, offset):
@@ -231,19 +377,28 @@ class PeerArena:
         from .. import _abi
         # epoch 0 = "next value of the device-side counter in this rank's pad": no per-call argument, so the launch can
         # be replayed from a CUDA graph (TrainPlan.run)
-        _abi.call("tmf_peer_barrier", self._pads, self.world, self.rank, 0)
+        _abi.call("tmf_peer_barrier", self._pads, self.world, self.rank, 0, self.timeout_ms)
+
+    def check(self):
+        """Raise if a barrier of this arena timed out on this rank (synchronises: reads one word of the pad).  Called
+        where the host synchronises anyway (loss read-out, end of fit, after a timed top-k)."""
+        if self.closed:
+            return
+        err = int(self._pad[self.ERR_WORD].item())
+        if err:
+            raise RuntimeError(f"peer barrier timed out on rank {self.rank} waiting for rank {err - 1} "
+                               "(TMF_PEER_TIMEOUT_S sets the limit); results of this exchange are invalid")
 
     def close(self):
-        from .. import _abi
-        import ctypes as C
+        """Collective: every rank's kernels have drained, then the mappings and the allocation go."""
+        if self.closed:
+            return
+        for v in list(self.views):
+            v._arena_closing(self)
+        self.views = []
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for g, b in enumerate(self.bases):
-            if g != self.rank:
-                _abi.call_nostream("tmf_ipc_close", C.c_void_p(b))
-        self._mem = None
-        _abi.call_nostream("tmf_peer_free", C.c_void_p(self._base))
-        self.bases = []
+        self._release()
 
 
 _arenas = {}
@@ -253,7 +408,6 @@ _peer_disabled = {}
 def peer_arena(nbytes, group=None, tag="default"):
     """The cached arena of ``group`` (grown collectively when too small), or None when peer memory is unavailable
     (IPC refused by the platform): callers then use the NCCL exchange.  The failure is reported once on stderr."""
-    import sys
     key = (id(group) if group is not None else 0, tag)
     if _peer_disabled.get(key):
         return None
@@ -261,18 +415,10 @@ def peer_arena(nbytes, group=None, tag="default"):
     if ar is not None and ar.nbytes >= nbytes:
         return ar
     if ar is not None:
-        ar.close()
+        ar.close()  # tensors of attached plans are moved out first (GradientSync._arena_closing)
         _arenas.pop(key)
-    ok = 1
-    try:
-        ar = PeerArena(nbytes, group)
-    except Exception as e:  # noqa: BLE001 -- any rank failing disables the peer path on all of them
-        print(f"[teamoflow_b200] peer memory unavailable on rank {dist.get_rank(group)} ({type(e).__name__}: {e}); "
-              "falling back to the NCCL exchange", file=sys.stderr, flush=True)
-        ok, ar = 0, None
-    flag = torch.tensor([ok], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag) == 0:
+    ar = PeerArena.create(nbytes, group)
+    if ar is None:
         _peer_disabled[key] = True
         return None
     _arenas[key] = ar

@@ -137,7 +137,7 @@ class MatrixFactorization:
             return [_public(tower.W, r), _public(tower.b, r)]
         return [_public(tower.W, r), _public(tower.Wr, tower.aux), _public(tower.br, tower.aux)]
 
-    def _prepare(self, user_features, item_features, tf_interactions, comm=None):
+    def _prepare(self, user_features, item_features, tf_interactions, comm=None, batch_size=None):
         """Everything ``fit`` does before its epoch loop (ref:110-123) plus the one-time device
         structures (CSR / item-major lists).  Returns the ``TrainPlan``."""
         Xu, Xi = as_features(user_features), as_features(item_features)
@@ -148,7 +148,10 @@ class MatrixFactorization:
         loss = self._loss_kind()
         tu = self._make_tower("user", self.user_repr_graph, self.user_weight_graph, Xu)
         ti = self._make_tower("item", self.item_repr_graph, self.item_weight_graph, Xi)
-        ip = eng.InteractionPlan(inter, loss, self.random_ind if loss == eng.WMRB else None)
+        if batch_size is None:
+            ip = eng.InteractionPlan(inter, loss, self.random_ind if loss == eng.WMRB else None)
+        else:
+            ip = eng.BatchedInteractions(inter, loss, self.random_ind if loss == eng.WMRB else None, batch_size)
         if loss == eng.WMRB:
             # the reference passes the constructor's n_items / n_samples to the loss (ref:165-167)
             if self.n_items is not None and self.n_items != n_items:
@@ -161,7 +164,7 @@ class MatrixFactorization:
         return self._plan
 
     def fit(self, epochs, user_features, item_features, tf_interactions, lr=1e-2, comm=None, verbose=True,
-            optimizer="fresh", resample_every=None, resample_seed=None):
+            optimizer="fresh", resample_every=None, resample_seed=None, batch_size=None):
         """Full-batch training, one gradient step per epoch (ref:96-187).
 
         Each epoch: embeddings -> scores of the observed (and sampled) pairs -> loss -> gradient of the
@@ -173,10 +176,13 @@ class MatrixFactorization:
           ``resample_every``  redraw the WMRB negatives every that many epochs with the device sampler (the reference
                               samples once per model, ref:72-73); ``resample_seed`` makes the draws reproducible.  The new
                               table replaces ``self.random_ind``; every table drawn is also kept in ``self._sample_log``.
+          ``batch_size``      mini-batch mode: USERS per mini-batch (contiguous blocks; MSE / WMRB).  An epoch is then one
+                              optimizer step per block, each on the summed loss of that block's interactions; ``None`` = the
+                              reference's full batch (ref:128).
         """
         if optimizer not in ("fresh", "adam"):
             raise ValueError("optimizer must be 'fresh' (reference behaviour) or 'adam'")
-        plan = self._prepare(user_features, item_features, tf_interactions, comm=comm)
+        plan = self._prepare(user_features, item_features, tf_interactions, comm=comm, batch_size=batch_size)
         if optimizer == "adam":
             plan.opt_state = ({}, {})
         if comm is not None:
@@ -226,10 +232,18 @@ class MatrixFactorization:
     # ------------------------------------------------------------------ prediction / ranking
 
     def predict(self, A=None):
-        """Dense ``U V^T`` (ref:189-201); with ``A`` also the scores of the unobserved cells."""
+        """Dense ``U V^T`` (ref:189-201); with ``A`` also the scores of the unobserved cells (``A == 0``) flattened
+        row-major (ref:197-198).  A sparse ``A`` (``SparseInteractions`` / scipy / torch sparse, distinct cells) is never
+        densified: the unobserved scores are gathered against its CSR (``tmf_gather_unobserved``)."""
         all_predictions = dense_scores(self.user_embedding, self.item_embedding)
         if A is not None:
-            A = A.to_dense() if isinstance(A, SparseInteractions) else to_device(A, torch.float32)
+            if _is_sparse_table(A):
+                n_u, n_i = all_predictions.shape
+                a_ptr, a_idx, _ = _csr_of(A, n_u, n_i, drop_zeros=True)
+                out = torch.empty(n_u * n_i - int(a_idx.numel()), dtype=torch.float32, device=all_predictions.device)
+                _abi.call("tmf_gather_unobserved", _abi.ptr(all_predictions), n_u, n_i, _abi.ptr(a_ptr), _abi.ptr(a_idx), _abi.ptr(out))
+                return all_predictions, out
+            A = to_device(A, torch.float32)
             return all_predictions, all_predictions[A == 0]
         return all_predictions
 
@@ -317,13 +331,81 @@ class MatrixFactorization:
             return ndcg[row_nnz > 0]
         return torch.where(~torch.isnan(ndcg), ndcg, torch.zeros_like(ndcg))
 
-    def retrieve_user_recs(self, user=None, k=None):
-        """Item rankings on RAW scores as a numpy int32 array (ref:416-438)."""
+    def retrieve_user_recs(self, user=None, k=None, exclude=None):
+        """Item rankings on RAW scores as a numpy int32 array (ref:416-438).
+
+        Extension (default = reference behaviour, which does NOT exclude seen items): ``exclude`` = an
+        interaction table (sparse or dense) whose non-zero cells are removed from every user's ranking -- "recommend k
+        unseen items" -- see ``recommend``."""
+        if exclude is not None:
+            if k is None:
+                raise ValueError("retrieve_user_recs(exclude=...) needs k")
+            out = self.recommend(exclude, k=k, users=None if user is None else [int(user)]).cpu().numpy().astype(np.int32)
+            return out if user is None else out[0]
         num_items = self.item_embedding.shape[0]
         users = None if user is None else torch.as_tensor([int(user)], device=self.user_embedding.device)
         idx = self._topk(num_items if k is None else k, clamp=False, users=users)
         out = idx.cpu().numpy().astype(np.int32)
         return out if user is None else out[0]
+
+    def recommend(self, seen, k=10, users=None):
+        """Masked top-k (extension): the ``k`` best items per user by RAW canonical score, ties -> lower item id,
+        EXCLUDING the non-zero cells of the interaction table ``seen`` (sparse or dense, never densified).  int32 ``[n, k]``
+        on the device; a user with fewer than ``k`` unseen items has its row padded with -1.
+
+        The fused tcgen05 top-k produces each row's top-``kc`` list (``kc = min(k + heaviest row, 128)``) and
+        ``tmf_filter_seen`` keeps the first ``k`` unseen entries; the few rows that have more seen items among their
+        top-``kc`` than the list can absorb are ranked exactly (dense canonical scores of those rows, seen cells masked)."""
+        n_u, n_i = self.user_embedding.shape[0], self.item_embedding.shape[0]
+        a_ptr, a_idx, _ = _csr_of(seen, n_u, n_i, drop_zeros=True)
+        dev = self.user_embedding.device
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        rows = None
+        if users is not None:
+            rows = torch.as_tensor(users, device=dev, dtype=torch.int64).reshape(-1)
+            cnt = (a_ptr[1:] - a_ptr[:-1])[rows]
+            sub_ptr = torch.zeros(rows.numel() + 1, dtype=torch.int32, device=dev)
+            sub_ptr[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+            take = torch.repeat_interleave(a_ptr[:-1][rows].to(torch.int64) - sub_ptr[:-1].to(torch.int64), cnt.to(torch.int64)) \
+                + torch.arange(int(sub_ptr[-1]), device=dev)
+            a_ptr, a_idx = sub_ptr, a_idx[take].contiguous()
+        n = n_u if rows is None else int(rows.numel())
+        out = torch.full((n, k), -1, dtype=torch.int32, device=dev)
+        if n == 0:
+            return out
+        row_nnz = (a_ptr[1:] - a_ptr[:-1])
+        kk = min(k, n_i)
+        kc = min(n_i, TOPK_FUSED_MAX_K, kk + int(row_nnz.max()))
+        short = torch.ones(n, dtype=torch.int32, device=dev)
+        if kc >= kk and kk <= TOPK_FUSED_MAX_K:
+            cand = self._topk(kc, clamp=False, users=rows)
+            got = torch.empty(n, kk, dtype=torch.int32, device=dev)
+            _abi.call("tmf_filter_seen", _abi.ptr(cand), None, n, kc, kk, _abi.ptr(a_ptr), _abi.ptr(a_idx), _abi.ptr(got), None,
+                      _abi.ptr(short))
+            ok = short == 0
+            out[ok, :kk] = got[ok]
+        todo = torch.nonzero(short).reshape(-1)
+        # exact fallback, a bounded block of rows at a time: dense canonical scores, seen cells -> -inf, stable ranking
+        U, V = eng.storage_of(self.user_embedding), eng.storage_of(self.item_embedding)
+        block = max(1, min(4096, (1 << 27) // max(n_i, 1)))
+        for b0 in range(0, int(todo.numel()), block):
+            sel = todo[b0:b0 + block]
+            gu = sel if rows is None else rows[sel]
+            Ub = U[gu].contiguous()
+            P = torch.empty(sel.numel(), n_i, dtype=torch.float32, device=dev)
+            _abi.call("tmf_predict_dense", _abi.ptr(Ub), Ub.shape[0], _abi.ptr(V), n_i, self.n_components, U.shape[1], _abi.ptr(P))
+            c = row_nnz[sel].to(torch.int64)
+            rr = torch.repeat_interleave(torch.arange(sel.numel(), device=dev), c)
+            first = torch.repeat_interleave(a_ptr[:-1][sel].to(torch.int64) - (torch.cumsum(c, 0) - c), c)
+            cols = a_idx[first + torch.arange(int(c.sum()), device=dev)].long()
+            P[rr, cols] = float("-inf")
+            order = _rank_rows(P, clamp=False)[:, :kk]
+            unseen = (n_i - c).clamp(max=kk)
+            order = torch.where(torch.arange(kk, device=dev)[None, :] < unseen[:, None], order, torch.full_like(order, -1))
+            out[sel, :kk] = order
+        return out
 
     # ------------------------------------------------------------------ save / load (in-memory, ref:440-475)
 
@@ -343,7 +425,8 @@ class MatrixFactorization:
         config = {"n_components": self.n_components, "user_repr_graph": type(self.user_repr_graph).__name__,
                   "item_repr_graph": type(self.item_repr_graph).__name__, "loss_graph": type(self.loss_graph).__name__,
                   "user_weight_graph": type(self.user_weight_graph).__name__, "item_weight_graph": type(self.item_weight_graph).__name__,
-                  "n_users": self.n_users, "n_items": self.n_items, "n_samples": self.n_samples}
+                  "n_users": self.n_users, "n_items": self.n_items, "n_samples": self.n_samples,
+                  "generate_sample": bool(self.generate_sample)}
         c = lambda x: None if x is None else x.detach().cpu()  # noqa: E731
         state = {"user_embedding": c(getattr(self, "user_embedding", None)), "item_embedding": c(getattr(self, "item_embedding", None)),
                  "user_trainable": None if self.user_trainable is None else [c(v) for v in self.user_trainable],
@@ -355,20 +438,36 @@ class MatrixFactorization:
         torch.save({"format": "teamoflow_b200.mf/1", "config": config, "state": state}, path)
 
     @classmethod
-    def load(cls, path, initializers=None):
-        """Rebuild a model written by ``save``.  Custom ``Initializer`` subclasses are not serialised: pass
-        ``initializers=(user_weight_graph, item_weight_graph)`` to restore them (default: ``NormalInitializer``)."""
+    def load(cls, path, initializers=None, graphs=None):
+        """Rebuild a model written by ``save``.  Class names in the file are resolved through a fixed table of the
+        package's own graph classes (nothing else can be instantiated from a file).  User-defined subclasses are not
+        serialised: pass ``initializers=(user_weight_graph, item_weight_graph)`` and / or
+        ``graphs={"user_repr_graph": obj, "item_repr_graph": obj, "loss_graph": obj}`` (instances) to restore them."""
         from . import embedding_graphs as _E, initializer_graphs as _I, loss_graphs as _L
+        known = {"LinearEmbedding": _E.LinearEmbedding, "BiasedLinearEmbedding": _E.BiasedLinearEmbedding,
+                 "ReLUEmbedding": _E.ReLUEmbedding, "MSELoss": _L.MSELoss, "WMRBLoss": _L.WMRBLoss,
+                 "KLDivergenceLoss": _L.KLDivergenceLoss}
+        known_init = {"NormalInitializer": _I.NormalInitializer, "UniformInitializer": _I.UniformInitializer}
         blob = torch.load(path, map_location="cpu", weights_only=True)
         if blob.get("format") != "teamoflow_b200.mf/1":
             raise ValueError("not a teamoflow_b200 model file")
         cfg, st = dict(blob["config"]), blob["state"]
-        for key, mod in (("user_repr_graph", _E), ("item_repr_graph", _E), ("loss_graph", _L)):
-            cfg[key] = getattr(mod, cfg[key])()
+        graphs = dict(graphs or {})
+        for key in ("user_repr_graph", "item_repr_graph", "loss_graph"):
+            if graphs.get(key) is not None:
+                cfg[key] = graphs[key]
+            elif cfg[key] in known:
+                cfg[key] = known[cfg[key]]()
+            else:
+                raise ValueError(f"{key} = {cfg[key]!r} is not one of the package's graph classes {sorted(known)}; "
+                                 f"pass an instance through load(..., graphs={{'{key}': obj}})")
         for j, key in enumerate(("user_weight_graph", "item_weight_graph")):
             given = None if initializers is None else initializers[j]
-            cfg[key] = given if given is not None else getattr(_I, cfg[key], _I.NormalInitializer)()
+            cfg[key] = given if given is not None else known_init.get(cfg[key], _I.NormalInitializer)()
+        # the sampled negatives are restored from the file below; do not draw a new table in the constructor
+        generate_sample = bool(cfg.pop("generate_sample", False))
         model = cls(**cfg)
+        model.generate_sample = generate_sample
         r = model.n_components
         g = lambda x: None if x is None else to_device(x, x.dtype)  # noqa: E731
         if st["user_embedding"] is not None:
@@ -426,10 +525,26 @@ def _rank_rows(P, clamp):
     return out
 
 
-def _csr_of(A, n_users, n_items):
-    """Interaction table (dense like the reference, or sparse) -> CSR on the device."""
+def _is_sparse_table(A):
+    if isinstance(A, SparseInteractions):
+        return True
+    if isinstance(A, torch.Tensor):
+        return A.layout != torch.strided
+    try:
+        from scipy import sparse as _sp
+        return _sp.issparse(A)
+    except Exception:  # pragma: no cover
+        return False
+
+
+def _csr_of(A, n_users, n_items, drop_zeros=False):
+    """Interaction table (dense like the reference, or sparse) -> CSR on the device.  ``drop_zeros``: explicitly stored
+    zeros are removed (they count as unobserved for ``A == 0``)."""
     inter = as_interactions(A)
     if inter.dense_shape != (n_users, n_items):
         raise ValueError(f"interaction table has shape {inter.dense_shape}, model has {(n_users, n_items)}")
+    if drop_zeros and inter.nnz and bool((inter.values == 0).any()):
+        keep = inter.values != 0
+        inter = SparseInteractions(inter.indices[keep], inter.values[keep], inter.dense_shape)
     row_ptr, col_idx, vals, _, _ = inter.csr()
     return row_ptr, col_idx, vals

@@ -450,6 +450,17 @@ def test_peer_alloc_export_and_barrier_single_rank():
     assert any(handle.raw)
     pads = (C.c_void_p * 1)(base.value)
     for epoch in (1, 2, 3):
-        _abi.call("tmf_peer_barrier", pads, 1, 0, epoch)
+        _abi.call("tmf_peer_barrier", pads, 1, 0, epoch, 0)
     torch.cuda.synchronize()
+    # a rank that never arrives: the barrier gives up after timeout_ms, flags the pad (byte 132 = 1 + missing rank) and
+    # returns -- no trap, the CUDA context stays usable
+    pads2 = (C.c_void_p * 2)(base.value, base.value + 2048)  # "rank 1" is a second pad nobody signals from
+    _abi.call("tmf_peer_barrier", pads2, 2, 0, 7, 50)
+    torch.cuda.synchronize()
+    from teamoflow_b200.mf.dist import _DevMem
+    pad = torch.as_tensor(_DevMem(base.value, 256), device="cuda").view(torch.int32)
+    assert int(pad[33]) == 2
+    _abi.call("tmf_fill_uniform", _abi.ptr(torch.empty(4, 4, device="cuda")), 4, 4, 4, 1)  # the context is alive
+    torch.cuda.synchronize()
+    del pad
     _abi.call_nostream("tmf_peer_free", base)

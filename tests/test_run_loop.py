@@ -82,4 +82,7 @@ def test_refused_capture_falls_back_to_the_eager_loop(monkeypatch, capsys):
     plan.run(4, 0.1)
     assert calls["eager"] == 4 and _Graph.replays == 0 and _abi.launch_count - l0 == 4 * LAUNCHES_PER_STEP
     assert "capture of the training step failed" in capsys.readouterr().err
-    assert eng.TrainPlan.USE_CUDA_GRAPH is False  # not retried (monkeypatch restores the class attribute)
+    # the failure is recorded on THIS plan only: other plans of the process may still capture
+    assert plan._graph_failed is True and eng.TrainPlan.USE_CUDA_GRAPH is True
+    plan.run(4, 0.1)  # not retried
+    assert calls["eager"] == 8 and _Graph.replays == 0
