@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the matrix-factorization hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c4mini]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c4|c4mini]
 
 Primary line (one JSON object on stdout, rank 0):
   metric  = training interactions/s, WMRB rank-64 on the ML-20M-shaped synthetic workload (BASELINE.json
@@ -11,12 +11,17 @@ Primary line (one JSON object on stdout, rank 0):
   e2e     = the same metric through MatrixFactorization.fit() from pinned HOST buffers (H2D of interactions
             and features, structure build, K epochs, D2H of the loss) -- one fit call of K epochs;
   roofline= dominant training kernel vs measured HBM peak; step_roofline = whole step vs SURVEY 8(d) B_alg;
+  parity_check = sampled oracle checks of the very state the timed loops left behind: c3 (and c4) -- losses and dE_u of
+            512 users and complete dE_i rows of 16 items against oracle.train_step_sparse restricted to those users;
+            c5 -- 64 rows of the top-k result bit for bit against the canonical score + (score desc, id asc);
+  c4      = BASELINE.json configs[3]: ONE 10M x 2M, 500M-interaction rank-128 problem, user-sharded over the N ranks
+            (strong scaling; the same dataset at every N, split by balanced user ranges);
   topk    = secondary metric of BASELINE.json: scored user-item pairs/s of the fused tcgen05 top-100
-            (1M x 1M rank-128 by default) with its tensor roofline;
-  cpu_baseline = the reference-faithful dense CPU step (oracle/autograd_twin, torch-CPU) on a bounded user
-            sample of the same workload.
-N > 1 (torchrun): users are sharded, every rank holds its own C3-sized user shard ("weak" scaling), the
-item gradient is all-reduced over NCCL each epoch.
+            (1M x 1M rank-128 by default, item-sharded over the N ranks) with its tensor roofline;
+  cpu_baseline = the reference-faithful dense CPU step (oracle/autograd_twin, torch-CPU) on bounded user samples of the
+            same workload, item-side fixed cost separated and extrapolated to the full user count (stated as such).
+N > 1 (torchrun): users are sharded, every rank holds its own C3-sized user shard ("weak" scaling), the item gradient is
+summed over NVLink peer memory each epoch (NCCL all-reduce as the fallback).
 """
 import argparse
 import json
@@ -40,12 +45,13 @@ WORKLOADS = {
                desc="ML-100K-shaped synthetic: 943 x 1682, 100k interactions (ratings>=4 positive), rank 32, WMRB S=336"),
     "c1": dict(n_u=1000, n_i=1000, nnz=10_000, r=10, S=0, mu=None, mi=None,
                desc="toy 1k x 1k, density 0.01, rank 10, MSE"),
-    # BASELINE.json configs[3]: ONE 10M x 2M problem, user-sharded over the ranks (strong scaling; per-rank sizes = total / world)
+    # BASELINE.json configs[3]: ONE 10M x 2M problem, user-sharded over the ranks (strong scaling: the SAME dataset at every N)
     "c4": dict(n_u=10_000_000, n_i=2_000_000, nnz=500_000_000, r=128, S=32, mu=None, mi=None, strong=True,
                desc="10M users x 2M items, 500M interactions, rank 128, WMRB S=32, identity features, user-sharded data parallel"),
     "c4mini": dict(n_u=1_250_000, n_i=2_000_000, nnz=62_500_000, r=128, S=32, mu=None, mi=None,
                    desc="1/8 user shard of the 10M x 2M, 500M-interaction rank-128 WMRB S=32 problem"),
 }
+PARITY_TOL = 1e-5  # north_star: losses, gradients and scores within 1e-5 relative in fp32
 
 
 def log(*a):
@@ -85,7 +91,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def __enter__(self):
         if self.h is not None:
@@ -129,6 +135,7 @@ def gen_interactions(n_u, n_i, nnz, seed, dev):
         u = torch.multinomial(wu, m, replacement=True, generator=g)
         i = torch.multinomial(wi, m, replacement=True, generator=g)
         keys = torch.unique(torch.cat([keys, u * n_i + i]))
+        del u, i
     if keys.numel() > nnz:
         sel = torch.randperm(keys.numel(), generator=g, device=dev)[:nnz]
         keys = keys[sel].sort().values
@@ -166,20 +173,38 @@ def alg_bytes(w, nnz, n_pos, Fu, Fi, nnz_xu, nnz_xi):
 
 
 class Workload:
-    def __init__(self, name, rank, world):
-        import scipy.sparse as sp
+    """Synthetic inputs of one configuration.  Weak-scaling workloads (c3 ...): every rank draws its own shard.  Strong-scaling
+    workloads (c4): every rank generates the SAME full dataset (same seed), then keeps the contiguous user range
+    ``dist.balanced_user_bounds`` assigns to it (equal interactions + sampled negatives per rank), user ids re-based."""
+
+    def __init__(self, name, rank, world, host_copy=True):
+        from teamoflow_b200.mf import dist as tdist
         from teamoflow_b200.mf import initializer_graphs as I, loss_graphs as L
         from teamoflow_b200.mf.matrix_factorization import MatrixFactorization
         from teamoflow_b200.mf.utils import random_sampler
         self.w = w = dict(WORKLOADS[name])
-        if w.get("strong"):  # one fixed problem split over the ranks
-            w["n_u"], w["nnz"] = w["n_u"] // world, w["nnz"] // world
         self.name, self.rank, self.world = name, rank, world
         dev = torch.device("cuda", torch.cuda.current_device())
-        n_u, n_i, r, S = w["n_u"], w["n_i"], w["r"], w["S"]
+        n_i, r, S = w["n_i"], w["r"], w["S"]
         seed = 20240 + {"c1": 1, "c2": 2, "c3": 3, "c4mini": 4, "c4": 4}[name]
         t0 = time.time()
-        rows, cols = gen_interactions(n_u, n_i, w["nnz"], seed * 1000 + rank, dev)
+        self.total_nnz = None
+        if w.get("strong"):
+            rows, cols = gen_interactions(w["n_u"], n_i, w["nnz"], seed * 1000, dev)  # identical on every rank
+            self.total_nnz = int(rows.numel())
+            lens = torch.bincount(rows, minlength=w["n_u"])
+            bounds = tdist.balanced_user_bounds((lens + S).cpu().numpy(), world)  # a user costs its interactions + its S negatives
+            lo, hi = bounds[rank], bounds[rank + 1]
+            csum = torch.cumsum(lens, 0)
+            a = int(csum[lo - 1]) if lo > 0 else 0
+            b = int(csum[hi - 1]) if hi > 0 else 0
+            rows, cols = (rows[a:b] - lo).clone(), cols[a:b].clone()
+            del lens, csum
+            torch.cuda.empty_cache()
+            w["n_u_total"], w["n_u"], self.user_range = w["n_u"], hi - lo, (lo, hi)
+        else:
+            rows, cols = gen_interactions(w["n_u"], n_i, w["nnz"], seed * 1000 + rank, dev)
+        n_u = w["n_u"]
         self.nnz = int(rows.numel())
         if name == "c2":  # ratings 1..5 with P=(.06,.11,.27,.34,.22); train on ratings >= 4 (benchmarking_ML.py:38,61)
             g = torch.Generator(device=dev); g.manual_seed(seed)
@@ -191,9 +216,16 @@ class Workload:
         else:
             vals = torch.ones(self.nnz, dtype=torch.float32, device=dev)
         self.n_pos = int((vals > 0).sum())
-        # pinned host copies: the inputs a user of the plugin API holds
-        self.h_indices = torch.stack([rows, cols], 1).cpu().pin_memory()
-        self.h_vals = vals.cpu().pin_memory()
+        idx32 = torch.stack([rows, cols], 1).to(torch.int32)
+        del rows, cols
+        if host_copy:
+            # pinned host copies: the inputs a user of the plugin API holds (int32 ids: half the H2D bytes of tf's int64)
+            self.h_indices = idx32.cpu().pin_memory()
+            self.h_vals = vals.cpu().pin_memory()
+            self.d_indices = self.d_vals = None
+        else:
+            self.h_indices = self.h_vals = None
+            self.d_indices, self.d_vals = idx32, vals
         self.Xu = side_features(n_u, n_u, w["mu"], seed + 11) if w["mu"] else None
         self.Xi = side_features(n_i, n_i, w["mi"], seed + 12) if w["mi"] else None
         self.Fu = n_u + (w["mu"][0] if w["mu"] else 0)
@@ -208,7 +240,7 @@ class Workload:
         self.lr = 0.1 if S else 1e-2
         self.bytes = alg_bytes(w, self.nnz, self.n_pos, self.Fu, self.Fi,
                                self.Xu.nnz if self.Xu is not None else 0, self.Xi.nnz if self.Xi is not None else 0)
-        log(f"[rank {rank}] workload {name}: nnz={self.nnz} n_pos={self.n_pos} built in {time.time() - t0:.1f}s; "
+        log(f"[rank {rank}] workload {name}: n_users={n_u} nnz={self.nnz} n_pos={self.n_pos} built in {time.time() - t0:.1f}s; "
             f"B_alg/epoch={self.bytes['total'] / 1e9:.3f} GB")
 
     def feature_args(self):
@@ -217,23 +249,26 @@ class Workload:
         xi = self.Xi if self.Xi is not None else FeatureMatrix.eye(self.w["n_i"])
         return xu, xi
 
-    def interactions_host(self):
-        return (self.h_indices, self.h_vals, (self.w["n_u"], self.w["n_i"]))
+    def interactions(self):
+        shape = (self.w["n_u"], self.w["n_i"])
+        if self.h_indices is not None:
+            return (self.h_indices, self.h_vals, shape)
+        return (self.d_indices, self.d_vals, shape)
 
     def h2d_bytes(self):
-        b = self.h_indices.numel() * 8 + self.h_vals.numel() * 4
+        b = self.h_indices.numel() * self.h_indices.element_size() + self.h_vals.numel() * 4
         for X in (self.Xu, self.Xi):
             if X is not None:
                 b += X.indptr.nbytes // 2 + X.indices.nbytes + X.data.nbytes  # indptr goes down as int32
         return b
 
 
-# ------------------------------------------------------------------------------------------- phase profile
+# ------------------------------------------------------------------------------------------- training bench
 
 
 def profile_phases(plan, lr, reps=3):
-    """CUDA-event time of each phase of the step (separate from the timed region)."""
-    names = ["embed_fwd", "user_pass", "item_pass", "comm", "embed_bwd", "adam"]
+    """CUDA-event time of each phase of the step (a separate pass, not the timed region)."""
+    names = ["embed_fwd", "user_pass", "item_pass", "user_bwd", "comm", "item_bwd", "adam"]
     acc = {n: 0.0 for n in names}
     for _ in range(reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
@@ -241,18 +276,245 @@ def profile_phases(plan, lr, reps=3):
         Eu = plan.u.forward(); Ei = plan.i.forward(); ev[1].record()
         plan.ip.user_pass(Eu, Ei, plan.r, plan.u.dE); ev[2].record()
         plan.ip.item_pass(Eu, plan.r, plan.i.dE); ev[3].record()
+        plan.u.backward(); ev[4].record()
+        fused = False
         if plan.comm is not None:
-            plan.comm.sync_item_grad(plan.i.dE)
-        ev[4].record()
-        plan.u.backward(); plan.i.backward()
-        if plan.comm is not None:
-            plan.comm.sync_shared_grads(plan.u, plan.i)
+            fused = plan.comm.sync_grads(plan, lr=lr)
         ev[5].record()
-        plan.u.update(lr); plan.i.update(lr); ev[6].record()
+        plan.i.backward(); ev[6].record()
+        plan.u.update(lr); plan.i.update(lr, skip=("W",) if fused else ()); ev[7].record()
         torch.cuda.synchronize()
         for j, n in enumerate(names):
             acc[n] += ev[j].elapsed_time(ev[j + 1]) / reps
+    acc["embed_bwd"] = acc.pop("user_bwd") + acc.pop("item_bwd")
     return acc
+
+
+KERNEL_OF = {"user_pass": "user_pass_kernel", "item_pass": "spmm_seg_kernel (item-major)", "embed_fwd": "spmm_seg_kernel (X.W)",
+             "embed_bwd": "spmm_seg_kernel (X^T.dE)", "adam": "adam1_kernel"}
+
+
+def train_bench(wl, comm, steps, warmup, local, world, hbm_peak):
+    """Device-resident timing of `steps` epochs of `wl` (inputs and structures already in HBM): returns the plan and a dict."""
+    from teamoflow_b200 import _abi
+    dev = torch.device("cuda", local)
+    xu, xi = wl.feature_args()
+    plan = wl.model._prepare(xu, xi, wl.interactions(), comm=comm)
+    if comm is not None:
+        comm.broadcast_params(plan.u, plan.i)
+    # warm-up through the same entry point as the timed loop (TrainPlan.run = the body of fit()'s epoch loop: first step
+    # eager, the rest replayed from ONE captured CUDA graph of a step); the capture happens here
+    plan.run(max(warmup, 3), wl.lr)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    l0 = _abi.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        plan.run(steps, wl.lr)
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+    launches = _abi.launch_count - l0
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
+    ms_step = float(ms_total) / steps
+    loss_now = plan.ip.mean_loss() if comm is None else comm.mean_loss(plan.ip)
+    phases = profile_phases(plan, wl.lr)
+    phase_bytes = {"user_pass": wl.bytes["user_pass"], "item_pass": wl.bytes["item_pass"],
+                   "embed_fwd": wl.bytes["features"] / 2, "embed_bwd": wl.bytes["features"] / 2, "adam": wl.bytes["adam"]}
+    dom = max(KERNEL_OF, key=lambda n: phases[n])
+    dom_gbs = phase_bytes[dom] / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
+    step_gbs = wl.bytes["total"] / (ms_step * 1e-3) / 1e9
+    return plan, dict(ms_step=ms_step, launches=launches, loss=loss_now, phases=phases, dom=dom, dom_gbs=dom_gbs, step_gbs=step_gbs,
+                      phase_bytes=phase_bytes, clocks=clk.summary())
+
+
+# ------------------------------------------------------------------------------------------- sampled parity checks
+
+
+def _rel_err(got, want):
+    want = np.asarray(want, np.float64)
+    scale = max(float(np.abs(want).max()) if want.size else 0.0, 1e-30)
+    return float(np.abs(np.asarray(got, np.float64) - want).max() / scale) if want.size else 0.0
+
+
+def parity_train_sample(plan, n_us=512, n_is=16, seed=1, max_len=200_000):
+    """Checks the CUDA training step against the oracle on a sample, at the weights the timed loop left behind.
+
+    Runs the step's kernels once more WITHOUT an update (embed -> user pass -> item-major pass; under user sharding this is
+    the rank's LOCAL partial dE_i, before the exchange), then compares on the host:
+      (A) `n_us` users (random, plus the heaviest one): per-interaction losses and their dE_u rows against
+          oracle.train_step_sparse run on exactly those users (their interactions, their negatives, the item rows they touch);
+      (B) `n_is` items: their COMPLETE dE_i rows against the same oracle run on ALL users whose interactions or negatives
+          touch those items (so the oracle's rows are complete too).
+    The WMRB indicator 1[h >= 0] is discontinuous: a hinge whose fp64 value is within the fp32 rounding of its two dot products
+    of 0 (|h| < 4e-6 (1 + sum|u_c v_c|)) may legitimately fall on the other side in fp32, so users holding such a hinge are excluded from the dE_u comparison and items they touch from the
+    dE_i comparison (counted in the result); losses are continuous and are compared for every sampled interaction."""
+    from oracle import mf_oracle as o
+    from scipy import sparse
+    from teamoflow_b200.mf import _engine as eng
+    ip, r = plan.ip, plan.r
+    wmrb = ip.loss == eng.WMRB
+    Eu = plan.u.forward(); Ei = plan.i.forward()
+    ip.user_pass(Eu, Ei, r, plan.u.dE)
+    ip.item_pass(Eu, r, plan.i.dE)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(seed)
+    row_ptr = ip.row_ptr
+    lens = (row_ptr[1:] - row_ptr[:-1])
+    n_users, n_items, S = ip.n_users, ip.n_items, ip.S
+
+    def run(users):
+        """oracle on the sub-problem of `users` (sorted, unique): returns losses per interaction position, dE_u rows,
+        (item id -> dE_i row) for every touched item, ambiguous-user mask, ambiguous item set."""
+        ut = torch.as_tensor(users, device=row_ptr.device, dtype=torch.int64)
+        a, b = row_ptr[ut].long(), row_ptr[ut + 1].long()
+        cnt = (b - a)
+        pos = torch.repeat_interleave(a - (torch.cumsum(cnt, 0) - cnt), cnt) + torch.arange(int(cnt.sum()), device=ut.device)
+        sub_rows = torch.repeat_interleave(torch.arange(ut.numel(), device=ut.device), cnt).cpu().numpy()
+        cols = ip.col_idx[pos].long()
+        vals = ip.vals[pos].cpu().numpy().astype(np.float64)
+        samp = ip.samp[ut].long() if wmrb else None
+        touched = torch.unique(torch.cat([cols, samp.reshape(-1)]) if wmrb else cols)
+        remap = torch.full((n_items,), -1, dtype=torch.int64, device=ut.device)
+        remap[touched] = torch.arange(touched.numel(), device=ut.device)
+        Eu_s = Eu[ut, :r].double().cpu().numpy()
+        Ei_s = Ei[touched, :r].double().cpu().numpy()
+        cols_s = remap[cols].cpu().numpy()
+        samp_s = remap[samp].cpu().numpy() if wmrb else None
+        lvec, gu, gi, _, _ = o.train_step_sparse(ip.loss, sparse.identity(len(users), format="csr"),
+                                                 sparse.identity(int(touched.numel()), format="csr"), "linear", "linear",
+                                                 {"W": Eu_s}, {"W": Ei_s}, sub_rows, cols_s, vals, samp_s, n_items, S or None, update=False)
+        amb_user = np.zeros(len(users), bool)
+        amb_items = np.zeros(0, np.int64)
+        if wmrb:
+            # a hinge is ambiguous when |h| is within the fp32 rounding of its two dot products: 4e-6 * (1 + sum|u_c v_c| of both)
+            p = np.einsum("kc,kc->k", Eu_s[sub_rows], Ei_s[cols_s])
+            pa = np.einsum("kc,kc->k", np.abs(Eu_s)[sub_rows], np.abs(Ei_s)[cols_s])
+            Es = Ei_s[samp_s.ravel()].reshape(len(users), S, -1)
+            ss = np.einsum("uc,usc->us", Eu_s, Es)
+            sa = np.einsum("uc,usc->us", np.abs(Eu_s), np.abs(Es))
+            del Es
+            pk = np.nonzero(vals > 0)[0]
+            amb_k, amb_j = [], []
+            for c0 in range(0, pk.size, 1 << 15):
+                kk = pk[c0:c0 + (1 << 15)]
+                h = (1.0 - p[kk])[:, None] + ss[sub_rows[kk]]
+                ak, aj = np.nonzero(np.abs(h) < 4e-6 * (1.0 + pa[kk][:, None] + sa[sub_rows[kk]]))
+                amb_k.append(kk[ak]); amb_j.append(samp_s[sub_rows[kk[ak]], aj])
+            amb_k = np.concatenate(amb_k) if amb_k else np.zeros(0, np.int64)
+            amb_user[sub_rows[amb_k]] = True
+            amb_items = np.unique(np.concatenate([cols_s[amb_k], np.concatenate(amb_j) if amb_j else np.zeros(0, np.int64)]))
+        return dict(pos=pos, lvec=lvec, vals=vals, dEu=gu["W"], dEi=gi["W"], touched=touched.cpu().numpy(), amb_user=amb_user,
+                    amb_items=amb_items, ut=ut)
+
+    out = {"tolerance": PARITY_TOL, "loss": ip.loss}
+    # ---- (A) users
+    cand = torch.nonzero((lens > 0) & (lens <= max_len)).reshape(-1).cpu().numpy()
+    users = rng.choice(cand, size=min(n_us, cand.size), replace=False)
+    heavy = int(torch.argmax(torch.where(lens <= max_len, lens, torch.zeros_like(lens))))
+    users = np.unique(np.concatenate([users, [heavy]]))
+    A = run(users)
+    lk = ip.loss_k[A["pos"]].double().cpu().numpy()
+    got_l = lk[A["vals"] > 0] if wmrb else lk
+    out["users"] = int(users.size)
+    out["interactions"] = int(A["pos"].numel())
+    out["heaviest_user_interactions"] = int(lens[heavy])
+    out["loss_max_rel_err"] = _rel_err(got_l, A["lvec"])
+    keep = ~A["amb_user"]
+    out["ambiguous_users_excluded"] = int(A["amb_user"].sum())
+    got_dEu = plan.u.dE[A["ut"], :r].double().cpu().numpy()
+    out["dEu_max_rel_err"] = _rel_err(got_dEu[keep], A["dEu"][keep])
+    # ---- (B) items: complete rows need every user that touches the item (interactions and negatives)
+    t_ptr = ip.t_ptr
+    tl = (t_ptr[1:] - t_ptr[:-1])
+
+    def entries_of(items):
+        it = torch.as_tensor(items, device=t_ptr.device, dtype=torch.int64)
+        a, b = t_ptr[it].long(), t_ptr[it + 1].long()
+        cnt = b - a
+        pos = torch.repeat_interleave(a - (torch.cumsum(cnt, 0) - cnt), cnt) + torch.arange(int(cnt.sum()), device=it.device)
+        which = torch.repeat_interleave(torch.arange(it.numel(), device=it.device), cnt)
+        return it, pos, which, cnt
+
+    icand = torch.nonzero((tl > 0) & (tl <= 1000)).reshape(-1).cpu().numpy()
+    items = np.sort(rng.choice(icand, size=min(2 * n_is, icand.size), replace=False)) if icand.size else np.zeros(0, np.int64)
+    out["items"], out["dEi_max_rel_err"] = 0, None
+    if items.size:
+        it, pos, which, _ = entries_of(items)
+        eu = ip.t_user[pos].long()
+        heavy_items = torch.unique(which[lens[eu] > max_len]).cpu().numpy()  # a too-heavy user makes the row too costly for the host
+        items = np.delete(items, heavy_items)[:n_is]
+    if items.size:
+        it, pos, which, _ = entries_of(items)
+        users_b = torch.unique(ip.t_user[pos].long()).cpu().numpy()
+        B = run(users_b)
+        where = {int(g): j for j, g in enumerate(B["touched"])}
+        amb = set(int(B["touched"][j]) for j in B["amb_items"])
+        rows_ok = [int(i) for i in items if int(i) in where and int(i) not in amb]
+        if rows_ok:
+            got = plan.i.dE[torch.as_tensor(rows_ok, device=it.device, dtype=torch.int64), :r].double().cpu().numpy()
+            want = np.stack([B["dEi"][where[i]] for i in rows_ok])
+            out["dEi_max_rel_err"] = _rel_err(got, want)
+        out["items"] = len(rows_ok)
+        out["items_users_involved"] = int(users_b.size)
+        out["ambiguous_items_excluded"] = int(items.size - len(rows_ok))
+    # ---- (C) the item-major segment-sum alone, on ANY item (the most popular one included): dE_i rows recomputed on the host in
+    # fp64 from the kernels' own coefficients (c_k / G_uj, whose producers (A) checks) and E_u rows, in list order
+    icand = torch.nonzero(tl > 0).reshape(-1).cpu().numpy()
+    out["segment_items"], out["dEi_segment_max_rel_err"] = 0, None
+    if icand.size:
+        pop = int(torch.argmax(tl))
+        items_c = np.unique(np.concatenate([rng.choice(icand, size=min(63, icand.size), replace=False), [pop]]))
+        it, pos, which, cnt = entries_of(items_c)
+        coef = ip.coef[ip.t_src[pos].long()].double()
+        rows_e = Eu[ip.t_user[pos].long(), :r].double() * coef[:, None]
+        want = torch.zeros(it.numel(), r, dtype=torch.float64, device=it.device).index_add_(0, which, rows_e).cpu().numpy()
+        got = plan.i.dE[it, :r].double().cpu().numpy()
+        out["segment_items"] = int(it.numel())
+        out["most_popular_item_entries"] = int(tl[pop])
+        out["dEi_segment_max_rel_err"] = _rel_err(got, want)
+    errs = [out["loss_max_rel_err"], out["dEu_max_rel_err"]] + [e for e in (out["dEi_max_rel_err"], out["dEi_segment_max_rel_err"]) if e is not None]
+    out["ok"] = bool(all(e <= PARITY_TOL for e in errs) and out["users"] > 0 and int(keep.sum()) > 0)
+    return out
+
+
+def parity_topk_rows(idx, U, r, k, v_shards, n_rows=64, n_cand=2000, seed=5):
+    """Bit-exact check of `n_rows` rows of a top-k result: the candidates are the top `n_cand` items per shard by fp64 score (a
+    superset of the answer by a huge margin), ranked on the host by the oracle's canonical score, (score desc, id asc).
+    `v_shards`: list of (item offset, V storage) covering all items."""
+    from oracle import mf_oracle as o
+    rng = np.random.default_rng(seed)
+    n_u = U.shape[0]
+    rows = np.unique(np.concatenate([[0, n_u // 2, n_u - 1], rng.choice(n_u, size=min(n_rows, n_u), replace=False)]))[:max(n_rows, 3)]
+    rt = torch.as_tensor(rows, device=U.device)
+    Ur = U[rt, :r].double()
+    cands = []
+    for off, V in v_shards:
+        sc = Ur @ V[:, :r].double().T
+        top = torch.topk(sc, min(n_cand, V.shape[0]), dim=1).indices + off
+        cands.append(top)
+    cand = torch.cat(cands, 1)
+    cand_np = cand.cpu().numpy()
+    U_np = U[rt, :r].cpu().numpy()
+    # gather the candidates' item rows shard by shard
+    Vrows = torch.empty(cand.shape[0], cand.shape[1], r, dtype=torch.float32, device=U.device)
+    for off, V in v_shards:
+        m = (cand >= off) & (cand < off + V.shape[0])
+        Vrows[m] = V[(cand[m] - off), :r]
+    Vrows = Vrows.cpu().numpy()
+    bad = 0
+    for j in range(rows.size):
+        sc = o.canonical_pair_scores(np.repeat(U_np[j:j + 1], cand_np.shape[1], 0), Vrows[j], np.arange(cand_np.shape[1]), np.arange(cand_np.shape[1]))
+        order = np.lexsort((cand_np[j], -sc.astype(np.float64)))[:k]
+        want = cand_np[j][order]
+        bad += int(not np.array_equal(want, idx[rows[j]].cpu().numpy()))
+    return {"rows": int(rows.size), "mismatching_rows": bad, "ok": bad == 0,
+            "method": f"top-{n_cand} fp64 candidates per shard -> oracle.canonical_pair_scores -> (score desc, id asc) -> first {k}"}
 
 
 # ------------------------------------------------------------------------------------------- top-k bench
@@ -260,13 +522,14 @@ def profile_phases(plan, lr, reps=3):
 
 def _topk_traffic(n_u, n_i, world):
     """DRAM bytes per launch of the dominant top-k kernel from the committed ncu capture (only for the captured shape)."""
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if world == 1 and n_u == 1_000_000 and n_i == 1_000_000 and os.path.exists(tpath):
-        return json.load(open(tpath)).get("score_topk_kernel")
-    return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if world == 1 and n_u == 1_000_000 and n_i == 1_000_000 and os.path.exists(tpath):
+            return json.load(open(tpath)).get("score_topk_kernel"), name
+    return None, None
 
 
-def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
+def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak, user_sharded_too=False):
     from teamoflow_b200 import _abi
     from teamoflow_b200.mf import dist as tdist
     from teamoflow_b200.mf._engine import new_storage
@@ -275,8 +538,14 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     bounds = tdist.shard_bounds(n_i, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     U = new_storage(n_u, r); U[:, :r] = torch.randn(n_u, r, generator=g, device=dev) / math.sqrt(r)
-    gi = torch.Generator(device=dev); gi.manual_seed(30000 + rank)
-    V = new_storage(hi - lo, r); V[:, :r] = torch.randn(hi - lo, r, generator=gi, device=dev) / math.sqrt(r)
+
+    def item_slab(gr):
+        gi = torch.Generator(device=dev); gi.manual_seed(30000 + gr)
+        n = bounds[gr + 1] - bounds[gr]
+        Vg = new_storage(n, r); Vg[:, :r] = torch.randn(n, r, generator=gi, device=dev) / math.sqrt(r)
+        return Vg
+
+    V = item_slab(rank)
     times = []
     l0 = _abi.launch_count
     for s in range(warmup + steps):
@@ -304,15 +573,14 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         phases = {f"{name}_ms": evs[j][1].elapsed_time(e) for j, (name, e) in enumerate(evs[1:])}
         phases["bound_sample_items"] = tdist.bound_sample_size(hi - lo, n_i, k, world)
         phases["exchange"] = tdist.exchange_mode()
-    # the alternative decomposition (users sharded, items replicated: no merge), reported beside the item-sharded one
+    # the alternative decomposition (users sharded, items replicated: no merge), only on request
     user_sharded = None
-    if world > 1:
+    if world > 1 and user_sharded_too:
         ub = tdist.shard_bounds(n_u, world)
         n_loc = ub[1] - ub[0]  # equal slices (the bench sizes divide evenly; a short last slice is padded)
         Uloc = new_storage(n_loc, r)
         Uloc[:ub[rank + 1] - ub[rank]] = U[ub[rank]:ub[rank + 1]]
-        gv = torch.Generator(device=dev); gv.manual_seed(30000)
-        Vfull = new_storage(n_i, r); Vfull[:, :r] = torch.randn(n_i, r, generator=gv, device=dev) / math.sqrt(r)
+        Vfull = torch.cat([item_slab(gr) for gr in range(world)])
         ts = []
         for s in range(warmup + steps):
             torch.distributed.barrier()
@@ -330,13 +598,15 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
         user_sharded = {"ms_per_step": ms_us, "value": float(n_u) * float(n_i) / (ms_us * 1e-3), "unit": "pairs/s",
                         "note": "users sharded, items replicated on every GPU, result all-gathered; no merge needed"}
         del Uloc, Vfull
-    # spot-check exactness of a few rows against the fp64 canonical definition (single GPU only)
-    ok = None
-    if world == 1:
-        rows = torch.tensor([0, n_u // 2, n_u - 1], device=dev)
-        sc64 = (U[rows, :r].double() @ V[:, :r].double().T)
-        want = torch.sort(sc64, dim=1, descending=True, stable=True).indices[:, :k].int()
-        ok = bool((idx[rows] == want).float().mean() > 0.99)
+    # ---- parity: sampled rows of the (merged) result, bit for bit against the oracle's canonical score + tie order
+    parity = None
+    if rank == 0:
+        try:
+            shards = [(bounds[gr], V if gr == rank else item_slab(gr)) for gr in range(world)]
+            parity = parity_topk_rows(idx, U, r, k, shards)
+            del shards
+        except Exception as e:
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
     # the recall_at_k path at the same scale (clamped scores, CSR interaction table; single GPU only)
     recall = None
     if world == 1:
@@ -368,6 +638,8 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     # e2e: host fp32 embeddings -> device -> top-k -> indices back on the host
     hU, hV = U.cpu().pin_memory(), V.cpu().pin_memory()
     h_out = torch.empty(n_u, k, dtype=torch.int32).pin_memory()  # the caller's (pinned) result buffer
+    if world > 1:
+        torch.distributed.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     dU, dV = hU.to(dev, non_blocking=True), hV.to(dev, non_blocking=True)
@@ -375,34 +647,40 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak):
     out = h_out.copy_(idx2, non_blocking=True)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    dt = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
+    traffic, traffic_src = _topk_traffic(n_u, n_i, world)
     return {"metric": "top-k scored user-item pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "config": {"workload": f"{n_u} users x {n_i} items rank-{r} top-{k} (raw scores), item-sharded x{world}", "k": k,
                        "exchange": (tdist.exchange_mode() + " (bounds all-gathered, lists merged over NVLink peer memory)") if world > 1 else "none"},
             "dtype": "16-bit tensor-core operands (fp16 or bf16, chosen from the data), fp32 accumulate in TMEM, fp64-accumulated rerank",
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12 / world, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": _topk_traffic(n_u, n_i, world),
-                         "traffic_note": "DRAM bytes of one score_topk_kernel launch (262,144 users x 1M items) from the committed ncu --set full capture"},
-            "e2e": {"value": pairs / (t1 - t0), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
+                         "frac": flops / (ms * 1e-3) / 1e12 / world / tf_peak, "traffic": traffic,
+                         "traffic_note": f"DRAM bytes of one score_topk_kernel launch from the committed ncu --set full capture (profiles/{traffic_src})"},
+            "e2e": {"value": pairs / float(dt), "unit": "pairs/s", "h2d_bytes_per_step": hU.numel() * 4 + hV.numel() * 4,
                     "d2h_bytes_per_step": out.numel() * 4},
-            "gpu_launches": launches, "spot_check_exact": ok, "user_sharded": user_sharded, "recall_path": recall,
+            "gpu_launches": launches, "parity_check": parity, "user_sharded": user_sharded, "recall_path": recall,
             "phases_ms": phases}
 
 
-# ------------------------------------------------------------------------------------------- CPU reference arm
+# ------------------------------------------------------------------------------------------- CPU baselines
 
 
-def cpu_reference_step(wl_name, budget_s=20.0, n_sub=None):
-    """The reference's own algorithm (dense features, dense U V^T, gathers, autograd of the summed loss,
-    Keras-Adam step 1) on host cores via oracle/autograd_twin (torch-CPU; TensorFlow is not installable
-    here), on a bounded user sample of the workload.  Returns (interactions/s, description, cores)."""
-    from oracle import autograd_twin as tw
-    from oracle import mf_oracle as o
-    w = WORKLOADS[wl_name]
-    n_i, r, S = w["n_i"], w["r"], w["S"]
-    if n_sub is None:
-        n_sub = {"c3": 1024, "c2": 943, "c1": 1000, "c4mini": 64, "c4": 64}[wl_name]
-    n_sub = min(n_sub, w["n_u"])
-    rng = np.random.default_rng(7)
+def _cpu_threads():
+    """All host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which
+    starved the reference arm of round 1 at N > 1)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # pragma: no cover
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def _cpu_sample(w, n_sub, rng):
+    n_i, S = w["n_i"], w["S"]
     per_user = max(1, w["nnz"] // w["n_u"])
     rows = np.repeat(np.arange(n_sub), per_user)
     wi = 1.0 / np.arange(1, n_i + 1)
@@ -411,28 +689,125 @@ def cpu_reference_step(wl_name, budget_s=20.0, n_sub=None):
     rows, cols = cells // n_i, cells % n_i
     vals = np.ones(rows.size, np.float32)
     samp = np.stack([rng.choice(n_i, max(S, 1), replace=False) for _ in range(n_sub)]) if S else None
-    # dense features exactly like the reference (tf.eye / dense [I|M]); user identity columns restricted to the sample
-    Xu = np.eye(n_sub, dtype=np.float32)
-    Xi = np.eye(n_i, dtype=np.float32)
-    if w["mu"]:
-        Xu = np.concatenate([Xu, (rng.random((n_sub, w["mu"][0])) < w["mu"][1] / w["mu"][0]).astype(np.float32)], 1)
-        Xi = np.concatenate([Xi, (rng.random((n_i, w["mi"][0])) < w["mi"][1] / w["mi"][0]).astype(np.float32)], 1)
-    pu = {"W": o.uniform_initializer(Xu.shape[1], r, rng)}
-    pi = {"W": o.uniform_initializer(Xi.shape[1], r, rng)}
-    loss = "wmrb" if S else "mse"
+    return rows, cols, vals, samp
+
+
+def _time_steps(fn, budget_s, max_steps=6):
     times = []
     t_all = time.perf_counter()
     while True:
         t0 = time.perf_counter()
-        _, _, _, pu, pi = tw.train_step(loss, Xu, Xi, "linear", "linear", pu, pi, rows, cols, vals, samp, n_i, S or None,
-                                        lr=0.1 if S else 1e-2)
+        fn()
         times.append(time.perf_counter() - t0)
-        if len(times) >= 2 and (time.perf_counter() - t_all > budget_s or len(times) >= 6):
+        if len(times) >= 2 and (time.perf_counter() - t_all > budget_s or len(times) >= max_steps):
             break
-    t = float(np.median(times[1:])) if len(times) > 1 else times[0]
-    desc = (f"{n_sub} of {w['n_u']} users x all {n_i} items, {rows.size} interactions, dense features + dense U.V^T "
-            f"+ autograd + Adam step-1, median of {len(times) - 1} steps")
-    return rows.size / t, desc, torch.get_num_threads()
+    return float(np.median(times[1:])) if len(times) > 1 else times[0], len(times) - 1
+
+
+def cpu_reference_step(wl_name, budget_s=20.0):
+    """The reference's own algorithm (dense features, dense U V^T, gathers, autograd of the summed loss, Keras-Adam step 1)
+    on host cores via oracle/autograd_twin (torch-CPU; TensorFlow is not installable here).
+
+    The full configuration cannot run densely on a host (C3: a 14.9 GB score matrix and a 76 GB dense user-feature matrix), so
+    the step is timed on TWO user samples (n and 2n users against ALL items).  Its cost is t(n) = t_item + n * t_user: the
+    item-side work (dense X_i W_i forward/backward over all items) is a fixed cost per step that a sample must not be charged
+    per interaction, so the two timings are solved for t_item and t_user and the full-configuration step is
+    EXTRAPOLATED as t_item + n_users * t_user.  (Favourable to the reference: its dense n_users x n_users identity-feature matmul
+    grows quadratically and is left out.)  Returns a dict; `value` = full-config interactions / extrapolated step time."""
+    from oracle import autograd_twin as tw
+    from oracle import mf_oracle as o
+    cores = _cpu_threads()
+    w = WORKLOADS[wl_name]
+    n_i, r, S = w["n_i"], w["r"], w["S"]
+    n1 = {"c3": 2048, "c2": 943, "c1": 1000, "c4mini": 32, "c4": 32}[wl_name]
+    full = n1 >= w["n_u"]
+    sizes = [w["n_u"]] if full else [n1, 4 * n1]
+    loss = "wmrb" if S else "mse"
+    meas = []
+    for n_sub in sizes:
+        rng = np.random.default_rng(7)
+        rows, cols, vals, samp = _cpu_sample(w, n_sub, rng)
+        # dense features exactly like the reference (tf.eye / dense [I|M]); user identity columns restricted to the sample
+        Xu = np.eye(n_sub, dtype=np.float32)
+        Xi = np.eye(n_i, dtype=np.float32)
+        if w["mu"]:
+            Xu = np.concatenate([Xu, (rng.random((n_sub, w["mu"][0])) < w["mu"][1] / w["mu"][0]).astype(np.float32)], 1)
+            Xi = np.concatenate([Xi, (rng.random((n_i, w["mi"][0])) < w["mi"][1] / w["mi"][0]).astype(np.float32)], 1)
+        state = {"pu": {"W": o.uniform_initializer(Xu.shape[1], r, rng)}, "pi": {"W": o.uniform_initializer(Xi.shape[1], r, rng)}}
+
+        def step():
+            _, _, _, state["pu"], state["pi"] = tw.train_step(loss, Xu, Xi, "linear", "linear", state["pu"], state["pi"], rows, cols, vals,
+                                                              samp, n_i, S or None, lr=0.1 if S else 1e-2)
+        t, n_t = _time_steps(step, budget_s / len(sizes))
+        meas.append((n_sub, rows.size, t, n_t))
+    if full:
+        n_sub, nnz_s, t, n_t = meas[0]
+        return {"value": nnz_s / t, "unit": "interactions/s", "cores": cores, "kind": "port", "same_config": True, "extrapolated": False,
+                "sample": f"the full configuration ({n_sub} users x {n_i} items, {nnz_s} interactions), dense features + dense U.V^T + "
+                          f"autograd + Adam step-1 (oracle/autograd_twin, torch-CPU), median of {n_t} steps"}
+    (na, nnz_a, ta, _), (nb, nnz_b, tb, n_t) = meas
+    t_user = (tb - ta) / (nb - na)
+    if not t_user > 0.02 * tb / nb:  # the slope drowned in timing noise: charge the whole larger step to its users (upper bound on t_user)
+        t_user = tb / nb
+    t_item = max(ta - na * t_user, 0.0)
+    t_full = t_item + w["n_u"] * t_user
+    return {"value": w["nnz"] / t_full, "unit": "interactions/s", "cores": cores, "kind": "port", "same_config": False, "extrapolated": True,
+            "measured": {"users": [na, nb], "interactions": [int(nnz_a), int(nnz_b)], "step_s": [ta, tb]},
+            "t_item_fixed_s": t_item, "t_per_user_s": t_user, "step_s_full_config_extrapolated": t_full,
+            "raw_sample_value": nnz_b / tb,
+            "sample": f"dense features + dense U.V^T + autograd + Adam step-1 (oracle/autograd_twin, torch-CPU) timed on {na} and {nb} of "
+                      f"{w['n_u']} users x all {n_i} items (median of {n_t} steps each); step(n) = t_item + n t_user solved from the two, "
+                      f"full configuration EXTRAPOLATED as t_item + {w['n_u']} t_user = {t_full:.1f} s per epoch"}
+
+
+def cpu_sparse_step(wl_name, budget_s=12.0, frac=64):
+    """The oracle's SPARSE restatement (only the needed dot products, segment-sum gradients: the algorithm the CUDA path
+    implements) in NumPy fp32 on a 1/`frac` user sample of the workload, all items; linear in users, so value = sample
+    interactions / sample step time (single-threaded NumPy apart from BLAS)."""
+    from oracle import mf_oracle as o
+    from scipy import sparse
+    w = WORKLOADS[wl_name]
+    n_i, r, S = w["n_i"], w["r"], w["S"]
+    n_sub = max(1, w["n_u"] // frac)
+    rng = np.random.default_rng(11)
+    rows, cols, vals, samp = _cpu_sample(w, n_sub, rng)
+    Xu, Xi = sparse.identity(n_sub, format="csr", dtype=np.float32), sparse.identity(n_i, format="csr", dtype=np.float32)
+    state = {"pu": {"W": o.uniform_initializer(n_sub, r, rng)}, "pi": {"W": o.uniform_initializer(n_i, r, rng)}}
+    loss = "wmrb" if S else "mse"
+
+    def step():
+        _, _, _, state["pu"], state["pi"] = o.train_step_sparse(loss, Xu, Xi, "linear", "linear", state["pu"], state["pi"], rows, cols, vals,
+                                                                samp, n_i, S or None, lr=0.1 if S else 1e-2)
+    t, n_t = _time_steps(step, budget_s, max_steps=4)
+    return {"value": rows.size / t, "unit": "interactions/s", "cores": 1, "kind": "port",
+            "sample": f"oracle.train_step_sparse (NumPy fp32) on {n_sub} of {w['n_u']} users x all {n_i} items, {rows.size} interactions, "
+                      f"identity features, median of {n_t} steps"}
+
+
+def cpu_topk(n_i, r, k, n_sub=48, budget_s=12.0):
+    """CPU baseline of the retrieval metric: blocked fp32 GEMM (torch-CPU, all cores) + per-block STABLE descending sort
+    (ties -> lower item id, like tf.math.top_k) + merge of the per-block lists, on `n_sub` users against all items."""
+    cores = _cpu_threads()
+    rng = np.random.default_rng(3)
+    U = torch.from_numpy((rng.standard_normal((n_sub, r)) / math.sqrt(r)).astype(np.float32))
+    V = torch.from_numpy((rng.standard_normal((n_i, r)) / math.sqrt(r)).astype(np.float32))
+    blk = 65536
+
+    def run():
+        best_s = np.full((n_sub, 0), 0, np.float32); best_i = np.zeros((n_sub, 0), np.int64)
+        for b0 in range(0, n_i, blk):
+            P = (U @ V[b0:b0 + blk].T).numpy()
+            kk = min(k, P.shape[1])
+            part = np.argpartition(-P, kk - 1, axis=1)[:, :kk]
+            ids = np.concatenate([best_i, part + b0], 1)
+            scs = np.concatenate([best_s, np.take_along_axis(P, part, 1)], 1)
+            order = np.lexsort((ids, -scs), axis=1)[:, :k]
+            best_i, best_s = np.take_along_axis(ids, order, 1), np.take_along_axis(scs, order, 1)
+        return best_i
+    t, n_t = _time_steps(run, budget_s, max_steps=4)
+    return {"value": n_sub * float(n_i) / t, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n_sub} users x all {n_i} items, rank {r}, top-{k}: blocked torch-CPU GEMM ({blk}-item blocks) + per-block partition + "
+                      f"(score desc, id asc) merge, median of {n_t} runs"}
 
 
 # ------------------------------------------------------------------------------------------- main
@@ -446,6 +821,36 @@ def _claim_stdout():
     return os.fdopen(saved, "w")
 
 
+def _teardown(world, plans, comm):
+    """Leave a multi-rank run without hanging: drop the captured graphs, synchronise, barrier, then destroy the process group from
+    a watchdog-guarded thread (round 1's graphs held NCCL work and destroy_process_group() never returned; with the peer-memory
+    exchange a captured step holds none, but a stuck teardown must never burn the box's clock)."""
+    if world <= 1:
+        return
+    import gc
+    for pl in plans:
+        if pl is not None:
+            pl.invalidate_graph()
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            torch.distributed.destroy_process_group()
+        finally:
+            done.set()
+    th = threading.Thread(target=_destroy, daemon=True)
+    th.start()
+    if not done.wait(20.0):
+        log("[bench] destroy_process_group did not return within 20 s; leaving with os._exit(0) (results are already printed)")
+        os._exit(0)
+
+
 def main():
     out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -456,7 +861,13 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--topk", default="1000000x1000000x128x100", help="users x items x rank x k of the secondary top-k bench; 'none' skips")
     ap.add_argument("--topk-steps", type=int, default=2)
+    ap.add_argument("--c4", default="auto", choices=["auto", "on", "off"], help="also run BASELINE configs[3] (one 10M x 2M problem, strong scaling); "
+                    "auto = on for the default c3 workload")
+    ap.add_argument("--c4-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--topk-user-sharded", action="store_true", help="also time the user-sharded alternative of the top-k (N > 1)")
     ap.add_argument("--topk-only", action="store_true", help="run only the secondary top-k bench (profiling aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -469,13 +880,23 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, desc, cores = cpu_reference_step(args.workload, budget_s=max(20.0, 8.0 * args.steps))
-        print(file=out_stream, flush=True, *[json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": w["desc"], "sample": desc},
-                          "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port", "sample": desc},
-                          "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})])
+        base = cpu_reference_step(args.workload, budget_s=max(20.0, 8.0 * args.steps))
+        line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": "interactions/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["desc"], "sample": base["sample"], "same_config": base["same_config"],
+                           "extrapolated": base["extrapolated"]},
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if args.topk != "none":
+            try:
+                tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
+                line["topk"] = {"metric": "top-k scored user-item pairs/sec", "cpu_baseline": cpu_topk(ti, tr, tk)}
+                line["topk"]["value"] = line["topk"]["cpu_baseline"]["value"]
+                line["topk"]["unit"] = "pairs/s"
+            except Exception as e:
+                line["topk"] = {"error": f"{type(e).__name__}: {e}"}
+        print(json.dumps(line), file=out_stream, flush=True)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
@@ -483,19 +904,21 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from teamoflow_b200 import _abi
     from teamoflow_b200.mf import dist as tdist
     dev = torch.device("cuda", local)
     hbm_peak, tf_peak, peak_src = peaks()
+    t_start = time.time()
 
     if args.topk_only:
         tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
-        res = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak)
+        res = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak, args.topk_user_sharded)
         if rank == 0:
             print(json.dumps(res), file=out_stream, flush=True)
+        _teardown(world, [], None)
         return
 
-    wl = Workload(args.workload, rank, world)
+    strong = bool(w.get("strong"))
+    wl = Workload(args.workload, rank, world, host_copy=not strong)
     w = wl.w  # per-rank sizes (differs from WORKLOADS[...] for strong-scaling workloads)
     comm = None
     if world > 1:
@@ -504,56 +927,36 @@ def main():
 
     # ---- device-resident measurement: inputs and structures already in HBM
     model = wl.model
-    plan = model._prepare(xu, xi, wl.interactions_host(), comm=comm)
-    if comm is not None:
-        comm.broadcast_params(plan.u, plan.i)
-    # warm-up through the same entry point as the timed loop (TrainPlan.run = the body of fit()'s epoch loop: first step
-    # eager, the rest replayed from ONE captured CUDA graph of a step); the capture happens here
-    plan.run(max(args.warmup, 3), wl.lr)
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    l0 = _abi.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
-        plan.run(args.steps, wl.lr)
-        e1.record()
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-    launches = _abi.launch_count - l0
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ms_total, op=torch.distributed.ReduceOp.MAX)
-    ms_step = float(ms_total) / args.steps
-    value = world * wl.nnz / (ms_step * 1e-3)
-    loss_now = plan.ip.mean_loss() if comm is None else comm.mean_loss(plan.ip)
-
-    phases = profile_phases(plan, wl.lr)
-    phase_bytes = {"user_pass": wl.bytes["user_pass"], "item_pass": wl.bytes["item_pass"],
-                   "embed_fwd": wl.bytes["features"] / 2, "embed_bwd": wl.bytes["features"] / 2, "adam": wl.bytes["adam"]}
-    dom = max(("user_pass", "item_pass", "embed_fwd", "embed_bwd", "adam"), key=lambda n: phases[n])
-    dom_gbs = phase_bytes[dom] / (phases[dom] * 1e-3) / 1e9 if phases[dom] > 0 else 0.0
-    kernel_of = {"user_pass": "user_pass_kernel", "item_pass": "spmm_seg_kernel (item-major)", "embed_fwd": "spmm_seg_kernel (X.W)",
-                 "embed_bwd": "spmm_seg_kernel (X^T.dE)", "adam": "adam1_kernel"}
-    step_gbs = wl.bytes["total"] / (ms_step * 1e-3) / 1e9
+    plan, tb = train_bench(wl, comm, args.steps, args.warmup, local, world, hbm_peak)
+    ms_step = tb["ms_step"]
+    total_nnz = wl.total_nnz if strong else world * wl.nnz
+    value = total_nnz / (ms_step * 1e-3)
+    dom = tb["dom"]
     traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture (C3 only)
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if args.workload == "c3" and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(kernel_of[dom])
+    traffic_src = None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if args.workload == "c3" and os.path.exists(tpath) and traffic is None:
+            traffic, traffic_src = json.load(open(tpath)).get(KERNEL_OF[dom]), name
+
+    parity = {}
+    if not args.no_parity:
+        try:
+            parity[args.workload] = parity_train_sample(plan)
+        except Exception as e:
+            parity[args.workload] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        log(f"[rank {rank}] parity {args.workload}: {parity[args.workload]}")
 
     # ---- end to end through the plugin API from pinned host buffers (one fit call of K epochs)
     e2e = None
-    if True:
-        from teamoflow_b200.mf.matrix_factorization import MatrixFactorization  # noqa: F401
+    if not args.no_e2e and not strong:
         dts = []
         for _ in range(3):  # three complete fit() calls from the host buffers; the median is reported
             if world > 1:
                 torch.distributed.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            model.fit(args.steps, xu, xi, wl.interactions_host(), lr=wl.lr, comm=comm, verbose=False)
+            model.fit(args.steps, xu, xi, wl.interactions(), lr=wl.lr, comm=comm, verbose=False)
             final_loss = model._plan.ip.mean_loss() if comm is None else comm.mean_loss(model._plan.ip)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
@@ -564,64 +967,130 @@ def main():
         dt = sorted(dts)[1]
         e2e = {"value": world * wl.nnz * args.steps / float(dt), "unit": "interactions/s",
                "h2d_bytes_per_step": wl.h2d_bytes() / args.steps, "d2h_bytes_per_step": 4.0 / args.steps,
-               "note": f"one MatrixFactorization.fit({args.steps} epochs) from pinned host COO + host CSR features, incl. H2D, "
+               "note": f"one MatrixFactorization.fit({args.steps} epochs) from pinned host COO (int32 ids) + host CSR features, incl. H2D, "
                        f"CSR/item-major structure build, weight init, {args.steps} epochs, D2H of the mean loss; "
                        f"median of 3 calls ({', '.join('%.3f' % x for x in dts)} s), final loss {final_loss:.5f}"}
 
     out = {"metric": metric, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if w.get("strong") else "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
            "config": {"workload": w["desc"], "n_users_per_gpu": w["n_u"], "n_items": w["n_i"], "nnz_per_gpu": wl.nnz, "rank": w["r"],
                       "n_samples": w["S"], "parallelism": f"user-sharded dp{world}" if world > 1 else "single GPU",
-                      "grad_exchange": ("tmf_peer_reduce_push over NVLink peer memory" if comm.peer else "NCCL all-reduce") if comm is not None else "none",
+                      "grad_exchange": ("tmf_peer_reduce_push over NVLink peer memory (item gradient + staged shared user-side gradients; "
+                                        "no NCCL inside the captured step)" if comm.peer else "NCCL all-reduce") if comm is not None else "none",
                       "l2_policy": "working set per step (interactions + lists + embeddings, ~%.1f GB) exceeds the 126 MB L2; no flush" % (
                           (wl.nnz * 28 + w["n_u"] * max(w["S"], 1) * 16) / 1e9),
-                      "loss_after": loss_now},
-           "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": dom_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                        "alg_bytes_per_launch": phase_bytes[dom], "ms_per_launch": phases[dom],
+                      "loss_after": tb["loss"]},
+           "roofline": {"bound": "hbm", "kernel": KERNEL_OF[dom], "achieved": tb["dom_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": tb["dom_gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                        "alg_bytes_per_launch": tb["phase_bytes"][dom], "ms_per_launch": tb["phases"][dom],
                         "note": "achieved = SURVEY-8d ALGORITHMIC bytes (every embedding-row gather counted as HBM bytes) / "
-                                "CUDA-event time; `traffic` = DRAM bytes of one launch from the committed ncu capture. Where the "
-                                "gathered table fits the 126 MB L2 (C3: 6.9 MB item table) traffic << algorithmic bytes, the "
-                                "fraction can exceed 1 and the kernel's real bound is instruction issue + L1/L2 gather latency "
-                                "(profiles/r01_summary.md v8: 67.7 % issue-active)"},
-           "step_roofline": {"alg_bytes_per_step": wl.bytes["total"], "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": step_gbs / hbm_peak},
-           "phases_ms": phases, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches}
+                                f"CUDA-event time; `traffic` = DRAM bytes of one launch from the committed ncu capture (profiles/{traffic_src}). "
+                                "Where the gathered table fits the 126 MB L2 (C3: 6.9 MB item table) traffic << algorithmic bytes, the "
+                                "fraction can exceed 1 and the kernel's real bound is instruction issue + L1/L2 gather latency"},
+           "step_roofline": {"alg_bytes_per_step": wl.bytes["total"], "achieved": tb["step_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                             "frac": tb["step_gbs"] / hbm_peak},
+           "phases_ms": tb["phases"], "clocks": tb["clocks"], "e2e": e2e, "gpu_launches": tb["launches"]}
+
+    plans = [plan, getattr(model, "_plan", None)]
+    # ---- BASELINE configs[3]: one 10M x 2M problem, strong scaling over the ranks
+    run_c4 = args.c4 == "on" or (args.c4 == "auto" and args.workload == "c3")
+    if run_c4:
+        try:
+            # free the C3 state first (the arena of the gradient exchange is re-sized collectively by attach)
+            for pl in plans:
+                if pl is not None:
+                    pl.invalidate_graph()
+            if comm is not None:
+                comm.detach(plan)
+            del plan, tb
+            model._plan = None
+            plans = []
+            wl.model = None
+            torch.cuda.empty_cache()
+            t0 = time.time()
+            wl4 = Workload("c4", rank, world, host_copy=False)
+            comm4 = tdist.GradientSync() if world > 1 else None
+            plan4, t4 = train_bench(wl4, comm4, args.c4_steps, 3, local, world, hbm_peak)
+            plans = [plan4]
+            par4 = None
+            if not args.no_parity:
+                try:
+                    par4 = parity_train_sample(plan4, n_us=256, n_is=8, max_len=50_000)
+                except Exception as e:
+                    par4 = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+                parity["c4"] = par4
+                log(f"[rank {rank}] parity c4: {par4}")
+            nnz_r = torch.tensor([wl4.nnz, wl4.w["n_u"]], device=dev, dtype=torch.int64)
+            per_rank = [nnz_r.tolist()]
+            if world > 1:
+                gl = [torch.zeros_like(nnz_r) for _ in range(world)]
+                torch.distributed.all_gather(gl, nnz_r)
+                per_rank = [g.tolist() for g in gl]
+            w4 = WORKLOADS["c4"]
+            bytes_total = alg_bytes(w4, wl4.total_nnz, wl4.total_nnz, w4["n_u"], w4["n_i"], 0, 0)["total"]
+            out["c4"] = {"metric": metric, "value": wl4.total_nnz / (t4["ms_step"] * 1e-3), "unit": "interactions/s", "ms_per_step": t4["ms_step"],
+                         "steps": args.c4_steps, "scaling": "strong", "n_gpus": world,
+                         "config": {"workload": w4["desc"], "one_problem": "the same dataset (seed) at every N; contiguous user ranges with equal "
+                                    "(interactions + sampled negatives) per rank (dist.balanced_user_bounds)",
+                                    "users_interactions_per_rank": [{"nnz": a, "users": b} for a, b in per_rank],
+                                    "grad_exchange": ("tmf_peer_reduce_push (1.02 GB dE_i: reduce-scatter + Adam + all-gather in one kernel)"
+                                                      if comm4.peer else "NCCL all-reduce") if comm4 is not None else "none",
+                                    "loss_after": t4["loss"]},
+                         "phases_ms": t4["phases"], "gpu_launches": t4["launches"], "clocks": t4["clocks"],
+                         "step_roofline": {"bound": "hbm", "alg_bytes_per_step_whole_problem": bytes_total,
+                                           "achieved": bytes_total / (t4["ms_step"] * 1e-3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s per GPU",
+                                           "frac": bytes_total / (t4["ms_step"] * 1e-3) / 1e9 / world / hbm_peak,
+                                           "note": "SURVEY-8d algorithmic bytes of the WHOLE problem / step time / N, against the measured HBM peak; "
+                                                   "the 1 GB item table does not fit L2, so HBM is the real bound here"},
+                         "roofline": {"bound": "hbm", "kernel": KERNEL_OF[t4["dom"]], "achieved": t4["dom_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": t4["dom_gbs"] / hbm_peak, "alg_bytes_per_launch": t4["phase_bytes"][t4["dom"]],
+                                      "ms_per_launch": t4["phases"][t4["dom"]]},
+                         "setup_s": time.time() - t0}
+            for pl in plans:
+                pl.invalidate_graph()
+            if comm4 is not None:
+                comm4.detach(plan4)
+            del plan4, wl4
+            plans = []
+            torch.cuda.empty_cache()
+        except Exception as e:  # keep the primary line alive
+            import traceback
+            log(traceback.format_exc())
+            out["c4"] = {"error": f"{type(e).__name__}: {e}"}
 
     if args.topk != "none":
         try:
             tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
-            out["topk"] = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak)
+            out["topk"] = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak, args.topk_user_sharded)
+            parity["c5"] = out["topk"].get("parity_check")
         except Exception as e:  # keep the primary line alive
+            import traceback
+            log(traceback.format_exc())
             out["topk"] = {"error": f"{type(e).__name__}: {e}"}
+    out["parity_check"] = {k: ("ok" if (v or {}).get("ok") else "FAILED") for k, v in parity.items()}
+    out["parity_detail"] = parity
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            val, desc, cores = cpu_reference_step(args.workload, budget_s=15.0)
-            out["cpu_baseline"] = {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port", "sample": desc}
+            out["cpu_baseline"] = cpu_reference_step(args.workload, budget_s=14.0)
         except Exception as e:
             out["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            out["cpu_baseline_sparse"] = cpu_sparse_step(args.workload, budget_s=8.0)
+        except Exception as e:
+            out["cpu_baseline_sparse"] = {"error": f"{type(e).__name__}: {e}"}
+        if args.topk != "none" and isinstance(out.get("topk"), dict) and "error" not in out["topk"]:
+            try:
+                tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
+                out["topk"]["cpu_baseline"] = cpu_topk(ti, tr, tk, budget_s=8.0)
+            except Exception as e:
+                out["topk"]["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    out["bench_wall_s"] = time.time() - t_start
     if rank == 0:
         print(json.dumps(out), file=out_stream, flush=True)
-    if world > 1:
-        # The captured step graphs hold NCCL work (the all-reduce of the shared user-side gradients).  Drop them while the
-        # communicator is alive, then leave WITHOUT tearing the process group down: destroy_process_group() after graph
-        # capture blocked forever in the first 2-GPU run of the graph path (the JSON line was already out).  Every rank
-        # has finished (barrier + synchronize), so the OS reclaims the rest.
-        for pl in (plan, getattr(model, "_plan", None)):
-            if pl is not None:
-                pl.invalidate_graph()
-        del plan
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        torch.distributed.barrier()
-        torch.cuda.synchronize()
         out_stream.flush()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    _teardown(world, plans, comm)
 
 
 if __name__ == "__main__":

@@ -58,6 +58,12 @@ TMF_API const char* tmf_last_error(void); /* thread-local, valid until the next 
  * loss_graphs.py:47 / utils.py:53-57). */
 TMF_API int tmf_rowptr_from_sorted(const int32_t* rows, int64_t nnz, int32_t n_rows, int32_t* row_ptr, tmf_stream_t stream);
 
+/* tf_interactions.indices ([nnz, 2], int64 like tf.sparse.SparseTensor or int32; index_bytes = 8 / 4) -> int32 row and
+ * column ids in one pass.  flags[0] (device int32, zeroed by the call): bit 0 = an id outside [0, n_rows) x [0, n_cols)
+ * (the reference's gather_nd raises there, matrix_factorization.py:154), bit 1 = not in row-major order. */
+TMF_API int tmf_coo_split(const void* indices, int32_t index_bytes, int64_t nnz, int64_t n_rows, int64_t n_cols, int32_t* rows,
+                  int32_t* cols, int32_t* flags, tmf_stream_t stream);
+
 /* Stable counting transpose: perm = stable argsort(keys) (keys in [0, n_keys)), ptr[n_keys+1] =
  * segment starts.  Builds the item-major (CSC) view of the interactions and of the sampled
  * negatives (random_ind, matrix_factorization.py:72-73) and X^T for the embedding backward.

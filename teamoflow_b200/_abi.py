@@ -22,6 +22,7 @@ SIGNATURES = {
     "tmf_abi_version": (_i32, []),
     "tmf_last_error": (C.c_char_p, []),
     "tmf_rowptr_from_sorted": (_i32, [_p, _i64, _i32, _p, _p]),
+    "tmf_coo_split": (_i32, [_p, _i32, _i64, _i64, _i64, _p, _p, _p, _p]),
     "tmf_transpose_ws_bytes": (_sz, [_i64]),
     "tmf_transpose_build": (_i32, [_p, _i64, _i32, _p, _p, _p, _sz, _p]),
     "tmf_tlist_users": (_i32, [_p, _i64, _i64, _p, _i32, _p, _p]),

@@ -30,6 +30,28 @@ __global__ void lower_bound_kernel(const int* __restrict__ keys, long long n, in
   ptr[j] = (int)lo;
 }
 
+// COO indices [nnz, 2] (int32 or int64, tf.sparse.SparseTensor.indices layout) -> int32 rows / cols in one pass, with the two
+// checks the host needs before it may use them: flags bit 0 = an id outside [0, n_rows) x [0, n_cols), bit 1 = not in
+// row-major order (stored order is kept; the caller then sorts).
+template <typename T>
+__global__ void coo_split_kernel(const T* __restrict__ idx2, long long nnz, long long n_rows, long long n_cols, int* __restrict__ rows,
+                                 int* __restrict__ cols, int* __restrict__ flags) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int f = 0;
+  for (; i < nnz; i += stride) {
+    const long long r = (long long)idx2[2 * i], c = (long long)idx2[2 * i + 1];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) f |= 1;
+    if (i > 0) {
+      const long long pr = (long long)idx2[2 * i - 2], pc = (long long)idx2[2 * i - 1];
+      if (pr > r || (pr == r && pc > c)) f |= 2;
+    }
+    rows[i] = (int)r;
+    cols[i] = (int)c;
+  }
+  if (f) atomicOr(flags, f);
+}
+
 __global__ void iota_kernel(int* __restrict__ x, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -128,6 +150,22 @@ extern "C" const char* tmf_last_error(void) { return g_err; }
 extern "C" int tmf_rowptr_from_sorted(const int32_t* rows, int64_t nnz, int32_t n_rows, int32_t* row_ptr, tmf_stream_t stream) {
   TMF_REQUIRE(n_rows >= 0 && nnz >= 0 && nnz < (1ll << 31), "tmf_rowptr_from_sorted: bad sizes");
   lower_bound_kernel<<<(unsigned)cdiv(n_rows + 1, 256), 256, 0, as_stream(stream)>>>(rows, nnz, n_rows, row_ptr);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
+extern "C" int tmf_coo_split(const void* indices, int32_t index_bytes, int64_t nnz, int64_t n_rows, int64_t n_cols, int32_t* rows,
+                             int32_t* cols, int32_t* flags, tmf_stream_t stream) {
+  TMF_REQUIRE(index_bytes == 4 || index_bytes == 8, "tmf_coo_split: indices must be int32 or int64");
+  TMF_REQUIRE(flags != nullptr && nnz >= 0 && nnz < (1ll << 31) && n_rows < (1ll << 31) && n_cols < (1ll << 31), "tmf_coo_split: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  TMF_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), st));
+  if (nnz == 0) return TMF_OK;
+  const unsigned grid = (unsigned)std::min<long long>(cdiv(nnz, 256), 148 * 16);
+  if (index_bytes == 8)
+    coo_split_kernel<long long><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(indices), nnz, n_rows, n_cols, rows, cols, flags);
+  else
+    coo_split_kernel<int><<<grid, 256, 0, st>>>(reinterpret_cast<const int*>(indices), nnz, n_rows, n_cols, rows, cols, flags);
   TMF_LAUNCH_CHECK();
   return TMF_OK;
 }

@@ -232,8 +232,10 @@ class InteractionPlan:
             ri = to_device(random_ind, torch.int64)
             if ri.dim() != 2 or ri.shape[0] != self.n_users:
                 raise ValueError(f"random_ind must be [n_users={self.n_users}, n_samples], got {tuple(ri.shape)}")
-            if ri.numel() and (int(ri.min()) < 0 or int(ri.max()) >= self.n_items):
-                raise ValueError("random_ind holds item ids outside [0, n_items)")
+            if ri.numel():
+                lo_hi = torch.stack(torch.aminmax(ri)).tolist()  # one synchronisation
+                if lo_hi[0] < 0 or lo_hi[1] >= self.n_items:
+                    raise ValueError("random_ind holds item ids outside [0, n_items)")
             if self.S and int(ri.shape[1]) != self.S:
                 raise ValueError("the number of samples per user cannot change between resamplings")
             self.S = int(ri.shape[1])

@@ -56,17 +56,32 @@ def build_transpose(keys_i32, n_keys):
 
 
 class SparseInteractions:
-    """COO interaction table in stored order, plus the sorted CSR view the kernels use."""
+    """COO interaction table in stored order, plus the sorted CSR view the kernels use.
+
+    ``indices`` may be int64 (``tf.sparse.SparseTensor``) or int32 (half the host->device bytes); the attribute
+    ``.indices`` is the reference's int64 ``[nnz, 2]`` tensor either way (materialised on first use)."""
 
     def __init__(self, indices, values, dense_shape):
-        self.indices = to_device(indices, torch.int64).reshape(-1, 2)
+        raw = indices if isinstance(indices, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(indices)))
+        if raw.dtype not in (torch.int32, torch.int64):
+            raw = raw.to(torch.int64)
+        if not raw.is_cuda and raw.numel() > (1 << 16) and not raw.is_pinned():
+            raw = raw.pin_memory()
+        self._raw = raw.to(device(), non_blocking=True).reshape(-1, 2).contiguous()
+        self._idx64 = self._raw if self._raw.dtype == torch.int64 else None
         self.values = to_device(values, torch.float32).reshape(-1)
         self.dense_shape = (int(dense_shape[0]), int(dense_shape[1]))
-        if self.indices.shape[0] != self.values.shape[0]:
+        if self._raw.shape[0] != self.values.shape[0]:
             raise ValueError("indices and values disagree on nnz")
         if self.values.numel() >= 2 ** 31:
             raise ValueError("nnz must be < 2^31")
         self._csr = None
+
+    @property
+    def indices(self):
+        if self._idx64 is None:
+            self._idx64 = self._raw.to(torch.int64)
+        return self._idx64
 
     @property
     def shape(self):
@@ -79,29 +94,33 @@ class SparseInteractions:
     def csr(self):
         """``(row_ptr, col_idx, vals, coo_rows, perm)``: row-major sorted int32 view; ``perm`` maps sorted
         position -> stored position (None when the stored order is already row-major, as
-        ``utils.py:53-57`` / ``input_utils.py:145-151`` produce)."""
+        ``utils.py:53-57`` / ``input_utils.py:145-151`` produce).  Ids outside ``dense_shape`` raise (the kernels
+        would gather rows past the end of the embedding tables; the reference's gather_nd raises there too,
+        matrix_factorization.py:154)."""
         if self._csr is None:
             n_u, n_i = self.dense_shape
-            rows64, cols64 = self.indices[:, 0], self.indices[:, 1]
-            if rows64.numel():
-                # ids outside dense_shape (e.g. 1-based MovieLens ids) would make the kernels gather rows past the end of
-                # the embedding tables; the reference's gather_nd raises there too (matrix_factorization.py:154)
-                lo_r, hi_r = torch.aminmax(rows64)
-                lo_c, hi_c = torch.aminmax(cols64)
-                lo_r, hi_r, lo_c, hi_c = torch.stack([lo_r, hi_r, lo_c, hi_c]).tolist()
-                if lo_r < 0 or lo_c < 0 or hi_r >= n_u or hi_c >= n_i:
-                    raise ValueError(f"interaction indices out of range for dense_shape {self.dense_shape}: rows in "
-                                     f"[{lo_r}, {hi_r}], cols in [{lo_c}, {hi_c}] (are the ids 1-based?)")
-            key = rows64 * n_i + cols64
+            nnz = self.nnz
+            dev = self.values.device
+            rows = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+            cols = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+            flags = torch.empty(1, dtype=torch.int32, device=dev)
+            _abi.call("tmf_coo_split", _abi.ptr(self._raw), self._raw.element_size(), nnz, n_u, n_i, _abi.ptr(rows), _abi.ptr(cols),
+                      _abi.ptr(flags))
+            f = int(flags.item())
+            if f & 1:
+                r64, c64 = self._raw[:, 0], self._raw[:, 1]
+                raise ValueError(f"interaction indices out of range for dense_shape {self.dense_shape}: rows in "
+                                 f"[{int(r64.min())}, {int(r64.max())}], cols in [{int(c64.min())}, {int(c64.max())}] "
+                                 "(are the ids 1-based?)")
             perm = None
-            if key.numel() > 1 and not bool((key[1:] >= key[:-1]).all()):
+            vals = self.values
+            if f & 2:  # stored order is not row-major: stable sort once, losses go back to stored order
+                key = rows.to(torch.int64) * n_i + cols.to(torch.int64)
                 key, perm = torch.sort(key, stable=True)
-                rows64, cols64 = rows64[perm], cols64[perm]
-            rows = rows64.to(torch.int32).contiguous()
-            cols = cols64.to(torch.int32).contiguous()
-            vals = (self.values if perm is None else self.values[perm]).contiguous()
-            row_ptr = torch.empty(n_u + 1, dtype=torch.int32, device=rows.device)
-            _abi.call("tmf_rowptr_from_sorted", _abi.ptr(rows), rows.numel(), n_u, _abi.ptr(row_ptr))
+                rows, cols = rows[perm].contiguous(), cols[perm].contiguous()
+                vals = vals[perm].contiguous()
+            row_ptr = torch.empty(n_u + 1, dtype=torch.int32, device=dev)
+            _abi.call("tmf_rowptr_from_sorted", _abi.ptr(rows), nnz, n_u, _abi.ptr(row_ptr))
             self._csr = (row_ptr, cols, vals, rows, perm)
         return self._csr
 

@@ -23,6 +23,7 @@ def _plan(monkeypatch, capture_fails=False):
     plan = object.__new__(eng.TrainPlan)
     plan.opt_state = None
     plan.comm = None
+    plan.batched = False
     calls = {"eager": 0, "captured": 0, "capturing": False}
 
     def step(lr):
