@@ -17,15 +17,15 @@ torch.cuda.set_device(0)
 wl = bench.Workload(name, 0, 1)
 xu, xi = wl.feature_args()
 for _ in range(2):
-    wl.model.fit(1, xu, xi, wl.interactions_host(), lr=wl.lr, verbose=False)
+    wl.model.fit(1, xu, xi, wl.interactions(), lr=wl.lr, verbose=False)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
-wl.model.fit(1, xu, xi, wl.interactions_host(), lr=wl.lr, verbose=False)
+wl.model.fit(1, xu, xi, wl.interactions(), lr=wl.lr, verbose=False)
 torch.cuda.synchronize()
 print("fit(1) wall: %.1f ms" % ((time.perf_counter() - t0) * 1e3))
 pr = cProfile.Profile()
 pr.enable()
-wl.model.fit(1, xu, xi, wl.interactions_host(), lr=wl.lr, verbose=False)
+wl.model.fit(1, xu, xi, wl.interactions(), lr=wl.lr, verbose=False)
 torch.cuda.synchronize()
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(45)

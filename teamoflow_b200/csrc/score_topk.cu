@@ -24,19 +24,28 @@
 namespace tmf {
 
 constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
-constexpr int BN = 128;        // items per accumulator tile (TMEM columns); two CTAs share an SM
+constexpr int BN = 128;        // items per accumulator tile (TMEM columns)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NSTAGES = 3;     // B-operand ring (16 KB stages)
-constexpr int TMEM_COLS = 2 * BN;  // two accumulators per CTA, double-buffered against the epilogue
-constexpr int CAP = 2048;      // candidate slots per row (appended, never compacted; saturation -> exact path)
-constexpr int INIT_N = 512;    // a row's threshold state is initialised from its first <= INIT_N entries
+constexpr int MAX_STAGES = 8;  // B-operand ring (16 KB stages); the launch uses as many as shared memory allows (>= 2)
+// ONE CTA per SM owns all 512 TMEM columns = four 128x128 fp32 accumulators, and runs four epilogue GROUPS of four warps:
+// group g filters the tiles nt = g (mod 4) out of accumulator g.  16 epilogue warps per SM (four per sub-partition) where the
+// previous layout (two CTAs x four warps) had eight: a tile's epilogue is a chain of TMEM round trips at IPC ~0.2 per warp, so
+// the sub-partitions' issue slots were 60 % idle and the tensor pipe waited for accumulators (46 % active).
+constexpr int NACC = 4;
+constexpr int TMEM_COLS = NACC * BN;
+// A row's candidates are kept per group ("virtual rows": group g sees every fourth tile of the row): CAPG slots each,
+// appended; the groups exchange their running thresholds through shared memory (any group's threshold is a valid
+// keep-threshold for the whole row), so together they append about what one list per row would.
+constexpr int CAPG = 1024;
+constexpr int CAP = NACC * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
+constexpr int INIT_N = 512;    // a virtual row's threshold state is initialised from its first <= INIT_N entries
 constexpr int CPL = INIT_N / 32;  // entries per lane in the warp-cooperative initial selection
 constexpr int NBINS = 48;      // per-row score histogram bins (16-bit counts, two per word)
 constexpr int QCAP = 16;       // per-row survivor queue slots in shared memory (drained warp-wide)
 constexpr int HSTRIDE = NBINS / 2 + 1;  // words per row, padded against bank conflicts
-constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 4 GB
-constexpr int TOPK_THREADS = 256;
+constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
+constexpr int TOPK_THREADS = 128 + NACC * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
@@ -123,6 +132,31 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for every outstanding tcgen05.ld of the thread; the "+r" operands pin the consumers of BOTH buffers behind it
+__device__ __forceinline__ void tmem_ld_wait_for16x2(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]),
+                 "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]),
+                 "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_for16(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+                 "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait_for8(uint32_t (&r)[8]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
@@ -174,13 +208,12 @@ struct TopkParams {
   long long n_users, n_items;   // real sizes
   int ub0, n_ublocks;           // this launch covers user blocks [ub0, ub0 + n_ublocks)
   int n_tiles, kb;              // item tiles of BN, k-blocks of BK
+  int nstages;                  // B-operand ring depth of this launch
   int k, clamp, item_offset;
   const float* erow;            // [n_users_pad] error bound E of each user row against this item slab (global row index)
-  float2* cand;                 // [batch rows][CAP] (approx score, item id bits), batch-local row index
-  int* cnt;                     // [batch rows] candidates per row, -1 = overflow (exact path)
-  float* thr_out;               // [batch rows] final keep-threshold of the row
-  int* ovf_count;               // [1]
-  int* ovf_rows;                // [n_users_pad] global rows handed to the exact path
+  float2* cand;                 // [batch rows][NACC][CAPG] (approx score, item id bits), batch-local row index
+  int* cnt;                     // [batch rows][NACC] candidates per (row, group), -1 = overflow (the rerank hands the row to the exact path)
+  float* thr_out;               // [batch rows][NACC] final keep-threshold of each group (each is valid for the whole row)
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
   const float* fmt_stats;       // operand statistics (see use_fp16); NULL with force_fmt >= 0
@@ -210,7 +243,7 @@ struct RowState {
   float thr;      // current keep-threshold (+inf for padded rows)
   float thr_ext;  // externally supplied floor of the threshold (-inf when there is none)
   float lo, w, inv_w, E;
-  int cnt;        // list length; > CAP = saturated (-> exact path)
+  int cnt;        // list length; > CAPG = saturated (-> exact path)
   int cq;         // entries waiting in the lane's queue
   int bthr, A;    // threshold bin and # entries with bin >= bthr
 };
@@ -244,7 +277,7 @@ __device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float
     const bool ok = (s < cq) && (e.x >= thr);
     const bool okh = ok && (e.x >= lo);
     const int b = (int)fminf(fmaxf((e.x - lo) * inv_w, 0.f), (float)(NBINS - 1));
-    const int st_ok = ok && (cnt < CAP);
+    const int st_ok = ok && (cnt < CAPG);
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.s32 p, %0, 0;\n\t"
@@ -308,49 +341,54 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int 
   }
 }
 
-// 8-column group maxima of one 32-column slice (3-input max tree, no branches)
-__device__ __forceinline__ void group_max4(const uint32_t (&r)[32], float* m8) {
+// hit bits of the two 8-column groups of one 16-column chunk: group maximum (3-input max tree, no branches) >= threshold
+__device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[16], float thr) {
+  unsigned hm = 0;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < 2; ++g) {
     const float a = fmaxf(fmaxf(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
     const float b = fmaxf(fmaxf(a, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
     const float c = fmaxf(fmaxf(b, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
-    m8[g] = fmaxf(c, __uint_as_float(r[8 * g + 7]));
+    hm |= (fmaxf(c, __uint_as_float(r[8 * g + 7])) >= thr) ? (1u << g) : 0u;
   }
+  return hm;
 }
 
 // Steady-state filter of one 128-column accumulator tile (rows with a threshold).  Pass 1 streams the tile through
-// registers once and keeps only the 16 group maxima -- no votes, no branches, all four TMEM loads pipelined.  One
-// REDUX.OR of the per-lane hit masks then names the 8-column groups in which ANY row of the warp has a survivor
-// (about 3 of 16 per tile at 1M items); only those are re-read from TMEM (x8) and their survivors queued with
-// predicated stores, all lanes convergent.  (The previous slice-at-a-time version spent ~700 cycles per slice in
-// vote -> branch -> vote chains and divergent push blocks; two epilogue warps per sub-partition cannot hide that.)
+// registers once, 16 columns at a time through two buffers (the load of chunk c+1 is in flight while chunk c is reduced),
+// and keeps only the 16 group-maximum hit bits -- no votes, no branches.  One REDUX.OR of the per-lane hit masks then names the
+// 8-column groups in which ANY row of the warp has a survivor (about 3 of 16 per tile at 1M items); only those are re-read
+// from TMEM (x8) and their survivors queued with predicated stores, all lanes convergent.
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
                                               const TopkParams& p) {
-  uint32_t ra[32], rb[32];
-  float m8[4];
+  uint32_t ra[16], rb[16];
   const float thr = st.thr;  // invalid rows carry thr = +inf; NaN-padded columns never win a max or a compare
-  unsigned hm = 0;
-  tmem_ld32(t_base, ra);
-  tmem_ld32(t_base + 32u, rb);
-  tmem_ld_wait_for(ra);   // (wait::ld covers both loads; the next pair is issued right behind)
-  group_max4(ra, m8);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (1u << g) : 0u;
-  tmem_ld32(t_base + 64u, ra);
-  tmem_ld_wait_for(rb);
-  group_max4(rb, m8);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (16u << g) : 0u;
-  tmem_ld32(t_base + 96u, rb);
-  tmem_ld_wait_for(ra);
-  group_max4(ra, m8);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (256u << g) : 0u;
-  tmem_ld_wait_for(rb);
-  group_max4(rb, m8);
-#pragma unroll
-  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (4096u << g) : 0u;
+  unsigned hm;
+  // tcgen05.wait::ld waits for EVERY outstanding load of the thread, so the overlap is: issue the load of chunk c+2 into the
+  // buffer just reduced, reduce the other buffer (chunk c+1, complete since the previous wait), then wait.
+  tmem_ld16(t_base, ra);
+  tmem_ld16(t_base + 16u, rb);
+  tmem_ld_wait_for16x2(ra, rb);
+  hm = chunk_hits(ra, thr);
+  tmem_ld16(t_base + 32u, ra);
+  hm |= chunk_hits(rb, thr) << 2;
+  tmem_ld_wait_for16(ra);
+  tmem_ld16(t_base + 48u, rb);
+  hm |= chunk_hits(ra, thr) << 4;
+  tmem_ld_wait_for16(rb);
+  tmem_ld16(t_base + 64u, ra);
+  hm |= chunk_hits(rb, thr) << 6;
+  tmem_ld_wait_for16(ra);
+  tmem_ld16(t_base + 80u, rb);
+  hm |= chunk_hits(ra, thr) << 8;
+  tmem_ld_wait_for16(rb);
+  tmem_ld16(t_base + 96u, ra);
+  hm |= chunk_hits(rb, thr) << 10;
+  tmem_ld_wait_for16(ra);
+  tmem_ld16(t_base + 112u, rb);
+  hm |= chunk_hits(ra, thr) << 12;
+  tmem_ld_wait_for16(rb);
+  hm |= chunk_hits(rb, thr) << 14;
   unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
   if (TMF_DBG(p) == 1) gmask = 0;
   const int id0 = p.item_offset + col0;
@@ -436,7 +474,7 @@ __device__ __noinline__ float warp_select_kth(const float2* buf, int n, int k, i
   return key2f(prefix);
 }
 
-// Warp-cooperative (re)build of one row's threshold state from its list of n (<= CAP) entries, streamed from L2:
+// Warp-cooperative (re)build of one row's threshold state from its list of n (<= CAPG) entries, streamed from L2:
 // exact k-th largest by radix select, histogram re-centred on [kth, kth + 4 (max - kth)), list compacted in place
 // against the new threshold (clamp mode also keeps the k lowest item ids).  Used once when a row has seen its first
 // 3 tiles and again whenever its list is about to saturate, so a badly placed histogram range heals itself.
@@ -689,25 +727,33 @@ __device__ __noinline__ void warp_rebuild_saturated(float2* buf, int n, int k, i
 }
 
 // ------------------------------------------------------------------ the fused kernel
+// dynamic shared memory besides the B ring: alignment slack, A tile, 256 B of barriers + TMEM slot, per-virtual-row histograms,
+// queues, published thresholds, rebuild outputs
+static size_t topk_smem_fixed_bytes(int kb) {
+  return 1024 + (size_t)kb * A_SUB_BYTES + 256 + (size_t)NACC * BM * HSTRIDE * 4 + 16 + (size_t)NACC * BM * QCAP * 8 +
+         (size_t)NACC * BM * 8 + (size_t)NACC * 4 * 8 * 4;
+}
+
 template <bool DUMP, bool PROF>
-__global__ void __launch_bounds__(TOPK_THREADS, 2)
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve (1024-byte aligned operand tiles first)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] bf16
-  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // NSTAGES x [BN][64] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGES * B_STAGE_BYTES);
-  uint64_t* full_bar = bars;                  // [NSTAGES]
-  uint64_t* empty_bar = bars + NSTAGES;       // [NSTAGES]
-  uint64_t* a_full = bars + 2 * NSTAGES;      // [1]
-  uint64_t* a_empty = a_full + 1;             // [1]
-  uint64_t* tfull = a_empty + 1;              // [2]
-  uint64_t* tempty = tfull + 2;               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(tmem_slot + 4);             // [BM][HSTRIDE] per-row score histograms
-  float2* queues = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(hist_rows + BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [BM][QCAP]
-  float* init_out = reinterpret_cast<float*>(queues + BM * QCAP);  // [4 warps][8]
+  unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] 16-bit
+  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // nstages x [BN][64] 16-bit
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nstages * B_STAGE_BYTES);
+  uint64_t* full_bar = bars;                        // [MAX_STAGES]
+  uint64_t* empty_bar = bars + MAX_STAGES;          // [MAX_STAGES]
+  uint64_t* a_full = bars + 2 * MAX_STAGES;         // [1]
+  uint64_t* a_empty = a_full + 1;                   // [1]
+  uint64_t* tfull = a_empty + 1;                    // [NACC]
+  uint64_t* tempty = tfull + NACC;                  // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
+  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 32);                  // [NACC * BM][HSTRIDE] per-virtual-row score histograms
+  float2* queues = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(hist_rows + NACC * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [NACC * BM][QCAP]
+  float2* thr_sh = queues + NACC * BM * QCAP;                                    // [NACC * BM] (threshold, user-block tag) published per virtual row
+  float* init_out = reinterpret_cast<float*>(thr_sh + NACC * BM);                // [NACC * 4 warps][8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto now = [] () -> long long { return PROF ? clock64() : 0ll; };  // cycle counters only in the profiling build
@@ -717,16 +763,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapV) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NSTAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_empty), 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {  // TMEM: 256 columns = two 128x128 fp32 accumulators (the SM's other CTA takes the other half)
+  if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < NACC * BM; i += TOPK_THREADS) thr_sh[i] = make_float2(-INFINITY, __int_as_float(-1));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -752,7 +799,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             w_empty += now() - t0;
             mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
             tma_load_2d(smem_u32(sB + stage * B_STAGE_BYTES), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
         }
         if (PROF) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
@@ -761,8 +808,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      uint32_t acc_bits = 0;  // bit a = parity of the number of times accumulator a has been filled
       // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
       const uint32_t idesc = f16 ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;
@@ -771,8 +819,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
+          const int acc = nt & (NACC - 1);
           long long t0 = now();
-          mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
+          mbar_wait(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
           w_tempty += now() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -789,11 +838,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
                               (uint32_t)((kb | k) != 0));
             }
             tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(smem_u32(&tfull[acc]));  // accumulator ready for the epilogue
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          tcgen05_commit(smem_u32(&tfull[acc]));  // accumulator ready for its epilogue group
+          acc_bits ^= 1u << acc;
         }
         tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
         if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
@@ -801,14 +849,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
-    int* radix = reinterpret_cast<int*>(queues + q * 32 * QCAP);  // radix-select scratch aliases the warp's (empty) queues
-    const uint32_t hrow = smem_u32(hist_rows + (q * 32 + lane) * HSTRIDE);
-    const uint32_t queue = smem_u32(queues + (q * 32 + lane) * QCAP);
-    float* iout = init_out + q * 8;
+    const int grp = (warp - 4) >> 2;  // epilogue group = accumulator = tile residue mod NACC
+    const int q = warp & 3;           // TMEM lane quarter == warp % 4
+    const int vrow = grp * BM + q * 32 + lane;  // virtual row: (group, row) has its own threshold state, queue and list
+    int* radix = reinterpret_cast<int*>(queues + (grp * BM + q * 32) * QCAP);  // radix-select scratch aliases the warp's (empty) queues
+    const uint32_t hrow = smem_u32(hist_rows + vrow * HSTRIDE);
+    const uint32_t queue = smem_u32(queues + vrow * QCAP);
+    float* iout = init_out + (grp * 4 + q) * 8;
     const int n_items = (int)p.n_items;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
     for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
       const long long lrow = (long long)ub * BM + q * 32 + lane;       // batch-local row (candidate buffers)
       const long long row = (long long)p.ub0 * BM + lrow;              // global row
@@ -836,18 +885,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           st.lo = INFINITY;
         }
       }
-      float2* buf = p.cand + lrow * CAP;
+      // publish (threshold, user block): the other groups of this row adopt it when it is higher than theirs.  The tag keeps a
+      // group that is still in the previous user block from reading a threshold that belongs to other rows.
+      const float tag = __int_as_float(ub);
+      if (!DUMP) thr_sh[vrow] = make_float2(valid ? st.thr : -INFINITY, tag);
+      float thr_pub = st.thr;
+      float2* buf = p.cand + (lrow * NACC + grp) * CAPG;
       long long w_tfull = 0, w_work = 0, w_init = 0;
-      for (int nt = 0; nt < p.n_tiles; ++nt) {
+      for (int nt = grp; nt < p.n_tiles; nt += NACC) {
         long long t0 = now();
-        mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+        mbar_wait(smem_u32(&tfull[grp]), acc_phase);
+        acc_phase ^= 1;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         long long t1 = now();
         w_tfull += t1 - t0;
         tcgen05_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
         const bool tail_tile = (nt + 1) * BN > n_items;
         if (!DUMP && warp_inited && TMF_DBG(p) < 2) {
+          // adopt the best threshold any group of this row has published for this user block (monotone, always valid)
+          if (valid) {
+#pragma unroll
+            for (int g2 = 0; g2 < NACC; ++g2) {
+              const float2 o = thr_sh[g2 * BM + q * 32 + lane];
+              if (g2 != grp && __float_as_int(o.y) == ub) st.thr = fmaxf(st.thr, o.x);
+            }
+          }
           epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, p);
         } else if (TMF_DBG(p) < 3) {
           uint32_t ra[32], rb[32];
@@ -865,9 +928,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         }
         // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
-        mbar_arrive(smem_u32(&tempty[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        mbar_arrive(smem_u32(&tempty[grp]));
         long long t2 = now();
         w_work += t2 - t1;
         if (!DUMP) {
@@ -879,12 +940,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
           // the same tile because everything is appended until then), later whenever a list is about to saturate
           const bool first = !warp_inited && __any_sync(0xffffffffu, valid && st.cnt >= INIT_N - BN);
-          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
+          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && (first || (warp_inited && st.cnt > CAPG - 4 * QCAP)));
           if (need) {  // the radix scratch aliases the queues: empty them first (lengths may grow a little)
             const long long tq = now();
             drain_queues(st, queue, buf, hrow, p.k, p.clamp);
             if (PROF && lane == 0) { atomicAdd(p.prof + 19, (unsigned long long)(now() - tq)); atomicAdd(p.prof + 18, 1ull); }
-            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
+            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && (first || (warp_inited && st.cnt > CAPG - 4 * QCAP)));
           }
           while (need) {
             const int owner = __ffs(need) - 1;
@@ -892,9 +953,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             const int n_o = __shfl_sync(0xffffffffu, st.cnt, owner);
             const float E_o = __shfl_sync(0xffffffffu, st.E, owner);
             __syncwarp();
-            float2* obuf = p.cand + ((long long)ub * BM + q * 32 + owner) * CAP;
-            uint32_t* ohist = hist_rows + (q * 32 + owner) * HSTRIDE;
+            float2* obuf = p.cand + (((long long)ub * BM + q * 32 + owner) * NACC + grp) * CAPG;
+            uint32_t* ohist = hist_rows + (grp * BM + q * 32 + owner) * HSTRIDE;
             const float lo_o = __shfl_sync(0xffffffffu, st.lo, owner);
+            // floor of the rebuilt threshold: the external bound and whatever the row's groups have agreed on so far
+            const float floor_o = __shfl_sync(0xffffffffu, fmaxf(st.thr_ext, warp_inited ? st.thr : -INFINITY), owner);
             const long long tr = now();
             int which = 0;
             if (first && n_o <= INIT_N) {
@@ -903,8 +966,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               which = 1;
               const float w_o = __shfl_sync(0xffffffffu, st.w, owner);
               const int bthr_o = __shfl_sync(0xffffffffu, st.bthr, owner);
-              const float ext_o = __shfl_sync(0xffffffffu, st.thr_ext, owner);
-              warp_rebuild_saturated(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, lo_o, w_o, bthr_o, ext_o, iout);
+              warp_rebuild_saturated(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, lo_o, w_o, bthr_o, floor_o, iout);
             } else {  // a bounded row (idle histogram) that filled up anyway: full selection
               which = 2;
               warp_rebuild_row(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, radix, iout);
@@ -914,15 +976,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               st.lo = iout[0]; st.w = iout[1]; st.inv_w = iout[2];
               st.bthr = __float_as_int(iout[3]); st.A = __float_as_int(iout[4]);
               st.cnt = __float_as_int(iout[5]);
-              st.thr = fmaxf(edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp), st.thr_ext);
-              if (st.cnt > CAP - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
-                st.cnt = CAP + 1;
+              st.thr = fmaxf(fmaxf(edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp), st.thr_ext), warp_inited ? st.thr : -INFINITY);
+              if (st.cnt > CAPG - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
+                st.cnt = CAPG + 1;
                 st.thr = INFINITY;
               }
             }
             __syncwarp();
           }
           if (first) warp_inited = true;
+          if (warp_inited && valid && st.thr > thr_pub && st.cnt <= CAPG) {  // publish a raised threshold
+            thr_pub = st.thr;
+            thr_sh[vrow] = make_float2(st.thr, tag);
+          }
         }
         w_init += now() - t2;
       }
@@ -931,15 +997,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
         atomicAdd(p.prof + 6, (unsigned long long)w_init); atomicAdd(p.prof + 7, 1ull);
       }
-      if (PROF) atomicAdd(p.prof + 20, (unsigned long long)(valid ? min(st.cnt, CAP) : 0));
-      const bool ovf = st.cnt > CAP;
-      if (valid && ovf) {
-        const int slot = atomicAdd(p.ovf_count, 1);
-        p.ovf_rows[slot] = (int)row;
-        if (PROF) atomicAdd(p.prof + 8, 1ull);
+      if (PROF) atomicAdd(p.prof + 20, (unsigned long long)(valid ? min(st.cnt, CAPG) : 0));
+      const bool ovf = st.cnt > CAPG;
+      if (PROF && valid && ovf) atomicAdd(p.prof + 8, 1ull);
+      if (!DUMP) {
+        p.cnt[lrow * NACC + grp] = valid ? (ovf ? -1 : st.cnt) : 0;
+        p.thr_out[lrow * NACC + grp] = ovf ? -INFINITY : st.thr;
       }
-      p.cnt[lrow] = valid ? (ovf ? -1 : st.cnt) : 0;
-      p.thr_out[lrow] = st.thr;
       __syncwarp();
     }
   }
@@ -1047,31 +1111,52 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   const long long lrow = (long long)blockIdx.x * RR_WARPS + w;
   if (lrow >= p.n_rows) return;
   const long long row = p.row0 + lrow;
-  const int n = p.cnt[lrow];
-  if (n < 0) return;  // overflowed in the main kernel: exact_rows_kernel owns it
-  const float2* buf = p.cand + lrow * CAP;
+  // the row's candidates: one list per epilogue group of the main kernel ([row][NACC][CAPG]); each group's final threshold is
+  // a valid keep-threshold for the whole row, so the highest one applies to all lists
+  int ng[NACC];
+  int n = 0;
+  bool overflowed = false;
+  float thr = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < NACC; ++g) {
+    ng[g] = p.cnt[lrow * NACC + g];
+    overflowed |= ng[g] < 0;
+    n += max(ng[g], 0);
+    thr = fmaxf(thr, p.thr[lrow * NACC + g]);
+  }
+  if (overflowed) {  // a list saturated in the main kernel (massive ties): the exact path ranks this row
+    if (lane == 0) {
+      const int slot = atomicAdd(p.ovf_count, 1);
+      p.ovf_rows[slot] = (int)row;
+    }
+    return;
+  }
+  float2* rowbuf = const_cast<float2*>(p.cand) + lrow * CAP;
   const int k = p.k;
   const unsigned lt = (1u << lane) - 1u;
   if (lane == 0) mbar_init(smem_u32(bar), 1);
   for (int c = lane; c < p.ld; c += 32) ud[c] = (double)p.U[row * p.ld + c];
-  float thr = p.thr[lrow];
   // ---- 1. superset by the main kernel's final threshold (or the clamp-mode filler rule)
   int m = 0;
-  for (int b0 = 0; b0 < n; b0 += 256) {
-    float2 x[8];
+#pragma unroll 1
+  for (int g = 0; g < NACC; ++g) {
+    const float2* buf = rowbuf + g * CAPG;
+    for (int b0 = 0; b0 < ng[g]; b0 += 256) {
+      float2 x[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int e = b0 + 32 * t + lane;
-      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
-    }
+      for (int t = 0; t < 8; ++t) {
+        const int e = b0 + 32 * t + lane;
+        x[t] = (e < ng[g]) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+      }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int e = b0 + 32 * t + lane;
-      const bool keep = e < n && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      const int pos = m + __popc(bal & lt);
-      if (keep && pos < SEL_CAP) pr[pos] = x[t];
-      m += __popc(bal);
+      for (int t = 0; t < 8; ++t) {
+        const int e = b0 + 32 * t + lane;
+        const bool keep = e < ng[g] && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        const int pos = m + __popc(bal & lt);
+        if (keep && pos < SEL_CAP) pr[pos] = x[t];
+        m += __popc(bal);
+      }
     }
   }
   __syncwarp();
@@ -1080,9 +1165,23 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
     float kth;
     if (m <= SEL_CAP) {
       kth = smem_select_kth(pr, m, k, radix);
-    } else {  // loose running threshold (badly placed histogram): select over the whole list in global memory
+    } else {  // loose running thresholds (badly placed histograms): make the row's lists one contiguous list in place, select over it
+      int off = ng[0];
+#pragma unroll 1
+      for (int g = 1; g < NACC; ++g) {
+        const float2* src = rowbuf + g * CAPG;
+        for (int b0 = 0; b0 < ng[g]; b0 += 32) {  // destination <= source: forward copy, reads of a batch precede its writes
+          const int e = b0 + lane;
+          const float2 x = e < ng[g] ? __ldcg(src + e) : make_float2(0.f, 0.f);
+          __syncwarp();
+          if (e < ng[g]) __stcg(rowbuf + off + e, x);
+        }
+        off += ng[g];
+        __syncwarp();
+      }
+      __threadfence_block();
       float mx;
-      kth = warp_select_kth(buf, n, k, radix, mx);
+      kth = warp_select_kth(rowbuf, n, k, radix, mx);
     }
     thr = fmaxf(thr, keep_threshold(kth, p.erow[row], p.clamp));
     if (m <= SEL_CAP) {
@@ -1104,7 +1203,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int e = b0 + 32 * t + lane;
-          x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+          x[t] = (e < n) ? __ldcg(rowbuf + e) : make_float2(-INFINITY, 0.f);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -1474,8 +1573,8 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   L.off_vnorm = o; o = align_up(o + (size_t)L.ni_pad * 4, 256);
   L.off_vmax = o; o += 256;
   L.off_cand = o; o = align_up(o + (size_t)L.batch_rows * CAP * 8, 256);
-  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
-  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
+  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * NACC * 4, 256);
+  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * NACC * 4, 256);
   L.off_ovfc = o; o += 256;
   L.off_ovfr = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.scratch_rows = (int)std::min<long long>(32, n_users);
@@ -1562,7 +1661,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.n_tiles = (int)(L.ni_pad / BN); p.kb = L.kb;
   p.k = k; p.clamp = clamp ? 1 : 0; p.item_offset = item_offset;
   p.erow = erow;
-  p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
+  p.cand = cand; p.cnt = cnt; p.thr_out = thr;
   p.dump = dump; p.dump_ld = n_items;
   p.row_bound = row_bound;
   p.fmt_stats = fmt_stats; p.force_fmt = force_fmt;
@@ -1581,8 +1680,11 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   q.U = U; q.V = V; q.erow = erow; q.prof = p.prof; q.cand = cand; q.cnt = cnt; q.thr = thr; q.ovf_count = ovfc; q.ovf_rows = ovfr;
   q.out_idx = out_idx; q.out_score = out_score;
 
-  const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 +
-                      (size_t)BM * HSTRIDE * sizeof(uint32_t) + 16 + (size_t)BM * QCAP * 8 + 4 * 8 * sizeof(float);
+  const size_t smem_max = 227 * 1024;
+  const size_t fixed = topk_smem_fixed_bytes(L.kb);
+  TMF_REQUIRE(fixed + 2 * B_STAGE_BYTES <= smem_max, "tmf_score_topk: shared memory exhausted (n_components too large)");
+  p.nstages = (int)std::min<size_t>(MAX_STAGES, (smem_max - fixed) / B_STAGE_BYTES);
+  const size_t smem = fixed + (size_t)p.nstages * B_STAGE_BYTES;
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1594,7 +1696,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   for (int ub0 = 0; ub0 < total_ublocks; ub0 += UB_BATCH) {
     p.ub0 = ub0;
     p.n_ublocks = std::min(UB_BATCH, total_ublocks - ub0);
-    const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
+    const int grid = std::min(kNumSMs, p.n_ublocks);  // one persistent CTA per SM (all of its TMEM, ~220 KB of its shared memory)
     if (dump != nullptr) score_topk_kernel<true, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
     else if (p.prof) score_topk_kernel<false, true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
     else score_topk_kernel<false, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);

@@ -1,8 +1,6 @@
 """Host logic of ``TrainPlan.run`` (first step eager, the rest replayed from one captured graph; eager fallbacks; the
 launch accounting bench.py's ``gpu_launches`` claim relies on).  CPU only: ``torch.cuda.CUDAGraph`` / ``torch.cuda.graph``
 are replaced by recording stand-ins."""
-import contextlib
-
 import pytest
 import torch
 
@@ -31,20 +29,19 @@ def _plan(monkeypatch, capture_fails=False):
         _abi.launch_count += LAUNCHES_PER_STEP
         _abi.call_count += LAUNCHES_PER_STEP
 
-    @contextlib.contextmanager
-    def graph_ctx(g):
+    def capture(fn):  # stand-in for eng.capture_graph (stream + capture_begin / capture_end around fn)
         if capture_fails:
             raise RuntimeError("capture refused")
         calls["capturing"] = True
         try:
-            yield
+            fn()
         finally:
             calls["capturing"] = False
+        return _Graph()
 
     plan.step = step
     _Graph.replays = 0
-    monkeypatch.setattr(torch.cuda, "CUDAGraph", _Graph)
-    monkeypatch.setattr(torch.cuda, "graph", graph_ctx)
+    monkeypatch.setattr(eng, "capture_graph", capture)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(eng.TrainPlan, "USE_CUDA_GRAPH", True)
     return plan, calls
