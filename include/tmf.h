@@ -250,6 +250,16 @@ TMF_API int tmf_dcg(const int32_t* topk, int64_t n_users, int32_t k, const int32
 TMF_API int tmf_idcg(int64_t n_users, int64_t n_items, int32_t k, const int32_t* a_ptr, const float* a_val, float* idcg,
              float* row_nnz, tmf_stream_t stream);
 
+/* fp32-accurate GEMM on the tensor cores (tcgen05 + TMEM + TMA): C[m, n] = op(A) op(B) with the same operand conventions as
+ * tmf_gemm_f32 (ta: A is stored [k, m]; tb: B is stored [n, k]; row-major, leading dimensions in floats).  Every operand is split
+ * exactly into three bf16 planes and the six significant plane products are accumulated in fp32 (error ~ 3 * 2^-24 |a||b| per
+ * product: the 1e-5 tolerance of north_star holds).  Used for the dense contractions of the towers -- the ReLU embedding's second
+ * stage and its backward (embedding_graphs.py:85-87) and X.W / X^T.dE for genuinely dense features (embedding_graphs.py:38) --
+ * above a size threshold; deterministic (fixed K-split order).  ws: tmf_gemm_tc_ws_bytes(m, n, k). */
+TMF_API size_t tmf_gemm_tc_ws_bytes(int64_t m, int64_t n, int64_t k);
+TMF_API int tmf_gemm_tc(int32_t ta, int32_t tb, int64_t m, int64_t n, int64_t k, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float* C, int64_t ldc, void* ws, size_t ws_bytes, tmf_stream_t stream);
+
 /* ------------------------------------------------------------------ multi-GPU exchange over NVLink peer memory
  * (new-build, SURVEY 8e: the reference has no distribution).  One process per GPU; a rank allocates its exchange
  * buffers with tmf_peer_alloc (plain cudaMalloc, zero-filled, SYNCHRONOUS), exports them with tmf_ipc_export (64-byte

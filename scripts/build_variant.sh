@@ -14,7 +14,7 @@ NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a
 mkdir -p ../../variants
 $NV "$@" -c $SRC -o /tmp/variant_$NAME.o 2> ../../variants/$NAME.ptxas.log
 OBJS=""
-for f in setup train score score_topk peer; do
+for f in setup train score score_topk peer gemm_tc; do
   if [ "$f.cu" == "$SRC" ]; then OBJS="$OBJS /tmp/variant_$NAME.o"; else OBJS="$OBJS $f.o"; fi
 done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/libtmf_$NAME.so $OBJS

@@ -47,6 +47,8 @@ SIGNATURES = {
     "tmf_col_sum": (_i32, [_p, _i64, _i32, _i32, _p, _p, _sz, _p]),
     "tmf_relu_mask": (_i32, [_p, _p, _i64, _p]),
     "tmf_gemm_f32": (_i32, [_i32, _i32, _i32, _i32, _i32, _p, _i32, _p, _i32, _p, _i32, _p]),
+    "tmf_gemm_tc_ws_bytes": (_sz, [_i64, _i64, _i64]),
+    "tmf_gemm_tc": (_i32, [_i32, _i32, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _sz, _p]),
     "tmf_gather_rows2d": (_i32, [_p, _i32, _i64, _p, _i32, _p, _p]),
     "tmf_gather_nd2": (_i32, [_p, _i64, _p, _i64, _p, _p]),
     "tmf_wmrb_forward": (_i32, [_i64, _p, _p, _p, _i32, _f32, _p, _p]),
@@ -81,7 +83,7 @@ call_count = 0
 launch_count = 0
 # kernels per ABI call where it is not 1 (memsets are not counted)
 KERNELS_PER_CALL = {"tmf_spmm_seg": 2, "tmf_transpose_build": 3, "tmf_l2_normalize_global": 3, "tmf_kl_coef": 5, "tmf_kl_moments": 2, "tmf_kl_coef_from_moments": 2,
-                    "tmf_reduce_sum": 2, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 8, "tmf_score_topk_bounded": 8}
+                    "tmf_reduce_sum": 2, "tmf_gemm_tc": 4, "tmf_col_sum": 2, "tmf_rank_rows": 2, "tmf_score_topk": 8, "tmf_score_topk_bounded": 8}
 
 
 class TmfError(RuntimeError):

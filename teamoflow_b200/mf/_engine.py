@@ -73,11 +73,24 @@ def spmm(n_seg, seg_ptr, n_entries, idx, cpos, coef, src, n_cols, out=None, ws=N
     return out
 
 
-def gemm(ta, tb, m, n, k, A, B, out=None):
+# dense contractions with at least this many multiply-adds go to the tensor cores (tmf_gemm_tc: tcgen05, operands split
+# exactly into three bf16 planes, fp32 accumulation in TMEM); smaller ones stay on the SIMT fp32 kernel (launch-bound anyway)
+TC_GEMM_MIN_MACS = 1 << 22
+
+
+def gemm(ta, tb, m, n, k, A, B, out=None, tc=None):
+    """``out[m, n] = op(A) op(B)`` (``ta``: A is stored [k, m]; ``tb``: B is stored [n, k]); storages with padded leading dims."""
     if out is None:
         out = torch.zeros(m, pad4(n), dtype=torch.float32, device=A.device)
-    _abi.call("tmf_gemm_f32", int(ta), int(tb), m, n, k, _abi.ptr(A), A.shape[1], _abi.ptr(B), B.shape[1],
-              _abi.ptr(out), out.shape[1])
+    use_tc = (m * n * k >= TC_GEMM_MIN_MACS) if tc is None else bool(tc)
+    if use_tc:
+        need = _abi.query("tmf_gemm_tc_ws_bytes", m, n, k)
+        ws = _ws(need)
+        _abi.call("tmf_gemm_tc", int(ta), int(tb), m, n, k, _abi.ptr(A), A.shape[1], _abi.ptr(B), B.shape[1],
+                  _abi.ptr(out), out.shape[1], _abi.ptr(ws), ws.numel())
+    else:
+        _abi.call("tmf_gemm_f32", int(ta), int(tb), m, n, k, _abi.ptr(A), A.shape[1], _abi.ptr(B), B.shape[1],
+                  _abi.ptr(out), out.shape[1])
     return out
 
 
@@ -119,6 +132,8 @@ class Tower:
     # -- helpers
     def _x_times(self, M, n_cols, out=None):
         X = self.X
+        if X.dense is not None:  # genuinely dense features: X M on the tensor cores (embedding_graphs.py:38)
+            return gemm(0, 0, self.n, n_cols, X.shape[1], X.dense, M, out=out)
         if X.identity:
             if out is None:
                 return M
@@ -128,6 +143,8 @@ class Tower:
 
     def _xt_times(self, D, n_cols):
         X = self.X
+        if X.dense is not None:  # X^T D: the stored [n, F] matrix read transposed
+            return gemm(1, 0, X.shape[1], n_cols, self.n, X.dense, D)
         if X.identity:
             return D
         ptr_t, rows_t, perm_t = X.transpose()

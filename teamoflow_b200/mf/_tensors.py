@@ -156,13 +156,20 @@ def as_interactions(x, shape=None):
     return SparseInteractions(idx, A[idx[:, 0], idx[:, 1]], tuple(A.shape))
 
 
-class FeatureMatrix:
-    """Feature matrix ``X [n, F]`` as CSR (``ptr``, ``idx``, ``val``) or the identity."""
+# a dense feature tensor with more than this fraction of non-zeros stays dense (X W on the tensor cores, tmf_gemm_tc); below
+# it the CSR gather / segment-sum wins (north_star: "a dense tcgen05/TMA GEMM only when the feature matrices are dense")
+DENSE_FEATURE_MIN_DENSITY = 0.25
 
-    def __init__(self, n_rows, n_cols, ptr=None, idx=None, val=None, identity=False):
+
+class FeatureMatrix:
+    """Feature matrix ``X [n, F]`` as CSR (``ptr``, ``idx``, ``val``), the identity, or -- when genuinely dense -- a dense
+    fp32 ``[n, ceil4(F)]`` storage (``dense``)."""
+
+    def __init__(self, n_rows, n_cols, ptr=None, idx=None, val=None, identity=False, dense=None):
         self.shape = (int(n_rows), int(n_cols))
         self.identity = bool(identity)
         self.ptr, self.idx, self.val = ptr, idx, val
+        self.dense = dense
         self._t = None
 
     @classmethod
@@ -171,6 +178,8 @@ class FeatureMatrix:
 
     @property
     def nnz(self):
+        if self.dense is not None:
+            return int((self.dense != 0).sum())
         return self.shape[0] if self.identity else int(self.idx.numel())
 
     def transpose(self):
@@ -188,6 +197,8 @@ class FeatureMatrix:
         dev = device()
         if self.identity:
             return torch.eye(n, dtype=torch.float32, device=dev)
+        if self.dense is not None:
+            return self.dense[:, :F].clone()
         out = torch.zeros(n, F, dtype=torch.float32, device=dev)
         rows = torch.repeat_interleave(torch.arange(n, device=dev), (self.ptr[1:] - self.ptr[:-1]).to(torch.int64))
         out.index_put_((rows, self.idx.long()), self.val, accumulate=True)
@@ -225,6 +236,10 @@ def as_features(x):
     if n == F and bool((X == torch.eye(n, device=X.device)).all()):
         return FeatureMatrix.eye(n)
     nz = torch.nonzero(X)  # row-major order
+    if nz.shape[0] > DENSE_FEATURE_MIN_DENSITY * n * F:
+        st = torch.zeros(n, pad4(F), dtype=torch.float32, device=X.device)
+        st[:, :F] = X
+        return FeatureMatrix(n, F, dense=st)
     counts = torch.bincount(nz[:, 0], minlength=n)
     ptr = torch.zeros(n + 1, dtype=torch.int32, device=X.device)
     ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)

@@ -574,3 +574,103 @@ def test_save_and_load_round_trip(tmp_path):
     assert torch.equal(again.recall_at_k(torch.as_tensor(A), k=5), model.recall_at_k(torch.as_tensor(A), k=5))
     # and it can be trained again (weights are re-initialised by fit like the reference does)
     again.fit(1, FeatureMatrix.eye(n_u), FeatureMatrix.eye(n_i), inter, lr=0.05, verbose=False)
+
+
+# ------------------------------------------------------------------------------- tensor-core GEMM (tcgen05, split-bf16)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(300, 70, 1000), (128, 64, 64), (1000, 160, 32), (320, 64, 50_000), (5, 3, 7)])
+def test_gemm_tc_matches_fp64_to_fp32_accuracy(ta, tb, m, n, k):
+    """tmf_gemm_tc (three exact bf16 planes per operand, six plane products, fp32 accumulation in TMEM) against an fp64
+    product: error bounded like an fp32 GEMM's (a few 2^-24 |a||b| per term), far inside north_star's 1e-5."""
+    from teamoflow_b200 import _abi
+    rng = np.random.default_rng(m * 7 + n * 3 + k + ta * 2 + tb)
+    A = (rng.standard_normal((k, m) if ta else (m, k)) * np.exp(rng.standard_normal((1, 1)))).astype(np.float32)
+    B = (rng.standard_normal((n, k) if tb else (k, n))).astype(np.float32)
+    A[0, 0] = 1e-20; B[0, 0] = 3e4  # small / large magnitudes survive the split
+    want = (A.T if ta else A).astype(np.float64) @ (B.T if tb else B).astype(np.float64)
+    bound = np.abs(A.T if ta else A).astype(np.float64) @ np.abs(B.T if tb else B).astype(np.float64)
+    pad = lambda x: torch.nn.functional.pad(torch.as_tensor(x, device="cuda"), (0, (-x.shape[1]) % 4)).contiguous()  # noqa: E731
+    At, Bt = pad(A), pad(B)
+    out = torch.full((m, (n + 3) // 4 * 4 + 4), 7.0, device="cuda")  # an ldc wider than n: columns >= n must stay untouched
+    need = _abi.query("tmf_gemm_tc_ws_bytes", m, n, k)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _abi.call("tmf_gemm_tc", ta, tb, m, n, k, _abi.ptr(At), At.shape[1], _abi.ptr(Bt), Bt.shape[1], _abi.ptr(out), out.shape[1],
+              _abi.ptr(ws), need)
+    got = cpu(out)
+    assert np.all(got[:, n:] == 7.0)
+    err = np.abs(got[:, :n] - want)
+    assert np.all(err <= 4e-7 * bound + 1e-30), f"max err/bound {np.max(err / (bound + 1e-300)):.3e}"
+    out2 = torch.full_like(out, 7.0)
+    _abi.call("tmf_gemm_tc", ta, tb, m, n, k, _abi.ptr(At), At.shape[1], _abi.ptr(Bt), Bt.shape[1], _abi.ptr(out2), out2.shape[1],
+              _abi.ptr(ws), need)
+    assert torch.equal(out, out2)  # deterministic (fixed K-split order)
+
+
+@pytest.mark.parametrize("kinds", [("relu", "linear"), ("linear", "relu")])
+def test_relu_tower_midsize_runs_its_gemms_on_the_tensor_cores(kinds):
+    """Large enough that H.W, H^T.dE and dE.W^T go through tmf_gemm_tc (>= TC_GEMM_MIN_MACS): parity like test_step_parity."""
+    _, _, _, eng, FM, SI, _ = _mods()
+    n_u, n_i, r, S = 2500, 1800, 24, 6
+    assert min(n_u, n_i) * r * 5 * r >= eng.TC_GEMM_MIN_MACS
+    for seed in range(20):
+        rng, rows, cols, vals, samp = make_problem(n_u, n_i, r, 30_000, S, 900 + seed)
+        pu = params_for(kinds[0], n_u, r, rng, 0.3)
+        pi = params_for(kinds[1], n_i, r, rng, 0.3)
+        for p in (pu, pi):
+            if "Wr" in p:  # identity features: X W_r is a row gather of the [n, 5r] table
+                p["Wr"] = (p["Wr"] * 0.4).astype(np.float32)
+        break
+    from scipy import sparse
+    Xu, Xi = sparse.identity(n_u, format="csr", dtype=np.float64), sparse.identity(n_i, format="csr", dtype=np.float64)
+    f = lambda d: {k: v.astype(np.float64) for k, v in d.items()}  # noqa: E731
+    want = o.train_step_sparse("mse", Xu, Xi, kinds[0], kinds[1], f(pu), f(pi), rows, cols, vals.astype(np.float64), samp, n_i, S, update=False)
+    m = build_model("mse", kinds, pu, pi, r, n_u, n_i, S, samp)
+    calls0 = dict(tc=0)
+    from teamoflow_b200 import _abi
+    real_call = _abi.call
+
+    def counting(name, *a):
+        calls0["tc"] += name == "tmf_gemm_tc"
+        return real_call(name, *a)
+    _abi.call = counting
+    try:
+        plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)))
+        plan.forward_backward()
+    finally:
+        _abi.call = real_call
+    assert calls0["tc"] >= 3, "the ReLU tower's contractions did not reach the tensor-core GEMM"
+    close(cpu(plan.ip.loss_vector()), want[0], name="loss")
+    for tower, g in ((plan.u, want[1]), (plan.i, want[2])):
+        for k in g:
+            got = cpu(tower.grads[k])[:, :g[k].shape[1]]
+            floor = np.abs(cpu(tower.dE)).sum(axis=0).max() if k in ("b", "br") else 0.0
+            close(got, g[k], name=f"{tower.kind}.{k}", floor=floor)
+
+
+def test_dense_features_stay_dense_and_use_the_tensor_core_gemm():
+    """A genuinely dense feature matrix (every entry non-zero) is not exploded into CSR: X.W and X^T.dE are tmf_gemm_tc calls
+    (embedding_graphs.py:38 with dense X; north_star: "a dense tcgen05/TMA GEMM only when the feature matrices are dense")."""
+    _, _, _, eng, FM, SI, _ = _mods()
+    from teamoflow_b200.mf._tensors import as_features
+    n_u, n_i, r, S, Fu, Fi = 2000, 1500, 32, 8, 96, 80
+    rng, rows, cols, vals, samp = make_problem(n_u, n_i, r, 20_000, S, 77)
+    Xu = rng.standard_normal((n_u, Fu)).astype(np.float32)
+    Xi = rng.standard_normal((n_i, Fi)).astype(np.float32)
+    assert as_features(torch.as_tensor(Xu)).dense is not None
+    sparse_like = np.where(rng.random((50, 40)) < 0.1, 1.0, 0.0).astype(np.float32)
+    assert as_features(torch.as_tensor(sparse_like)).dense is None  # a mostly-zero dense tensor still becomes CSR
+    pu = {"W": (rng.standard_normal((Fu, r)) * 0.1).astype(np.float32), "b": np.zeros((1, r), np.float32)}
+    pi = {"W": (rng.standard_normal((Fi, r)) * 0.1).astype(np.float32)}
+    want = oracle64("mse", Xu, Xi, ("biased", "linear"), pu, pi, rows, cols, vals, samp, n_i, S, 0.01)
+    m = build_model("mse", ("biased", "linear"), pu, pi, r, n_u, n_i, S, samp)
+    plan = m._prepare(torch.as_tensor(Xu), torch.as_tensor(Xi), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)))
+    assert plan.u.X.dense is not None and plan.i.X.dense is not None
+    plan.forward_backward()
+    close(cpu(plan.ip.loss_vector()), want[0], name="loss")
+    close(cpu(plan.u.grads["W"])[:, :r], want[1]["W"], name="dWu (X^T dE, dense X)")
+    close(cpu(plan.u.grads["b"])[:, :r], want[1]["b"], name="db", floor=np.abs(cpu(plan.u.dE)).sum(axis=0).max())
+    close(cpu(plan.i.grads["W"])[:, :r], want[2]["W"], name="dWi")
+    Eu, _ = o.embed_forward("biased", Xu.astype(np.float64), {k: v.astype(np.float64) for k, v in pu.items()})
+    close(cpu(plan.u.E)[:, :r], Eu, name="E_u = X W + b")
