@@ -523,7 +523,7 @@ def parity_train_sample(plan, n_us=512, n_is=16, seed=1, max_len=200_000, strict
         pop = int(torch.argmax(tl))
         items_c = np.unique(np.concatenate([rng.choice(icand, size=min(63, icand.size), replace=False), [pop]]))
         it, pos, which, cnt = entries_of(items_c)
-        coef = ip.coef[ip.t_src[pos].long()].double()
+        coef = (ip.coef[pos] if ip.coef_pos is not None else ip.coef[ip.t_src[pos].long()]).double()  # list order when the user pass scatters
         rows_e = Eu[ip.t_user[pos].long(), :r].double() * coef[:, None]
         want = torch.zeros(it.numel(), r, dtype=torch.float64, device=it.device).index_add_(0, which, rows_e).cpu().numpy()
         got = plan.i.dE[it, :r].double().cpu().numpy()

@@ -108,6 +108,9 @@ TMF_API int tmf_spmm_seg(int32_t n_seg, const int32_t* seg_ptr, int64_t n_entrie
  * (MSE loss_graphs.py:47-52 / WMRB :74-88), d(sum loss)/d(score) coefficients and dE_u.
  *   loss_out[nnz]        per-interaction loss (0 where WMRB ignores a non-positive value)
  *   coef_out[nnz + n_users*n_samples]   c_k, then G[u, j] (WMRB only)
+ *   coef_pos (optional, NULL = that natural order): coefficient slot e is stored at coef_out[coef_pos[e]] instead -- pass the
+ *   inverse of tmf_transpose_build's permutation and the item-major pass reads its coefficients in list order (tmf_spmm_seg
+ *   with cpos = NULL: coalesced) instead of gathering 4-byte values one 32-byte sector each
  *   dEu[n_users, ld]
  *   work list (optional, NULL = one item per user in natural order): n_work items (user, [a, b) slice of the
  *   user's interactions, slot); slot = -1 for whole users, otherwise the row of part_G [n_slots, ceil4(S)] /
@@ -120,13 +123,13 @@ TMF_API int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int64_
                   const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
                   const int32_t* samp, int32_t n_samples, int32_t n_work, const int32_t* work_user, const int32_t* work_a,
                   const int32_t* work_b, const int32_t* work_slot, float* part_G, float* part_E, int32_t* counter,
-                  float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream);
+                  float* loss_out, float* coef_out, const int32_t* coef_pos, float* dEu, tmf_stream_t stream);
 
 /* Sums the partial G / dE_u of split users in slice order and adds the sample term (deterministic). */
 TMF_API int tmf_user_pass_fixup(int32_t loss, int32_t n_split, const int32_t* split_user, const int32_t* split_first,
                         const int32_t* split_nseg, const float* Ei, int32_t ld, const int32_t* samp, int32_t n_samples,
-                        int64_t nnz, const float* part_G, const float* part_E, float* coef_out, float* dEu,
-                        tmf_stream_t stream);
+                        int64_t nnz, const float* part_G, const float* part_E, float* coef_out, const int32_t* coef_pos,
+                        float* dEu, tmf_stream_t stream);
 
 /* p[k] = <Eu[rows[k]], Ei[cols[k]]>  (tf.gather_nd(predictions, indices), matrix_factorization.py:154,160) */
 TMF_API int tmf_pair_dots(int64_t nnz, const int32_t* rows, const int32_t* cols, const float* Eu, const float* Ei,

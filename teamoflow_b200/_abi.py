@@ -34,8 +34,8 @@ SIGNATURES = {
     "tmf_spmm_ws_bytes": (_sz, [_i64, _i32]),
     "tmf_spmm_seg": (_i32, [_i32, _p, _i64, _p, _p, _p, _p, _i32, _p, _i32, _i32, _p, _sz, _p]),
     "tmf_user_pass": (_i32, [_i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _p,
-                             _p, _p, _p, _p]),
-    "tmf_user_pass_fixup": (_i32, [_i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p, _p]),
+                             _p, _p, _p, _p, _p]),
+    "tmf_user_pass_fixup": (_i32, [_i32, _i32, _p, _p, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p, _p, _p]),
     "tmf_pair_dots": (_i32, [_i64, _p, _p, _p, _p, _i32, _p, _p]),
     "tmf_kl_coef": (_i32, [_i64, _p, _p, _p, _p, _p, _p]),
     "tmf_kl_moments": (_i32, [_i64, _p, _p, _p, _p, _p]),

@@ -37,6 +37,8 @@ struct UserPassParams {
   int* counter;
   float* loss_out;
   float* coef_out;
+  const int* coef_pos;    // optional: coefficient slot e (c_k at k, G_uj at nnz + u S + j) is stored at coef_out[coef_pos[e]] -- the
+                          // item-major order of the list the item pass streams, so that pass reads its coefficients coalesced
   float* dEu;
   float scale;  // n_items / n_samples (python true division, loss_graphs.py:86)
 };
@@ -124,7 +126,10 @@ user_pass_kernel(const UserPassParams p) {
 
     if (a == b) {  // no interactions: all gradients of this user are zero
       if (LOSS == TMF_LOSS_WMRB)
-        for (int j = tid; j < S; j += NT) p.coef_out[p.nnz + (long long)u * S + j] = 0.f;
+        for (int j = tid; j < S; j += NT) {
+          const long long e = p.nnz + (long long)u * S + j;
+          p.coef_out[p.coef_pos ? p.coef_pos[e] : e] = 0.f;
+        }
       for (int c = tid; c < ld; c += NT) p.dEu[(long long)u * ld + c] = 0.f;
       continue;
     }
@@ -214,7 +219,7 @@ user_pass_kernel(const UserPassParams p) {
     // row group and iteration: score, S hinge terms (each lane owns JPL of them, evaluated two at a time with packed
     // fp32x2 instructions), dL/dscore, and acc += c * row while the row is still in registers.  Lane 0 of the group
     // stores (1 + m, c); the logarithm is applied by a coalesced in-place pass after the loop.
-    auto process = [&](const float4 (&row)[VPL], const float a_k, const int k) {
+    auto process = [&](const float4 (&row)[VPL], const float a_k, const int k, const int cpos_k) {
       const bool active = k < b;
       const float pk = gsum<LPR>(dotv<VPL>(eu, row));
       float c = 0.f, d = 0.f;
@@ -279,7 +284,7 @@ user_pass_kernel(const UserPassParams p) {
       for (int v = 0; v < VPL; ++v) fma4(acc[v], c, row[v]);
       if (lg == 0 && active) {
         p.loss_out[k] = d;
-        p.coef_out[k] = c;
+        p.coef_out[cpos_k] = c;
       }
     };
     // Software pipeline over PD row buffers: (item id, value) of an interaction are fetched PD iterations ahead, its row
@@ -288,19 +293,21 @@ user_pass_kernel(const UserPassParams p) {
     // warp would leave the memory system idle).  Iteration i uses buffer i % PD; the loop is unrolled PD times so the
     // buffers are addressed statically (no register copies).  Indices past the slice are clamped (a tail iteration
     // re-reads the last row and is masked by `active`).
-    auto fetch_idx = [&](int& idx, float& a_k, const int k) {
+    const int* cpos = p.coef_pos;
+    auto fetch_idx = [&](int& idx, float& a_k, int& pos, const int k) {
       const int kc = min(k, b - 1);
       idx = p.col_idx[kc];
       a_k = p.val[kc];
+      pos = cpos ? cpos[kc] : kc;
     };
     {
       const int n_it = (b - a + NG - 1) / NG;
       int k = a + g;
       float4 rows[PD][VPL];
-      int ids[PD];
+      int ids[PD], ps[PD];
       float vs[PD];
 #pragma unroll
-      for (int q = 0; q < PD; ++q) fetch_idx(ids[q], vs[q], k + q * NG);
+      for (int q = 0; q < PD; ++q) fetch_idx(ids[q], vs[q], ps[q], k + q * NG);
 #pragma unroll
       for (int q = 0; q < PD - 1; ++q) load_item<VPL>(ei_lane, ids[q], ld_bytes, rows[q]);
       for (int it = 0; it < n_it; it += PD, k += PD * NG) {
@@ -310,8 +317,9 @@ user_pass_kernel(const UserPassParams p) {
             const int qn = (q + PD - 1) % PD;                       // buffer of iteration it + q + PD - 1
             load_item<VPL>(ei_lane, ids[qn], ld_bytes, rows[qn]);
             const float v = vs[q];
-            fetch_idx(ids[q], vs[q], k + (q + PD) * NG);
-            process(rows[q], v, k + q * NG);
+            const int pk = ps[q];
+            fetch_idx(ids[q], vs[q], ps[q], k + (q + PD) * NG);
+            process(rows[q], v, k + q * NG, pk);
           }
         }
       }
@@ -331,18 +339,25 @@ user_pass_kernel(const UserPassParams p) {
           }
           if (g == 0) {
             const int j0 = lg + LPR * (2 * t), j1 = lg + LPR * (2 * t + 1);
-            float* dst = slot < 0 ? p.coef_out + p.nnz + (long long)u * S   // whole user
-                                  : p.part_G + (long long)slot * p.s_pad;   // slice: summed by the fix-up kernel
-            if (j0 < S) { dst[j0] = gj2[t].x; sS[j0] = gj2[t].x; }
-            if (j1 < S) { dst[j1] = gj2[t].y; sS[j1] = gj2[t].y; }
+            if (slot < 0) {  // whole user: final G_uj (scattered to the item-major slot when coef_pos is given)
+              const long long e0 = p.nnz + (long long)u * S;
+              if (j0 < S) { p.coef_out[cpos ? cpos[e0 + j0] : e0 + j0] = gj2[t].x; sS[j0] = gj2[t].x; }
+              if (j1 < S) { p.coef_out[cpos ? cpos[e0 + j1] : e0 + j1] = gj2[t].y; sS[j1] = gj2[t].y; }
+            } else {         // slice: partial sums, added up by the fix-up kernel
+              float* dst = p.part_G + (long long)slot * p.s_pad;
+              if (j0 < S) { dst[j0] = gj2[t].x; sS[j0] = gj2[t].x; }
+              if (j1 < S) { dst[j1] = gj2[t].y; sS[j1] = gj2[t].y; }
+            }
           }
         }
       } else {
         for (int j = tid; j < S; j += NT) {  // fixed group order => deterministic
           float G = sG[j];
           for (int gg = 1; gg < NG; ++gg) G += sG[gg * p.s_pad + j];
-          if (slot < 0) p.coef_out[p.nnz + (long long)u * S + j] = G;
-          else p.part_G[(long long)slot * p.s_pad + j] = G;
+          if (slot < 0) {
+            const long long e = p.nnz + (long long)u * S + j;
+            p.coef_out[cpos ? cpos[e] : e] = G;
+          } else p.part_G[(long long)slot * p.s_pad + j] = G;
           sS[j] = G;
         }
       }
@@ -411,7 +426,8 @@ __global__ void __launch_bounds__(256) user_fixup_kernel(const UserPassParams p,
       for (int j = tid; j < S; j += 256) {
         float G = 0.f;
         for (int sg = 0; sg < nseg; ++sg) G += p.part_G[(long long)(first + sg) * p.s_pad + j];
-        p.coef_out[p.nnz + (long long)u * S + j] = G;
+        const long long e = p.nnz + (long long)u * S + j;
+        p.coef_out[p.coef_pos ? p.coef_pos[e] : e] = G;
         sG[j] = G;
       }
     }
@@ -953,7 +969,8 @@ extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int
                              const float* val, const float* Eu, const float* Ei, int32_t ld, int32_t n_comp,
                              const int32_t* samp, int32_t n_samples, int32_t n_work, const int32_t* work_user,
                              const int32_t* work_a, const int32_t* work_b, const int32_t* work_slot, float* part_G,
-                             float* part_E, int32_t* counter, float* loss_out, float* coef_out, float* dEu, tmf_stream_t stream) {
+                             float* part_E, int32_t* counter, float* loss_out, float* coef_out, const int32_t* coef_pos, float* dEu,
+                             tmf_stream_t stream) {
   TMF_REQUIRE(loss == TMF_LOSS_MSE || loss == TMF_LOSS_WMRB, "tmf_user_pass: unknown loss %d", loss);
   TMF_REQUIRE(n_users >= 0 && n_items > 0 && ld > 0 && ld % 4 == 0 && n_comp <= ld, "tmf_user_pass: bad shape");
   TMF_REQUIRE(ld <= 256, "tmf_user_pass: n_components up to 256 supported (ld=%d)", ld);
@@ -969,7 +986,7 @@ extern "C" int tmf_user_pass(int32_t loss, int32_t n_users, int32_t n_items, int
   p.work_user = work_user; p.work_a = work_a; p.work_b = work_b; p.work_slot = work_slot; p.part_G = part_G; p.part_E = part_E;
   p.n_work = work_user ? n_work : n_users;
   TMF_REQUIRE(!work_user || (work_a && work_b && work_slot), "tmf_user_pass: incomplete work list");
-  p.counter = counter; p.loss_out = loss_out; p.coef_out = coef_out; p.dEu = dEu;
+  p.counter = counter; p.loss_out = loss_out; p.coef_out = coef_out; p.coef_pos = coef_pos; p.dEu = dEu;
   p.scale = loss == TMF_LOSS_WMRB ? (float)((double)n_items / (double)n_samples) : 0.f;
   cudaStream_t st = as_stream(stream);
   p.nnz = nnz;  // the G block of coef_out starts at nnz
@@ -1174,14 +1191,14 @@ extern "C" int tmf_wmrb_forward(int64_t n_pos, const int32_t* pos_rows, const fl
 
 extern "C" int tmf_user_pass_fixup(int32_t loss, int32_t n_split, const int32_t* split_user, const int32_t* split_first,
                                    const int32_t* split_nseg, const float* Ei, int32_t ld, const int32_t* samp, int32_t n_samples,
-                                   int64_t nnz, const float* part_G, const float* part_E, float* coef_out, float* dEu,
-                                   tmf_stream_t stream) {
+                                   int64_t nnz, const float* part_G, const float* part_E, float* coef_out, const int32_t* coef_pos,
+                                   float* dEu, tmf_stream_t stream) {
   if (n_split == 0) return TMF_OK;
   TMF_REQUIRE(split_user && split_first && split_nseg && part_E && dEu, "tmf_user_pass_fixup: null pointer");
   UserPassParams p{};
   p.ld = ld; p.n_samples = loss == TMF_LOSS_WMRB ? n_samples : 0; p.s_pad = (p.n_samples + 3) & ~3; p.nnz = nnz;
   p.Ei = Ei; p.samp = samp; p.part_G = const_cast<float*>(part_G); p.part_E = const_cast<float*>(part_E);
-  p.coef_out = coef_out; p.dEu = dEu;
+  p.coef_out = coef_out; p.coef_pos = coef_pos; p.dEu = dEu;
   const size_t smem = (size_t)(p.s_pad + ld + 1024) * sizeof(float);  // (256 / nvp) partial rows of ld floats <= 1024 floats
   TMF_REQUIRE(smem <= 48 * 1024 && ld <= 256, "tmf_user_pass_fixup: n_samples too large");
   user_fixup_kernel<<<std::min(n_split, 148 * 4), 256, smem, as_stream(stream)>>>(p, loss, n_split, split_user, split_first, split_nseg);

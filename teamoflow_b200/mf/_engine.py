@@ -262,6 +262,15 @@ class InteractionPlan:
             keys = torch.cat([self.col_idx, self.samp.reshape(-1)])
         self.T = int(keys.numel())
         self.t_ptr, self.t_src = build_transpose(keys, self.n_items)
+        # Coefficients in item-major order: when the gathered table E_u fits the L2 (the item pass is then bound by the latency of
+        # its 4-byte coefficient gathers, one 32-byte DRAM sector each) the user pass stores c_k / G_uj straight into the slot the
+        # item pass will read (coef_pos = inverse of the transpose permutation) and the item pass streams them.  On HBM-bound
+        # problems (E_u far larger than L2) the scattered partial-sector writes cost more DRAM traffic than the gathers: keep the
+        # natural order there.
+        self.coef_pos = None
+        if self.loss in (MSE, WMRB) and self.DIRECT_COEF and self.n_users * 4 * 64 <= self.DIRECT_COEF_MAX_TABLE_BYTES and self.T:
+            self.coef_pos = torch.empty(self.T, dtype=torch.int32, device=dev)
+            self.coef_pos[self.t_src.long()] = torch.arange(self.T, dtype=torch.int32, device=dev)
         if self.t_user is None or self.t_user.numel() < max(self.T, 1):
             self.t_user = torch.empty(max(self.T, 1), dtype=torch.int32, device=dev)
         _abi.call("tmf_tlist_users", _abi.ptr(self.t_src), self.T, self.nnz, _abi.ptr(self.coo_rows), max(self.S, 1),
@@ -270,6 +279,8 @@ class InteractionPlan:
     # users with more interactions than the slice length are processed as several slices (load balance: tmf_user_pass gives
     # a work item to ONE warp).  1024 on large problems; shorter -- down to 32 -- when the whole problem would otherwise
     # not fill the machine's ~9.5k resident warp slots (a 943-user problem's heaviest user must not be one warp's tail).
+    DIRECT_COEF = os.environ.get("TMF_DIRECT_COEF", "1") != "0"   # development switch (A/B of the two coefficient layouts)
+    DIRECT_COEF_MAX_TABLE_BYTES = 64 << 20                        # n_users x 256 B (a rank-64 row) must fit comfortably in the 126 MB L2
     SPLIT = 1024
     SPLIT_MIN = 32
     TARGET_ITEMS = 148 * 32 * 2
@@ -318,11 +329,12 @@ class InteractionPlan:
                       _abi.ptr(self.row_ptr), _abi.ptr(self.col_idx), _abi.ptr(self.vals), _abi.ptr(Eu), _abi.ptr(Ei),
                       Eu.shape[1], r, _abi.ptr(self.samp), self.S, self.n_work, _abi.ptr(self.w_user), _abi.ptr(self.w_a),
                       _abi.ptr(self.w_b), _abi.ptr(self.w_slot), _abi.ptr(self.part_G), _abi.ptr(self.part_E),
-                      _abi.ptr(self.counter), _abi.ptr(self.loss_k), _abi.ptr(self.coef), _abi.ptr(dEu))
+                      _abi.ptr(self.counter), _abi.ptr(self.loss_k), _abi.ptr(self.coef), _abi.ptr(self.coef_pos), _abi.ptr(dEu))
             if self.n_split:
                 _abi.call("tmf_user_pass_fixup", _LOSS_CODE[self.loss], self.n_split, _abi.ptr(self.split_user),
                           _abi.ptr(self.split_first), _abi.ptr(self.split_nseg), _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.samp),
-                          self.S, self.nnz, _abi.ptr(self.part_G), _abi.ptr(self.part_E), _abi.ptr(self.coef), _abi.ptr(dEu))
+                          self.S, self.nnz, _abi.ptr(self.part_G), _abi.ptr(self.part_E), _abi.ptr(self.coef), _abi.ptr(self.coef_pos),
+                          _abi.ptr(dEu))
         else:
             _abi.call("tmf_pair_dots", self.nnz, _abi.ptr(self.coo_rows), _abi.ptr(self.col_idx), _abi.ptr(Eu),
                       _abi.ptr(Ei), Eu.shape[1], _abi.ptr(self.p))
@@ -349,7 +361,8 @@ class InteractionPlan:
     def item_pass(self, Eu, r, dEi):
         """dE_i[i] = sum over the item-major list of coef * E_u[user]  (deterministic)."""
         ws = self._spmm_ws(dEi.shape[1])
-        spmm(self.n_items, self.t_ptr, self.T, self.t_user, self.t_src, self.coef, Eu, r, out=dEi, ws=ws)
+        cpos = None if self.coef_pos is not None else self.t_src  # coefficients already in list order: streamed, not gathered
+        spmm(self.n_items, self.t_ptr, self.T, self.t_user, cpos, self.coef, Eu, r, out=dEi, ws=ws)
 
     # -- loss reporting (matrix_factorization.py:165-167, :179)
     def loss_vector(self):

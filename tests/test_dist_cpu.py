@@ -101,6 +101,58 @@ def test_user_sharded_training_allreduce():
     _spawn(_dp_training)
 
 
+class _FakePlan:
+    """What GradientSync.sync_grads touches of a TrainPlan: the item tower's dE and the user tower's grads."""
+
+    def __init__(self, u, i):
+        self.u, self.i = u, i
+
+
+def _sync_grads_and_kl(rank, world):
+    # ---- one call exchanges the item gradient AND the shared user-side slices (NCCL/gloo form: no peer arena on CPU)
+    class IT:
+        kind = "linear"
+    it = IT()
+    it.dE = torch.full((6, 4), float(rank + 1))
+    g = {"W": torch.full((7, 4), float(rank + 1)), "b": torch.full((1, 4), float(10 * (rank + 1)))}
+    u = _FakeTower("biased", g, {"W": torch.zeros(7, 4), "b": torch.zeros(1, 4)})
+    comm = tdist.GradientSync(shared_user_rows=5)
+    assert comm.peer is False  # no CUDA here: the collective path
+    fused = comm.sync_grads(_FakePlan(u, it), lr=0.1)
+    assert fused is False
+    assert torch.all(it.dE == 3.0)
+    assert torch.all(g["W"][:5] == rank + 1) and torch.all(g["W"][5:] == 3.0) and torch.all(g["b"] == 30.0)
+    # ---- KL under user sharding: the six additive moments of the rank's interactions, summed, give the global statistics
+    rng = np.random.default_rng(5)
+    p = rng.standard_normal(400) * 0.3 + 0.1
+    vals = rng.choice([-1.0, 1.0, 2.0], 400)
+    mine = slice(0, 150) if rank == 0 else slice(150, 400)
+
+    def moments(pp, vv):
+        pos = vv > 0
+        return np.array([pos.sum(), pp[pos].sum(), (pp[pos] ** 2).sum(), (~pos).sum(), pp[~pos].sum(), (pp[~pos] ** 2).sum()])
+    m = torch.from_numpy(moments(p[mine], vals[mine]))
+    comm.allreduce_kl_moments(m)
+    np.testing.assert_allclose(m.numpy(), moments(p, vals), rtol=1e-13)
+    n_p, s_p, q_p, n_n, s_n, q_n = m.numpy()
+    mp, mn = s_p / n_p, s_n / n_n
+    vp, vn = q_p / n_p - mp ** 2, q_n / n_n - mn ** 2
+    from scipy import special
+    loss = 1.0 - special.ndtr((mp - mn) / np.sqrt(vp + vn))
+    np.testing.assert_allclose(loss, float(o.kl_loss(p, vals)), rtol=1e-10)  # == the single-process KL of all interactions
+
+    class KLPlan:
+        loss = "kl"
+
+        def mean_loss(self):
+            return 0.25
+    assert comm.mean_loss(KLPlan()) == 0.25  # already global: no second reduction
+
+
+def test_sync_grads_collective_form_and_kl_moments():
+    _spawn(_sync_grads_and_kl)
+
+
 def _sharded_topk(rank, world):
     rng = np.random.default_rng(9)
     n_u, n_i, r, k = 25, 90, 8, 7

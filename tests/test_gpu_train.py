@@ -674,3 +674,39 @@ def test_dense_features_stay_dense_and_use_the_tensor_core_gemm():
     close(cpu(plan.i.grads["W"])[:, :r], want[2]["W"], name="dWi")
     Eu, _ = o.embed_forward("biased", Xu.astype(np.float64), {k: v.astype(np.float64) for k, v in pu.items()})
     close(cpu(plan.u.E)[:, :r], Eu, name="E_u = X W + b")
+
+
+def test_item_major_coefficient_layout_is_bitwise_the_gather_layout():
+    """The user pass may store c_k / G_uj straight into the item-major slots (coef_pos) so that the item pass streams them;
+    the sums run over the same values in the same order, so every gradient is bit-identical to the gather layout --
+    including split (heavy) users, whose G is finished by the fix-up kernel, and users without interactions."""
+    _, _, _, eng, FM, SI, _ = _mods()
+    n_u, n_i, r, S = 700, 900, 16, 24
+    rng = np.random.default_rng(4)
+    lens = np.minimum((3000.0 / np.arange(1, n_u + 1)).astype(np.int64), n_i)
+    lens[5] = 0
+    rows = np.repeat(np.arange(n_u), lens)
+    cols = np.concatenate([np.sort(rng.choice(n_i, l, replace=False)) for l in lens])
+    vals = rng.choice(np.array([1.0, 2.0, -1.0], np.float32), rows.size)
+    samp = np.stack([rng.choice(n_i, S, replace=False) for _ in range(n_u)]).astype(np.int64)
+    pu = {"W": (rng.standard_normal((n_u, r)) * 0.3).astype(np.float32)}
+    pi = {"W": (rng.standard_normal((n_i, r)) * 0.3).astype(np.float32)}
+    res = {}
+    keep = eng.InteractionPlan.DIRECT_COEF, eng.InteractionPlan.SPLIT
+    try:
+        eng.InteractionPlan.SPLIT = 128  # the heaviest users (up to 900 interactions) are processed as slices
+        for loss in ("wmrb", "mse"):
+            for direct in (True, False):
+                eng.InteractionPlan.DIRECT_COEF = direct
+                m = build_model(loss, ("linear", "linear"), pu, pi, r, n_u, n_i, S, samp)
+                plan = m._prepare(FM.eye(n_u), FM.eye(n_i), SI(np.stack([rows, cols], 1), vals, (n_u, n_i)))
+                assert (plan.ip.coef_pos is not None) == direct and plan.ip.n_split > 0
+                plan.forward_backward()
+                res[(loss, direct)] = (plan.u.dE.clone(), plan.i.dE.clone(), plan.ip.loss_k.clone())
+            for a, b in zip(res[(loss, True)], res[(loss, False)]):
+                assert torch.equal(a, b), loss
+    finally:
+        eng.InteractionPlan.DIRECT_COEF, eng.InteractionPlan.SPLIT = keep
+    want = oracle64("wmrb", np.eye(n_u, dtype=np.float32), np.eye(n_i, dtype=np.float32), ("linear", "linear"), pu, pi, rows, cols, vals,
+                    samp, n_i, S, 0.1)
+    close(cpu(res[("wmrb", True)][1])[:, :r], want[2]["W"], name="dE_i (item-major coefficients)")
