@@ -8,10 +8,18 @@
 //     A.B^T  ~  A1.B1 + A1.B2 + A2.B1 + A1.B3 + A3.B1 + A2.B2          (dropped terms <= 3 * 2^-24 |a||b|)
 // i.e. fp32-level accuracy at 1/6 of the bf16 tensor rate -- still several times the SIMT fp32 rate of gemm_f32_kernel.
 //
+// The tensor core's own fp32 accumulation is NOT round-to-nearest: measured on B200, a chain of n accumulating MMAs leaves an
+// error that grows ~linearly with n (4-6e-7 sum|a||b| after the 24 MMAs of one 64-wide k-block, 2.6e-6 after 384, 5e-6 after
+// 768) where IEEE fp32 adds would leave ~1e-7.  So a chain never runs longer than ONE k-block: every k-block is computed
+// into a fresh TMEM accumulator (two of them, double-buffered) and the epilogue warps add it to fp32 register accumulators
+// with ordinary round-to-nearest adds ("promotion", as FP8 GEMMs do) -- the error then stays at the one-block level however
+// large K is.
+//
 //   split3_pack_kernel : fp32 [R, C] (row-major, optional transpose) -> three K-major bf16 planes [3][rows_pad][k_pad]
 //   gemm_tc_kernel     : one 128 x BN output tile per CTA and K split; warp 0 = TMA producer (3 A + 3 B sub-tiles per
 //                        64-wide k-block, 128-byte swizzle), warp 1 = single-thread tcgen05.mma issuer (24 MMAs per k-block),
-//                        warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> global, row per thread)
+//                        warp 2 = TMEM allocator, warps 4-7 = promotion + epilogue (tcgen05.ld of each k-block's tile -> fp32
+//                        register accumulators, row per thread -> global)
 //   splitk_reduce_kernel: fixed-order sum of the K-split partial tiles (deterministic)
 #include <cuda_bf16.h>
 
@@ -86,12 +94,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * STAGE);
   uint64_t* full_bar = bars;        // [nstages <= 4]
   uint64_t* empty_bar = bars + 4;   // [4]
-  uint64_t* tfull = bars + 8;       // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* tfull = bars + 8;       // [2]
+  uint64_t* tempty = bars + 10;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.z * p.kb_per;
   const int kb1 = min(kb0 + p.kb_per, p.kb_total);
-  const int n_kb = kb1 - kb0;  // >= 1 by construction of the grid
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -99,11 +107,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
-    mbar_init(smem_u32(tfull), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+  if (warp == 2) {  // two BN-column accumulators, double-buffered against the promotion
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -130,15 +138,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer
+    if (lane == 0) {  // ---- MMA issuer: one k-block = one fresh accumulator
       constexpr uint32_t idesc = umma_idesc_bf16(GT_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
+        const int it = kb - kb0, acc = it & 1;
+        mbar_wait(smem_u32(&tempty[acc]), ((uint32_t)(it >> 1) & 1u) ^ 1u);  // the promotion drained this accumulator's previous block
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tcgen05_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)stage * STAGE);
         const uint32_t b_base = a_base + 3 * GT_A_SUB;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         // smallest terms first: (A2,B2) (A1,B3) (A3,B1) (A1,B2) (A2,B1) (A1,B1)
         const int ia[6] = {1, 0, 2, 0, 1, 0};
         const int ib[6] = {1, 2, 0, 1, 0, 0};
@@ -146,41 +157,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         for (int c = 0; c < 6; ++c) {
 #pragma unroll
           for (int k = 0; k < GT_BK / 16; ++k) {
-            tcgen05_mma_f16(tmem_base, umma_desc_sw128(a_base + ia[c] * GT_A_SUB + k * 32), umma_desc_sw128(b_base + ib[c] * B_SUB + k * 32),
-                            idesc, (uint32_t)((kb != kb0) || c != 0 || k != 0));
+            tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_base + ia[c] * GT_A_SUB + k * 32), umma_desc_sw128(b_base + ib[c] * B_SUB + k * 32),
+                            idesc, (uint32_t)(c != 0 || k != 0));
           }
         }
         tcgen05_commit(smem_u32(&empty_bar[stage]));
+        tcgen05_commit(smem_u32(&tfull[acc]));
         if (++stage == p.nstages) { stage = 0; phase ^= 1; }
       }
-      tcgen05_commit(smem_u32(tfull));
     }
   } else if (warp >= 4) {
-    // ---- epilogue: thread = output row (TMEM lane), 32 columns per load
+    // ---- promotion + epilogue: thread = output row (TMEM lane); fp32 register accumulators, IEEE round-to-nearest adds
     const int q = warp & 3;
-    mbar_wait(smem_u32(tfull), 0);
-    __syncwarp();
-    tcgen05_fence_after();
-    const long long row = m0 + q * 32 + lane;
-    float* out = p.C + (p.splits > 1 ? (long long)blockIdx.z * p.M * p.N : 0) + row * (p.splits > 1 ? p.N : p.ldc);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait_for(v);
-      if (row < p.M) {
+    float accr[BN];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const long long col = n0 + c0 + j;
-          if (col < p.N) out[col] = __uint_as_float(v[j]);
-        }
+    for (int j = 0; j < BN; ++j) accr[j] = 0.f;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      const int it = kb - kb0, acc = it & 1;
+      mbar_wait(smem_u32(&tfull[acc]), (uint32_t)(it >> 1) & 1u);
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_base + (uint32_t)c0, v);
+        tmem_ld_wait_for(v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) accr[c0 + j] = __fadd_rn(accr[c0 + j], __uint_as_float(v[j]));
+      }
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&tempty[acc]));
+    }
+    const long long row = m0 + q * 32 + lane;
+    if (row < p.M) {
+      float* out = p.C + (p.splits > 1 ? (long long)blockIdx.z * p.M * p.N : 0) + row * (p.splits > 1 ? p.N : p.ldc);
+#pragma unroll
+      for (int j = 0; j < BN; ++j) {
+        const long long col = n0 + j;
+        if (col < p.N) out[col] = accr[j];
       }
     }
-    tcgen05_fence_before();
   }
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
-  (void)n_kb;
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long M, long long N, float* __restrict__ C, long long ldc) {
@@ -205,14 +225,10 @@ static GemmTcPlan gemm_tc_plan(long long m, long long n, long long k) {
   P.k_pad = cdiv(k, GT_BK) * GT_BK;
   P.kb_total = (int)(P.k_pad / GT_BK);
   const long long tiles = (P.m_pad / GT_BM) * (P.n_pad / P.bn);
-  // K splits: (1) fill the 148 SMs when there are few output tiles (e.g. H^T dE: 3 tiles, K = n_users), at least 4 k-blocks
-  // each; (2) bound the length of one fp32 accumulation chain inside the tensor core to 32 k-blocks (2048 products per
-  // plane pair) -- the partial tiles are then added by splitk_reduce_kernel with IEEE round-to-nearest fp32 adds -- unless
-  // the partial buffer would exceed 1 GB
+  // K splits: fill the 148 SMs when there are few output tiles (e.g. H^T dE: 3 tiles, K = n_users), at least 4 k-blocks each;
+  // the partial tiles are added by splitk_reduce_kernel in split order (deterministic)
   long long splits = 1;
   if (tiles < kNumSMs) splits = std::min<long long>(cdiv(kNumSMs, tiles), std::max<long long>(1, P.kb_total / 4));
-  const long long chain_splits = cdiv(P.kb_total, 32);
-  if (chain_splits > splits && (double)chain_splits * (double)m * (double)n * 4.0 <= 1.0e9) splits = chain_splits;
   P.kb_per = (int)cdiv(P.kb_total, splits);
   P.splits = (int)cdiv(P.kb_total, P.kb_per);
   const int stage = 3 * GT_A_SUB + 3 * P.bn * GT_BK * 2;

@@ -35,16 +35,16 @@ constexpr int MAX_STAGES = 8;  // B-operand ring (16 KB stages); the launch uses
 // the sub-partitions' issue slots were 60 % idle and the tensor pipe waited for accumulators (46 % active).
 constexpr int NACC = 4;
 constexpr int TMEM_COLS = NACC * BN;
-// A row's candidates are kept per group ("virtual rows": group g sees every fourth tile of the row): CAPG slots each,
-// appended; the groups exchange their running thresholds through shared memory (any group's threshold is a valid
-// keep-threshold for the whole row), so together they append about what one list per row would.
+// A row's candidates are appended per group (group g sees every fourth tile of the row): CAPG slots each.  The running
+// threshold is per ROW: one score histogram per row in shared memory, fed by all four groups (red.shared), from which any
+// group derives "the highest bin edge with >= k entries at or above it" -- a lower bound of the row's k-th best score so far.
+// (A first version kept a private histogram per group: each group then tracks the k-th best of ITS quarter of the items,
+// roughly the 4k-th best overall, 3.4x the survivors and 525 ms where the two-CTA kernel took 322.)
 constexpr int CAPG = 1024;
 constexpr int CAP = NACC * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
-constexpr int INIT_N = 512;    // a virtual row's threshold state is initialised from its first <= INIT_N entries
-constexpr int CPL = INIT_N / 32;  // entries per lane in the warp-cooperative initial selection
-constexpr int NBINS = 48;      // per-row score histogram bins (16-bit counts, two per word)
-constexpr int QCAP = 16;       // per-row survivor queue slots in shared memory (drained warp-wide)
-constexpr int HSTRIDE = NBINS / 2 + 1;  // words per row, padded against bank conflicts
+constexpr int NBINS = 48;      // per-row score histogram bins (32-bit counts)
+constexpr int QCAP = 16;       // per-(row, group) survivor queue slots in shared memory (drained warp-wide)
+constexpr int HSTRIDE = NBINS + 1;  // words per row: odd, so the lanes' rows fall into different banks
 constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
 constexpr int TOPK_THREADS = 128 + NACC * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
@@ -109,30 +109,30 @@ __device__ __forceinline__ float keep_threshold(float kth, float E, int clamp) {
   return clamp ? fmaxf(kth - E, 0.f) - E : kth - 2.f * E;
 }
 
-// ---- per-row running threshold: a lane-private 48-bin histogram of the appended scores (16-bit counts, two
-// bins per shared-memory word).  bthr = the highest bin whose "at or above" count A is still >= k, so the lower
-// edge of bin bthr is a valid lower bound of the k-th largest score seen so far; it only ever rises.
+// ---- per-row running threshold: a 48-bin histogram of the appended scores per ROW in shared memory (32-bit counts),
+// shared by the row's four epilogue groups and double-buffered by user-block parity.  "The highest bin whose at-or-above
+// count is >= k" gives a lower bound of the k-th largest score seen so far: a scan that races with other groups'
+// increments can only UNDER-count, so every threshold it yields is valid; the published threshold (ordered uint32 key,
+// red.shared.max) only rises.  The bin range is set once per row from the row's first tile: [mean, mean + 2.5 (max - mean)).
 //
 // ---- SIMD list maintenance.  A lane that finds a survivor only pushes (score, item) onto its own small
 // shared-memory queue (3 instructions, no dependent loads).  When a queue is about to fill, the WHOLE warp
-// drains: iteration s handles entry s of every lane at once, each lane appending to its own row's list and
-// updating its own histogram -- the ~40-instruction append runs once per queue slot for 32 rows instead of
+// drains: iteration s handles entry s of every lane at once, each lane appending to its own (row, group) list and
+// counting the entry in its row's histogram -- the append code runs once per queue slot for 32 rows instead of
 // once per survivor with 1-3 active lanes (measured: 400-600 cycles per survivor in the divergent versions).
 struct RowState {
-  float thr;      // current keep-threshold (+inf for padded rows)
+  float thr;      // current keep-threshold (+inf for padded rows and for lists handed to the exact path)
   float thr_ext;  // externally supplied floor of the threshold (-inf when there is none)
   float lo, w, inv_w, E;
   int cnt;        // list length; > CAPG = saturated (-> exact path)
   int cq;         // entries waiting in the lane's queue
-  int bthr, A;    // threshold bin and # entries with bin >= bthr
 };
 
-__device__ __forceinline__ int hist_get(const uint32_t* hrow, int b) { return (int)((hrow[b >> 1] >> ((b & 1) * 16)) & 0xffffu); }
 // explicit shared-space accesses: through generic pointers these compile to the slower ST.E/LD.E with 64-bit addressing
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ int hist_get_s(uint32_t hrow, int b) { return (int)((lds_u32(hrow + 4u * (uint32_t)(b >> 1)) >> ((b & 1) * 16)) & 0xffffu); }
 
 __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, float E, int clamp) {
   const float edge = lo + (float)bthr * w;
@@ -140,13 +140,25 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
   return keep_threshold(edge - slack, E, clamp);
 }
 
-// warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane).  Iterations are
-// independent of each other -- fire-and-forget histogram increments (red.shared), list stores that nobody waits
-// for, threshold fixed for the duration -- so they pipeline; the threshold advances once at the end.
-struct DrainRet { float thr; int cnt, bthr, A; };
+// all lanes, each for its own row: highest bin with >= k entries at or above it (-1 when the row has fewer than k binned
+// entries).  Walks down from the top bin; the warp stops when every lane has its answer.
+__device__ __forceinline__ int hist_threshold_bin(uint32_t hrow, int k) {
+  int cum = 0, found = -1;
+  for (int b = NBINS - 1; b >= 0; --b) {
+    cum += (int)lds_u32_volatile(hrow + 4u * (uint32_t)b);
+    if (found < 0 && cum >= k) found = b;
+    if ((b & 7) == 0 && __all_sync(0xffffffffu, found >= 0)) break;
+  }
+  return found;
+}
+
+// warp-wide drain of the per-lane queues (all lanes must call; cq may differ per lane): appends the queued survivors that
+// still pass the row's threshold to the lane's list and counts them in the row's histogram (fire-and-forget red.shared),
+// then re-derives the row's threshold from the histogram and publishes it.  Returns the new list length.
 // (out of line, state by value in registers: inlining it at every call site costs registers in the tile loop)
-__device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float lo, float w, float inv_w, float E, int cnt, int cq, int bthr, int A,
-                                                 uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
+struct DrainRet { float thr; int cnt; };
+__device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float lo, float w, float inv_w, float E, int cnt, int cq,
+                                                 uint32_t queue, float2* buf, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
   int maxq = cq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
@@ -162,61 +174,38 @@ __device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float
         "setp.ne.s32 p, %0, 0;\n\t"
         "setp.ne.s32 q, %1, 0;\n\t"
         "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
-        "@q red.shared.add.u32 [%5], %6;\n\t"
-        "@q red.shared.max.u32 [%7], %8;\n\t}"
-        ::"r"(st_ok), "r"((int)okh), "l"(buf + cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)(b >> 1)),
-          "r"(1u << ((b & 1) * 16)), "r"(hrow + 4u * (uint32_t)(NBINS / 2)), "r"(f2key(e.x))
+        "@q red.shared.add.u32 [%5], 1;\n\t}"
+        ::"r"(st_ok), "r"((int)okh), "l"(buf + cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)b)
         : "memory");
     cnt += ok ? 1 : 0;
-    A += (okh && b >= bthr) ? 1 : 0;
   }
   __syncwarp();
-  bool moved = false;
-  while (bthr < NBINS - 1) {
-    const int hb = hist_get_s(hrow, bthr);
-    if (A - hb < k) break;
-    A -= hb;
-    ++bthr;
-    moved = true;
+  if (maxq > 0) {  // warp-uniform: something may have been counted (queues only fill once the row state is live: lo is finite)
+    const int bthr = hist_threshold_bin(hrow, k);
+    if (bthr >= 0) {
+      const float t = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
+      if (t > thr && thr < INFINITY) {
+        thr = t;
+        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
+      }
+    }
   }
-  if (moved) thr = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
   DrainRet r;
-  r.thr = thr; r.cnt = cnt; r.bthr = bthr; r.A = A;
+  r.thr = thr; r.cnt = cnt;
   return r;
 }
-__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
-  const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, st.bthr, st.A, queue, buf, hrow, k, clamp);
-  st.thr = r.thr; st.cnt = r.cnt; st.bthr = r.bthr; st.A = r.A;
+__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
+  const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, queue, buf, hrow, thr_slot, k, clamp);
+  st.thr = r.thr; st.cnt = r.cnt;
   st.cq = 0;
 }
 
-// One 32-column slice of a row's accumulator BEFORE the row's threshold exists (first 3 tiles): every column is
-// appended directly.  (Clamp-mode "filler" items -- the k <= 128 lowest ids -- therefore need no special case.)
-template <bool DUMP>
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int n_items, bool tail_tile, bool valid, bool warp_inited,
-                                               RowState& st, uint32_t queue, float2* buf, uint32_t hrow, long long row,
-                                               const TopkParams& p) {
-  if (DUMP) {
-    if (valid) {
+// dense-score dump of one 32-column slice (bring-up / error-bound tests and tmf_score_dense_*)
+__device__ __forceinline__ void dump_chunk(const uint32_t (&r)[32], int col0, int n_items, bool valid, long long row, const TopkParams& p) {
+  if (valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
-    }
-    return;
-  }
-  if (TMF_DBG(p) == 2 || TMF_DBG(p) == 3) return;
-  const int id0 = p.item_offset + col0;
-  if (!warp_inited) {  // warp-uniform: no threshold yet, keep everything (coalesced per lane, no queue)
-    if (valid) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (col0 + j < n_items) {
-          __stcg(buf + st.cnt, make_float2(__uint_as_float(r[j]), __int_as_float(id0 + j)));
-          ++st.cnt;
-        }
-      }
-    }
-    return;
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
   }
 }
 
@@ -239,7 +228,7 @@ __device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[16], float th
 // 8-column groups in which ANY row of the warp has a survivor (about 3 of 16 per tile at 1M items); only those are re-read
 // from TMEM (x8) and their survivors queued with predicated stores, all lanes convergent.
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
-                                              const TopkParams& p) {
+                                              uint32_t thr_slot, const TopkParams& p) {
   uint32_t ra[16], rb[16];
   const float thr = st.thr;  // invalid rows carry thr = +inf; NaN-padded columns never win a max or a compare
   unsigned hm;
@@ -276,7 +265,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowStat
     gmask &= gmask - 1;
     uint32_t v[8];
     tmem_ld8(t_base + (uint32_t)(8 * g), v);
-    if (__any_sync(0xffffffffu, st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+    if (__any_sync(0xffffffffu, st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
     tmem_ld_wait_for8(v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -353,27 +342,13 @@ __device__ __noinline__ float warp_select_kth(const float2* buf, int n, int k, i
   return key2f(prefix);
 }
 
-// Warp-cooperative (re)build of one row's threshold state from its list of n (<= CAPG) entries, streamed from L2:
-// exact k-th largest by radix select, histogram re-centred on [kth, kth + 4 (max - kth)), list compacted in place
-// against the new threshold (clamp mode also keeps the k lowest item ids).  Used once when a row has seen its first
-// 3 tiles and again whenever its list is about to saturate, so a badly placed histogram range heals itself.
-// Results in out[0..5] (shared memory): lo, w, inv_w, bthr, A, n_new.
-__device__ __noinline__ void warp_rebuild_row(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
-                                              int* radix, float* out) {
+// Warp-cooperative compaction of one (row, group) list that is about to fill: entries below the row's current threshold
+// (they can no longer be in the answer) are dropped in place, in ONE streaming pass (clamp mode also keeps the k lowest item
+// ids: the zero-score fillers).  The histogram is not touched: dropped entries sit below the threshold bin, which the
+// threshold scan never reaches again.  Returns the new length (all lanes).
+__device__ __noinline__ int warp_compact_row(float2* buf, int n, float thr, int k, int clamp, int item_offset) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  float mx;
-  const float kth = warp_select_kth(buf, n, k, radix, mx);
-  float W = 4.0f * (mx - kth);
-  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(kth), 1.0f) * 1e-3f;
-  const float lo = kth;
-  const float w = W / (float)NBINS;
-  const float inv_w = (float)NBINS / W;
-  const float thr = keep_threshold(kth, E, clamp);  // exact k-th: the tightest valid threshold
-  // ---- compact in place against thr and rebuild the histogram from the kept entries >= lo
-  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
-  __syncwarp();
-  if (lane == 0) hrow[NBINS / 2] = f2key(mx);
   int base = 0;
   for (int b0 = 0; b0 < n; b0 += 32 * 8) {
     float2 x[8];
@@ -388,229 +363,20 @@ __device__ __noinline__ void warp_rebuild_row(float2* buf, int n, int k, int cla
       const int e = b0 + 32 * t + lane;
       const bool keep = e < n && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        __stcg(buf + base + __popc(bal & lt), x[t]);
-        if (x[t].x >= lo) {
-          const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
-          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
-        }
-      }
+      if (keep) __stcg(buf + base + __popc(bal & lt), x[t]);
       base += __popc(bal);
     }
     __syncwarp();
   }
-  if (lane == 0) {
-    // highest bin with at least k entries at or above it (bin 0 qualifies: >= k entries are >= kth)
-    int A = 0, bthr = 0;
-    for (int b = NBINS - 1; b >= 0; --b) {
-      A += hist_get(hrow, b);
-      if (A >= k) { bthr = b; break; }
-    }
-    out[0] = lo; out[1] = w; out[2] = inv_w; out[3] = __int_as_float(bthr); out[4] = __int_as_float(A);
-    out[5] = __int_as_float(base);
-  }
-  __syncwarp();
-}
-
-// all lanes: highest bin with at least k entries at or above it (bin 0 qualifies whenever >= k entries are >= lo).
-// Lane L owns histogram word L (bins 2L, 2L+1); a suffix scan over the lanes replaces a 48-step serial walk.
-__device__ __forceinline__ void finish_rebuild(const uint32_t* hrow, int k, float lo, float w, float inv_w, int n_new, float* out) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t word = lane < NBINS / 2 ? hrow[lane] : 0u;
-  const int c0 = (int)(word & 0xffffu), c1 = (int)(word >> 16);
-  int incl = c0 + c1;  // entries in bins >= 2 * lane after the scan
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_down_sync(0xffffffffu, incl, o);
-    if (lane + o < 32) incl += v;
-  }
-  const int at_hi = incl - c0;  // entries in bins >= 2 * lane + 1
-  const unsigned hit_hi = __ballot_sync(0xffffffffu, at_hi >= k);
-  const unsigned hit_lo = __ballot_sync(0xffffffffu, incl >= k);
-  int bthr = 0, A = __shfl_sync(0xffffffffu, incl, 0);
-  const int Lh = hit_hi ? 31 - __clz(hit_hi) : -1, Ll = hit_lo ? 31 - __clz(hit_lo) : -1;
-  if (Lh >= 0 && 2 * Lh + 1 >= 2 * Ll) {
-    bthr = 2 * Lh + 1;
-    A = __shfl_sync(0xffffffffu, at_hi, Lh);
-  } else if (Ll >= 0) {
-    bthr = 2 * Ll;
-    A = __shfl_sync(0xffffffffu, incl, Ll);
-  }
-  if (lane == 0) {
-    out[0] = lo; out[1] = w; out[2] = inv_w; out[3] = __int_as_float(bthr); out[4] = __int_as_float(A);
-    out[5] = __int_as_float(n_new);
-  }
-}
-
-// ---- FIRST (re)build of a row (n <= INIT_N entries), entirely in registers.  The entries are loaded once (CPL per lane,
-// one L2 round trip) and bucketed linearly over [min, max] into 256 shared-memory counters -- low contention, where the
-// radix passes of warp_select_kth pile most keys onto one exponent bucket; the bucket holding the k-th largest is
-// re-bucketed once over its own [min, max].  The smallest member of the final bucket is the bound: by construction at
-// least k entries are >= it, and it lies within 2^-16 of the score range of the exact k-th.  ~400 instructions per row
-// where the four streaming radix passes took ~42 k cycles (25 % of a 125k-item sweep, measured with TMF_TOPK_PROF).
-// Outputs as warp_rebuild_row; word NBINS/2 of the histogram row receives the key of the row maximum.
-__device__ __noinline__ void warp_rebuild_first(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
-                                                int* cnt256, float* out) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  float2 x[CPL];
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const int e = lane + 32 * t;
-    x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
-  }
-  unsigned mem = 0;  // bit t: entry t can still be the k-th largest
-  float mn = INFINITY, mx = -INFINITY;
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    if (lane + 32 * t < n) { mem |= 1u << t; mn = fminf(mn, x[t].x); mx = fmaxf(mx, x[t].x); }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  }
-  const float row_max = mx;
-  float lo_b = mn, hi_b = mx;
-  int krem = min(k, n);
-#pragma unroll 1
-  for (int level = 0; level < 2 && hi_b > lo_b; ++level) {
-    const float scale = 256.0f / (hi_b - lo_b);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cnt256[lane * 8 + i] = 0;
-    __syncwarp();
-    int bk[CPL];
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) {
-      bk[t] = (int)fminf(fmaxf((x[t].x - lo_b) * scale, 0.f), 255.f);
-      if ((mem >> t) & 1u) smem_inc(&cnt256[bk[t]]);
-    }
-    __syncwarp();
-    int c[8];
-    int lsum = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {  // lane L owns buckets 255-8L .. 248-8L, visited in descending order
-      c[i] = cnt256[255 - 8 * lane - i];
-      lsum += c[i];
-    }
-    int incl = lsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const unsigned reach = __ballot_sync(0xffffffffu, incl >= krem);
-    const int F = reach ? __ffs(reach) - 1 : 31;  // reach != 0: the members number >= krem
-    int bin = 0, knew = 1;
-    if (lane == F) {
-      int cum = incl - lsum;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (cum + c[i] >= krem) { bin = 255 - 8 * lane - i; knew = krem - cum; break; }
-        cum += c[i];
-      }
-    }
-    bin = __shfl_sync(0xffffffffu, bin, F);
-    krem = __shfl_sync(0xffffffffu, knew, F);
-    float nlo = INFINITY, nhi = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < CPL; ++t) {
-      if (((mem >> t) & 1u) && bk[t] == bin) { nlo = fminf(nlo, x[t].x); nhi = fmaxf(nhi, x[t].x); }
-      else mem &= ~(1u << t);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      nlo = fminf(nlo, __shfl_xor_sync(0xffffffffu, nlo, o));
-      nhi = fmaxf(nhi, __shfl_xor_sync(0xffffffffu, nhi, o));
-    }
-    lo_b = nlo; hi_b = nhi;
-    __syncwarp();
-  }
-  const float kth = lo_b;  // >= k entries are >= kth
-  float W = 4.0f * (row_max - kth);
-  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(kth), 1.0f) * 1e-3f;
-  const float lo = kth;
-  const float w = W / (float)NBINS;
-  const float inv_w = (float)NBINS / W;
-  const float thr = keep_threshold(kth, E, clamp);
-  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
-  __syncwarp();
-  if (lane == 0) hrow[NBINS / 2] = f2key(row_max);
-  int base = 0;
-#pragma unroll
-  for (int t = 0; t < CPL; ++t) {
-    const bool keep = (lane + 32 * t < n) && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      __stcg(buf + base + __popc(bal & lt), x[t]);
-      if (x[t].x >= lo) {
-        const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
-      }
-    }
-    base += __popc(bal);
-  }
-  __syncwarp();
-  finish_rebuild(hrow, k, lo, w, inv_w, base, out);
-  __syncwarp();
-}
-
-// ---- SATURATION rebuild of a row whose histogram is live: ONE streaming pass.  The current bin edge is already a valid
-// lower bound of the k-th largest, so no selection is needed: the list is compacted against the current threshold and the
-// kept entries are re-binned into a histogram re-centred on [edge, edge + 2 (row max - edge)) -- finer bins, hence a tighter
-// running threshold from here on.  (The select-based rebuild streamed the ~2000 entries five times.)
-__device__ __noinline__ void warp_rebuild_saturated(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
-                                                    float lo_old, float w_old, int bthr_old, float thr_floor, float* out) {
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const float slack = 4e-7f * (fabsf(lo_old) + (float)NBINS * w_old);
-  const float edge = lo_old + (float)bthr_old * w_old - slack;   // >= k entries are >= edge (histogram invariant)
-  const float row_max = key2f(hrow[NBINS / 2]);
-  const float thr = fmaxf(keep_threshold(edge, E, clamp), thr_floor);
-  float W = 2.0f * (row_max - edge);
-  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(edge), 1.0f) * 1e-3f;
-  const float lo = edge;
-  const float w = W / (float)NBINS;
-  const float inv_w = (float)NBINS / W;
-  __syncwarp();
-  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
-  __syncwarp();
-  if (lane == 0) hrow[NBINS / 2] = f2key(row_max);
-  int base = 0;
-  for (int b0 = 0; b0 < n; b0 += 32 * 8) {
-    float2 x[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int e = b0 + 32 * t + lane;
-      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
-    }
-    __syncwarp();  // every read of this batch precedes its writes (writes land at or below b0)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int e = b0 + 32 * t + lane;
-      const bool keep = e < n && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
-      const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        __stcg(buf + base + __popc(bal & lt), x[t]);
-        if (x[t].x >= lo) {
-          const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
-          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
-        }
-      }
-      base += __popc(bal);
-    }
-    __syncwarp();
-  }
-  finish_rebuild(hrow, k, lo, w, inv_w, base, out);
-  __syncwarp();
+  return base;
 }
 
 // ------------------------------------------------------------------ the fused kernel
 // dynamic shared memory besides the B ring: alignment slack, A tile, 256 B of barriers + TMEM slot, per-virtual-row histograms,
 // queues, published thresholds, rebuild outputs
 static size_t topk_smem_fixed_bytes(int kb) {
-  return 1024 + (size_t)kb * A_SUB_BYTES + 256 + (size_t)NACC * BM * HSTRIDE * 4 + 16 + (size_t)NACC * BM * QCAP * 8 +
-         (size_t)NACC * BM * 8 + (size_t)NACC * 4 * 8 * 4;
+  return 1024 + (size_t)kb * A_SUB_BYTES + 256 + (size_t)2 * BM * HSTRIDE * 4 + 16 + (size_t)2 * BM * 16 + (size_t)2 * BM * 8 +
+         (size_t)NACC * 4 * 4 + (size_t)NACC * BM * QCAP * 8;
 }
 
 template <bool DUMP, bool PROF>
@@ -629,10 +395,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   uint64_t* tfull = a_empty + 1;                    // [NACC]
   uint64_t* tempty = tfull + NACC;                  // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
-  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 32);                  // [NACC * BM][HSTRIDE] per-virtual-row score histograms
-  float2* queues = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(hist_rows + NACC * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [NACC * BM][QCAP]
-  float2* thr_sh = queues + NACC * BM * QCAP;                                    // [NACC * BM] (threshold, user-block tag) published per virtual row
-  float* init_out = reinterpret_cast<float*>(thr_sh + NACC * BM);                // [NACC * 4 warps][8]
+  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 32);                  // [2][BM][HSTRIDE] per-row score histograms (by user-block parity)
+  float4* rowp = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(hist_rows + 2 * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [2][BM] (lo, w, 1/w, -)
+  uint2* thr_sh = reinterpret_cast<uint2*>(rowp + 2 * BM);                       // [2][BM] (threshold key, user block it belongs to)
+  int* done_sh = reinterpret_cast<int*>(thr_sh + 2 * BM);                        // [NACC][4] last user block each epilogue warp has finished
+  float2* queues = reinterpret_cast<float2*>(done_sh + NACC * 4);                // [NACC * BM][QCAP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto now = [] () -> long long { return PROF ? clock64() : 0ll; };  // cycle counters only in the profiling build
@@ -652,7 +419,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < NACC * BM; i += TOPK_THREADS) thr_sh[i] = make_float2(-INFINITY, __int_as_float(-1));
+  for (int i = threadIdx.x; i < 2 * BM; i += TOPK_THREADS) thr_sh[i] = make_uint2(0u, 0xffffffffu);
+  if (threadIdx.x < NACC * 4) done_sh[threadIdx.x] = -1;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -730,132 +498,137 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
     const int grp = (warp - 4) >> 2;  // epilogue group = accumulator = tile residue mod NACC
     const int q = warp & 3;           // TMEM lane quarter == warp % 4
-    const int vrow = grp * BM + q * 32 + lane;  // virtual row: (group, row) has its own threshold state, queue and list
-    int* radix = reinterpret_cast<int*>(queues + (grp * BM + q * 32) * QCAP);  // radix-select scratch aliases the warp's (empty) queues
-    const uint32_t hrow = smem_u32(hist_rows + vrow * HSTRIDE);
-    const uint32_t queue = smem_u32(queues + vrow * QCAP);
-    float* iout = init_out + (grp * 4 + q) * 8;
+    const int trow = q * 32 + lane;   // row of the CTA's user tile
+    const uint32_t queue = smem_u32(queues + (grp * BM + trow) * QCAP);
     const int n_items = (int)p.n_items;
     uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
-    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-      const long long lrow = (long long)ub * BM + q * 32 + lane;       // batch-local row (candidate buffers)
+    int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
+    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x, ++n_ub) {
+      const int par = n_ub & 1;
+      const uint32_t hrow = smem_u32(hist_rows + (par * BM + trow) * HSTRIDE);
+      const uint32_t thr_slot = smem_u32(thr_sh + par * BM + trow);  // .x = threshold key, .y = tag
+      const long long lrow = (long long)ub * BM + trow;                // batch-local row (candidate buffers)
       const long long row = (long long)p.ub0 * BM + lrow;              // global row
       const bool valid = row < p.n_users;
       RowState st;
       st.thr = valid ? -INFINITY : INFINITY;
-      st.lo = 0.f; st.w = 0.f; st.inv_w = 0.f;
+      st.lo = INFINITY; st.w = 0.f; st.inv_w = 0.f;
       st.E = p.erow[row];
-      st.cnt = 0; st.cq = 0; st.bthr = 0; st.A = 0;
-      bool warp_inited = false;
+      st.cnt = 0; st.cq = 0;
       // External bound (item-sharded scoring): B = a lower bound of the row's k-th best CANONICAL score over all
       // slabs, so a member of the global top-k has s~ >= B - E.  Clamp mode: only a positive bound says anything
-      // (with B <= 0 the zero-score fillers matter).  When every valid row of the warp has such a floor the
-      // warm-up (3 unfiltered tiles + radix-select rebuild per row) is skipped: the rows start filtering at the
-      // floor with an idle histogram (lo = +inf); a list that still fills up heals through the usual rebuild.
+      // (with B <= 0 the zero-score fillers matter).  Such a row filters at that floor from its first tile on.
       st.thr_ext = -INFINITY;
-      if (!DUMP && p.row_bound != nullptr) {
-        if (valid) {
-          const float B = p.row_bound[row];
-          if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
-        }
-        if (__all_sync(0xffffffffu, !valid || st.thr_ext > -INFINITY)) {
-          warp_inited = true;
-          if (valid) st.thr = st.thr_ext;
-          st.lo = INFINITY;
-        }
+      if (!DUMP && p.row_bound != nullptr && valid) {
+        const float B = p.row_bound[row];
+        if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
       }
-      // publish (threshold, user block): the other groups of this row adopt it when it is higher than theirs.  The tag keeps a
-      // group that is still in the previous user block from reading a threshold that belongs to other rows.
-      const float tag = __int_as_float(ub);
-      if (!DUMP) thr_sh[vrow] = make_float2(valid ? st.thr : -INFINITY, tag);
-      float thr_pub = st.thr;
+      if (valid) st.thr = st.thr_ext;
       float2* buf = p.cand + (lrow * NACC + grp) * CAPG;
-      long long w_tfull = 0, w_work = 0, w_init = 0;
+      bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
       for (int nt = grp; nt < p.n_tiles; nt += NACC) {
-        long long t0 = now();
         mbar_wait(smem_u32(&tfull[grp]), acc_phase);
         acc_phase ^= 1;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
-        long long t1 = now();
-        w_tfull += t1 - t0;
         tcgen05_fence_after();
         const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
-        const bool tail_tile = (nt + 1) * BN > n_items;
-        if (!DUMP && warp_inited && TMF_DBG(p) < 2) {
-          // adopt the best threshold any group of this row has published for this user block (monotone, always valid)
-          if (valid) {
+        if (DUMP) {
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
+            tmem_ld_wait_for(ra);
+            dump_chunk(ra, nt * BN + ch * 32, n_items, valid, row, p);
+          }
+        } else if (nt == 0) {
+          // ---- the row's FIRST tile (group 0): everything at or above the external floor is appended; its mean and maximum set
+          // the histogram's bin range; a second read of the (still resident) accumulator bins the appended scores.
+          // The buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that.
+          if (lane < NACC)
+            while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
+          __syncwarp();
+          float mx = -INFINITY, sum = 0.f;
+          int nv = 0;
+          const int id0 = p.item_offset;
+          uint32_t ra[32];
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
+            tmem_ld_wait_for(ra);
 #pragma unroll
-            for (int g2 = 0; g2 < NACC; ++g2) {
-              const float2 o = thr_sh[g2 * BM + q * 32 + lane];
-              if (g2 != grp && __float_as_int(o.y) == ub) st.thr = fmaxf(st.thr, o.x);
+            for (int j = 0; j < 32; ++j) {
+              const int col = ch * 32 + j;
+              const float x = __uint_as_float(ra[j]);
+              if (col < n_items) {
+                mx = fmaxf(mx, x);
+                sum += x;
+                ++nv;
+                if (valid && x >= st.thr_ext) {
+                  __stcg(buf + st.cnt, make_float2(x, __int_as_float(id0 + col)));
+                  ++st.cnt;
+                }
+              }
             }
           }
-          epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, p);
-        } else if (TMF_DBG(p) < 3) {
-          uint32_t ra[32], rb[32];
-          tmem_ld32(t_base, ra);
+          const float mean = nv > 0 ? sum / (float)nv : 0.f;
+          float W = 2.5f * (mx - mean);
+          if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(mean), 1.0f) * 1e-3f;
+          st.lo = mean; st.w = W / (float)NBINS; st.inv_w = (float)NBINS / W;
+          for (int b2 = 0; b2 < HSTRIDE; ++b2) sts_u32(hrow + 4u * (uint32_t)b2, 0u);
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ch += 2) {
-            // chunk ch is in ra; chunk ch+1 is fetched into rb while ra is filtered (and vice versa)
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
-            tmem_ld32(t_base + (uint32_t)((ch + 1) * 32), rb);
-            epilogue_chunk<DUMP>(ra, nt * BN + ch * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
-            tmem_ld_wait_for(rb);
-            if (ch + 2 < BN / 32) tmem_ld32(t_base + (uint32_t)((ch + 2) * 32), ra);
-            epilogue_chunk<DUMP>(rb, nt * BN + (ch + 1) * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(ra[j]);
+              if (ch * 32 + j < n_items && valid && x >= st.thr_ext && x >= st.lo) {
+                const int b2 = (int)fminf((x - st.lo) * st.inv_w, (float)(NBINS - 1));
+                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hrow + 4u * (uint32_t)b2) : "memory");
+              }
+            }
           }
+          {
+            const int bthr = hist_threshold_bin(hrow, p.k);  // warp-collective (votes): every lane calls it, `valid` only masks the use
+            if (valid && bthr >= 0) st.thr = fmaxf(st.thr, edge_threshold(st.lo, st.w, bthr, st.E, p.clamp));
+          }
+          rowp[par * BM + trow] = make_float4(st.lo, st.w, st.inv_w, 0.f);
+          __threadfence_block();
+          thr_sh[par * BM + trow] = make_uint2(f2key(st.thr), (uint32_t)ub);  // publishes the row: the other groups may start
+          ready = true;
+        } else {
+          if (!ready) {  // first own tile of this user block: wait for group 0 to publish the row, adopt its bin range
+            while (lds_u32_volatile(thr_slot + 4u) != (uint32_t)ub) __nanosleep(32);
+            __syncwarp();
+            __threadfence_block();
+            const float4 rp = rowp[par * BM + trow];
+            st.lo = rp.x; st.w = rp.y; st.inv_w = rp.z;
+            ready = true;
+          }
+          if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));  // the row's best threshold so far
+          if (TMF_DBG(p) < 2) epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, thr_slot, p);
         }
         // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
         mbar_arrive(smem_u32(&tempty[grp]));
-        long long t2 = now();
-        w_work += t2 - t1;
         if (!DUMP) {
-          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) {
-            const long long td = now();
-            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-            if (PROF && lane == 0) { atomicAdd(p.prof + 10, (unsigned long long)(now() - td)); atomicAdd(p.prof + 11, 1ull); }
-          }
-          // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
-          // the same tile because everything is appended until then), later whenever a list is about to saturate
-          const bool first = !warp_inited && __any_sync(0xffffffffu, valid && st.cnt >= INIT_N - BN);
-          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && (first || (warp_inited && st.cnt > CAPG - 4 * QCAP)));
-          if (need) {  // the radix scratch aliases the queues: empty them first (lengths may grow a little)
-            const long long tq = now();
-            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-            if (PROF && lane == 0) { atomicAdd(p.prof + 19, (unsigned long long)(now() - tq)); atomicAdd(p.prof + 18, 1ull); }
-            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && (first || (warp_inited && st.cnt > CAPG - 4 * QCAP)));
+          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
+          // a list about to fill: drop what the row's threshold has overtaken
+          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && st.cnt > CAPG - 4 * QCAP);
+          if (need) {
+            drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
+            if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));
+            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && st.cnt > CAPG - 4 * QCAP);
           }
           while (need) {
             const int owner = __ffs(need) - 1;
             need &= need - 1;
             const int n_o = __shfl_sync(0xffffffffu, st.cnt, owner);
-            const float E_o = __shfl_sync(0xffffffffu, st.E, owner);
-            __syncwarp();
+            const float thr_o = __shfl_sync(0xffffffffu, st.thr, owner);
             float2* obuf = p.cand + (((long long)ub * BM + q * 32 + owner) * NACC + grp) * CAPG;
-            uint32_t* ohist = hist_rows + (grp * BM + q * 32 + owner) * HSTRIDE;
-            const float lo_o = __shfl_sync(0xffffffffu, st.lo, owner);
-            // floor of the rebuilt threshold: the external bound and whatever the row's groups have agreed on so far
-            const float floor_o = __shfl_sync(0xffffffffu, fmaxf(st.thr_ext, warp_inited ? st.thr : -INFINITY), owner);
-            const long long tr = now();
-            int which = 0;
-            if (first && n_o <= INIT_N) {
-              warp_rebuild_first(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, radix, iout);
-            } else if (lo_o < INFINITY && !first) {  // live histogram: compaction + re-centring in one pass
-              which = 1;
-              const float w_o = __shfl_sync(0xffffffffu, st.w, owner);
-              const int bthr_o = __shfl_sync(0xffffffffu, st.bthr, owner);
-              warp_rebuild_saturated(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, lo_o, w_o, bthr_o, floor_o, iout);
-            } else {  // a bounded row (idle histogram) that filled up anyway: full selection
-              which = 2;
-              warp_rebuild_row(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, radix, iout);
-            }
-            if (PROF && lane == 0) { atomicAdd(p.prof + 13 + 2 * which, (unsigned long long)(now() - tr)); atomicAdd(p.prof + 12 + 2 * which, 1ull); }
+            const int n_new = warp_compact_row(obuf, n_o, thr_o, p.k, p.clamp, p.item_offset);
             if (lane == owner) {
-              st.lo = iout[0]; st.w = iout[1]; st.inv_w = iout[2];
-              st.bthr = __float_as_int(iout[3]); st.A = __float_as_int(iout[4]);
-              st.cnt = __float_as_int(iout[5]);
-              st.thr = fmaxf(fmaxf(edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp), st.thr_ext), warp_inited ? st.thr : -INFINITY);
+              st.cnt = n_new;
               if (st.cnt > CAPG - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
                 st.cnt = CAPG + 1;
                 st.thr = INFINITY;
@@ -863,27 +636,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             }
             __syncwarp();
           }
-          if (first) warp_inited = true;
-          if (warp_inited && valid && st.thr > thr_pub && st.cnt <= CAPG) {  // publish a raised threshold
-            thr_pub = st.thr;
-            thr_sh[vrow] = make_float2(st.thr, tag);
-          }
         }
-        w_init += now() - t2;
       }
-      if (!DUMP) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
-      if (PROF && lane == 0) {
-        atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
-        atomicAdd(p.prof + 6, (unsigned long long)w_init); atomicAdd(p.prof + 7, 1ull);
-      }
-      if (PROF) atomicAdd(p.prof + 20, (unsigned long long)(valid ? min(st.cnt, CAPG) : 0));
-      const bool ovf = st.cnt > CAPG;
-      if (PROF && valid && ovf) atomicAdd(p.prof + 8, 1ull);
       if (!DUMP) {
+        drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
+        const bool ovf = st.cnt > CAPG;
+        float thr_fin = st.thr;
+        if (ready && !ovf) thr_fin = fmaxf(thr_fin, key2f(lds_u32_volatile(thr_slot)));
         p.cnt[lrow * NACC + grp] = valid ? (ovf ? -1 : st.cnt) : 0;
-        p.thr_out[lrow * NACC + grp] = ovf ? -INFINITY : st.thr;
+        p.thr_out[lrow * NACC + grp] = ovf ? -INFINITY : thr_fin;
       }
       __syncwarp();
+      if (lane == 0) { __threadfence_block(); done_sh[grp * 4 + q] = n_ub; }  // this warp no longer touches the buffers of this parity
     }
   }
 
