@@ -28,7 +28,7 @@ constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
 constexpr int BN = 128;        // items per accumulator tile (TMEM columns)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 8;  // B-operand ring (16 KB stages); the launch uses as many as shared memory allows (>= 2)
+constexpr int MAX_STAGES = 12; // B-operand ring (16 KB stages, 8 KB per CTA of a pair); the launch uses as many as shared memory allows (>= 2)
 // ONE CTA per SM owns all 512 TMEM columns = four 128x128 fp32 accumulators, and runs four epilogue GROUPS of four warps:
 // group g filters the tiles nt = g (mod 4) out of accumulator g.  16 epilogue warps per SM (four per sub-partition) where the
 // previous layout (two CTAs x four warps) had eight: a tile's epilogue is a chain of TMEM round trips at IPC ~0.2 per warp, so
@@ -43,7 +43,13 @@ constexpr int TMEM_COLS = NACC * BN;
 constexpr int CAPG = 1024;
 constexpr int CAP = NACC * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
 constexpr int NBINS = 48;      // per-row score histogram bins (32-bit counts)
-constexpr int QCAP = 16;       // per-(row, group) survivor queue slots in shared memory (drained warp-wide)
+#ifndef TMF_QCAP
+#define TMF_QCAP 16
+#endif
+#ifndef TMF_PF_TILES
+#define TMF_PF_TILES 0
+#endif
+constexpr int QCAP = TMF_QCAP;       // per-(row, group) survivor queue slots in shared memory (drained warp-wide)
 constexpr int HSTRIDE = NBINS + 1;  // words per row: odd, so the lanes' rows fall into different banks
 constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
 constexpr int TOPK_THREADS = 128 + NACC * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
@@ -372,22 +378,33 @@ __device__ __noinline__ int warp_compact_row(float2* buf, int n, float thr, int 
 }
 
 // ------------------------------------------------------------------ the fused kernel
-// dynamic shared memory besides the B ring: alignment slack, A tile, 256 B of barriers + TMEM slot, per-virtual-row histograms,
+// dynamic shared memory besides the B ring: alignment slack, A tile, 320 B of barriers + TMEM slot, per-virtual-row histograms,
 // queues, published thresholds, rebuild outputs
 static size_t topk_smem_fixed_bytes(int kb) {
-  return 1024 + (size_t)kb * A_SUB_BYTES + 256 + (size_t)2 * BM * HSTRIDE * 4 + 16 + (size_t)2 * BM * 16 + (size_t)2 * BM * 8 +
+  return 1024 + (size_t)kb * A_SUB_BYTES + 320 + (size_t)2 * BM * HSTRIDE * 4 + 16 + (size_t)2 * BM * 16 + (size_t)2 * BM * 8 +
          (size_t)NACC * 4 * 4 + (size_t)NACC * BM * QCAP * 8;
 }
 
-template <bool DUMP, bool PROF>
+// CG2: the CTAs of a 2-CTA cluster work as a pair (tcgen05 cta_group::2): CTA r scores user block 2j + r, holds its own A tile
+// and HALF of every B stage (64 of the tile's 128 items), and one M = 256 MMA issued by the leader fills both CTAs' TMEM.  A B
+// stage is then 8 KB per SM for a full tile's worth of tensor work: with one CTA per SM the stage ring is what limits the
+// pipe (measured: 4 x 16 KB stages in flight per SM and a ~1.5 us load round trip = 43 GB/s per SM, tensor pipe 33 % active).
+template <bool DUMP, bool PROF, bool CG2>
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
+  constexpr int B_STAGE = CG2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;  // bytes of a B stage in THIS CTA's shared memory
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
+  const int cta_stride = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int cta_first = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  // user blocks of this CTA: first_ub, first_ub + ub_step, ...   (CG2: pair j takes blocks 2j and 2j + 1)
+  const int first_ub = CG2 ? 2 * cta_first + (int)crank : cta_first;
+  const int ub_step = CG2 ? 2 * cta_stride : cta_stride;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve (1024-byte aligned operand tiles first)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] 16-bit
-  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // nstages x [BN][64] 16-bit
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nstages * B_STAGE_BYTES);
+  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // nstages x [BN (CG2: BN/2)][64] 16-bit
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nstages * B_STAGE);
   uint64_t* full_bar = bars;                        // [MAX_STAGES]
   uint64_t* empty_bar = bars + MAX_STAGES;          // [MAX_STAGES]
   uint64_t* a_full = bars + 2 * MAX_STAGES;         // [1]
@@ -395,7 +412,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   uint64_t* tfull = a_empty + 1;                    // [NACC]
   uint64_t* tempty = tfull + NACC;                  // [NACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
-  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 32);                  // [2][BM][HSTRIDE] per-row score histograms (by user-block parity)
+  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 40);                  // [2][BM][HSTRIDE] per-row score histograms (by user-block parity)
   float4* rowp = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(hist_rows + 2 * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [2][BM] (lo, w, 1/w, -)
   uint2* thr_sh = reinterpret_cast<uint2*>(rowp + 2 * BM);                       // [2][BM] (threshold key, user block it belongs to)
   int* done_sh = reinterpret_cast<int*>(thr_sh + 2 * BM);                        // [NACC][4] last user block each epilogue warp has finished
@@ -412,17 +429,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_empty), 1);
-    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), CG2 ? 256 : 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < 2 * BM; i += TOPK_THREADS) thr_sh[i] = make_uint2(0u, 0xffffffffu);
   if (threadIdx.x < NACC * 4) done_sh[threadIdx.x] = -1;
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -431,21 +454,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
-      for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+      for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
         long long t0 = now();
-        mbar_wait(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
+        mbar_wait_ctrl(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
         long long w_empty = 0, w_aempty = now() - t0;
-        mbar_expect_tx(smem_u32(a_full), p.kb * A_SUB_BYTES);
-        for (int kb = 0; kb < p.kb; ++kb)
-          tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
+        if (!CG2 || crank == 0) mbar_expect_tx(smem_u32(a_full), (CG2 ? 2 : 1) * p.kb * A_SUB_BYTES);  // the pair's A tiles complete on the leader's barrier
+        for (int kb = 0; kb < p.kb; ++kb) {
+          if constexpr (CG2) tma_load_2d_cg2(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
+          else tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
+        }
         a_phase ^= 1;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           for (int kb = 0; kb < p.kb; ++kb) {
             t0 = now();
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            mbar_wait_ctrl(smem_u32(&empty_bar[stage]), phase ^ 1);
             w_empty += now() - t0;
-            mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
-            tma_load_2d(smem_u32(sB + stage * B_STAGE_BYTES), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
+            if constexpr (CG2) {  // this CTA's half of the tile (items nt * 128 + 64 * rank ...), bytes of both halves land on the leader's barrier
+              if (crank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
+              tma_load_2d_cg2(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN + (int)crank * (BN / 2), smem_u32(&full_bar[stage]));
+            } else {
+              mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
+              tma_load_2d(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
+            }
+#if TMF_PF_TILES > 0
+            if (nt + TMF_PF_TILES < p.n_tiles)  // warm the L2 for a tile further down the sweep (no shared memory needed)
+              asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmapV), "r"(kb * BK), "r"((nt + TMF_PF_TILES) * BN) : "memory");
+#endif
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
         }
@@ -453,44 +487,51 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (one thread; CG2: of the leader CTA only) =====================
+    if (lane == 0 && crank == 0) {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       uint32_t acc_bits = 0;  // bit a = parity of the number of times accumulator a has been filled
       // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
-      const uint32_t idesc = f16 ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;
-      for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
-        mbar_wait(smem_u32(a_full), a_phase);
+      constexpr uint32_t kId = CG2 ? umma_idesc_bf16(2 * BM, BN) : kIdesc;
+      const uint32_t idesc = f16 ? (kId & ~((1u << 7) | (1u << 10))) : kId;
+      for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
+        mbar_wait_ctrl(smem_u32(a_full), a_phase);
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           const int acc = nt & (NACC - 1);
           long long t0 = now();
-          mbar_wait(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
+          mbar_wait_ctrl(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
           w_tempty += now() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
             t0 = now();
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            mbar_wait_ctrl(smem_u32(&full_bar[stage]), phase);
             w_full += now() - t0;
             tcgen05_fence_after();
             const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
-                              (uint32_t)((kb | k) != 0));
+              if constexpr (CG2)
+                tcgen05_mma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                                    (uint32_t)((kb | k) != 0));
+              else
+                tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                                (uint32_t)((kb | k) != 0));
             }
-            tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&empty_bar[stage])); else tcgen05_commit(smem_u32(&empty_bar[stage]));
             if (++stage == p.nstages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(smem_u32(&tfull[acc]));  // accumulator ready for its epilogue group
+          // accumulator ready for its epilogue group (of both CTAs of a pair)
+          if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&tfull[acc])); else tcgen05_commit(smem_u32(&tfull[acc]));
           acc_bits ^= 1u << acc;
         }
-        tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
+        if constexpr (CG2) tcgen05_commit_cg2(smem_u32(a_empty)); else tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
         if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
@@ -503,7 +544,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     const int n_items = (int)p.n_items;
     uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
     int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
-    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x, ++n_ub) {
+    for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step, ++n_ub) {
       const int par = n_ub & 1;
       const uint32_t hrow = smem_u32(hist_rows + (par * BM + trow) * HSTRIDE);
       const uint32_t thr_slot = smem_u32(thr_sh + par * BM + trow);  // .x = threshold key, .y = tag
@@ -610,7 +651,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         }
         // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
-        mbar_arrive(smem_u32(&tempty[grp]));
+        if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[grp])); else mbar_arrive(smem_u32(&tempty[grp]));
         if (!DUMP) {
           if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
           // a list about to fill: drop what the row's threshold has overtaken
@@ -651,9 +692,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   }
 
+  tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its shared memory until here
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -1177,7 +1221,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   TopkLayout L{};
-  L.nu_pad = cdiv(n_users, BM) * BM;
+  L.nu_pad = cdiv(n_users, 2 * BM) * (2 * BM);  // whole PAIRS of user blocks (the CTA pair of cta_group::2 takes two at a time)
   L.ni_pad = cdiv(n_items, BN) * BN;
   L.batch_rows = std::min<long long>(L.nu_pad, (long long)UB_BATCH * BM);
   L.k_pad = (int)(cdiv(r, BK) * BK);
@@ -1271,7 +1315,12 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   CUtensorMap tmapU, tmapV;
   int rc = make_tmap(&tmapU, Ub, L.nu_pad, L.k_pad, BM);
   if (rc) return rc;
-  rc = make_tmap(&tmapV, Vb, L.ni_pad, L.k_pad, BN);
+  // CTA pairs (cta_group::2) unless switched off for an A/B (development builds only)
+  bool cg2 = true;
+#ifdef TMF_DEVTOOLS
+  { const char* e = getenv("TMF_TOPK_CG2"); if (e) cg2 = atoi(e) != 0; }
+#endif
+  rc = make_tmap(&tmapV, Vb, L.ni_pad, L.k_pad, cg2 ? BN / 2 : BN);  // a pair's CTA loads its half of every item tile
   if (rc) return rc;
 
   TopkParams p{};
@@ -1300,12 +1349,31 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
 
   const size_t smem_max = 227 * 1024;
   const size_t fixed = topk_smem_fixed_bytes(L.kb);
-  TMF_REQUIRE(fixed + 2 * B_STAGE_BYTES <= smem_max, "tmf_score_topk: shared memory exhausted (n_components too large)");
-  p.nstages = (int)std::min<size_t>(MAX_STAGES, (smem_max - fixed) / B_STAGE_BYTES);
-  const size_t smem = fixed + (size_t)p.nstages * B_STAGE_BYTES;
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t stage_bytes = cg2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+  TMF_REQUIRE(fixed + 2 * stage_bytes <= smem_max, "tmf_score_topk: shared memory exhausted (n_components too large)");
+  p.nstages = (int)std::min<size_t>(MAX_STAGES, (smem_max - fixed) / stage_bytes);
+  const size_t smem = fixed + (size_t)p.nstages * stage_bytes;
+  auto launch_main = [&](int grid) -> int {
+    void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
+    if (dump != nullptr) kern = cg2 ? score_topk_kernel<true, false, true> : score_topk_kernel<true, false, false>;
+    else if (p.prof) kern = cg2 ? score_topk_kernel<false, true, true> : score_topk_kernel<false, true, false>;
+    else kern = cg2 ? score_topk_kernel<false, false, true> : score_topk_kernel<false, false, false>;
+    TMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TOPK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmapU, tmapV, p));
+    return TMF_OK;
+  };
   const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8 + 32 * STG_STRIDE * 4 + 16);
   TMF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
 
@@ -1314,10 +1382,10 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   for (int ub0 = 0; ub0 < total_ublocks; ub0 += UB_BATCH) {
     p.ub0 = ub0;
     p.n_ublocks = std::min(UB_BATCH, total_ublocks - ub0);
-    const int grid = std::min(kNumSMs, p.n_ublocks);  // one persistent CTA per SM (all of its TMEM, ~220 KB of its shared memory)
-    if (dump != nullptr) score_topk_kernel<true, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
-    else if (p.prof) score_topk_kernel<false, true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
-    else score_topk_kernel<false, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    // one persistent CTA per SM (all of its TMEM, ~220 KB of its shared memory); n_ublocks is even, CTA pairs need an even grid
+    const int grid = std::min(kNumSMs, p.n_ublocks) & ~1;
+    rc = launch_main(grid);
+    if (rc) return rc;
     TMF_LAUNCH_CHECK();
     if (dump != nullptr) continue;
     q.row0 = (long long)ub0 * BM;

@@ -22,23 +22,51 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // suspend-time hint: without it try_wait returns after ~30 cycles and the single-thread TMA / MMA waiters spin at full
 // issue rate (ncu: 550 M TRYWAITs per 17 ms), stealing issue slots from the epilogue warps of their SM sub-partition
-constexpr uint32_t kSuspendHintNs = 4000;
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+// Two flavours of waiting.  The single-thread TMA-producer / MMA-issuer waits sit on the tensor pipe's critical path (with one
+// CTA per SM nobody else keeps the pipe fed while they sleep): a short suspend hint.  The epilogue waits (32 lanes x 16 warps
+// per SM spinning for an accumulator) use a long one so their polling does not eat the issue slots of the working warps.
+#ifndef TMF_HINT_CTRL_NS
+#define TMF_HINT_CTRL_NS 4000
+#endif
+#ifndef TMF_HINT_EPI_NS
+#define TMF_HINT_EPI_NS 4000
+#endif
+constexpr uint32_t kSuspendHintNs = TMF_HINT_EPI_NS;
+constexpr uint32_t kSuspendHintCtrlNs = TMF_HINT_CTRL_NS;
+template <uint32_t HINT>
+__device__ __forceinline__ bool mbar_try_wait_h(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
-      : "memory");
+  if constexpr (HINT == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(HINT)
+        : "memory");
+  }
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) { return mbar_try_wait_h<kSuspendHintNs>(bar, parity); }
 // bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_ctrl(uint32_t bar, uint32_t parity) {  // producer / MMA-issuer flavour
+  uint32_t spins = 0;
+  while (!mbar_try_wait_h<kSuspendHintCtrlNs>(bar, parity)) {
+    if (++spins > (1u << 25)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
@@ -118,6 +146,44 @@ __device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
                : "memory");
+}
+
+// ---- CTA pair (cta_group::2): two SMs of a cluster execute ONE MMA of M = 256 -- each CTA supplies its 128 rows of A and its
+// half of the B tile (N/2 rows) from its own shared memory and receives its 128 rows of D in its own TMEM -- so a B stage costs
+// each SM half the shared memory and half the L2 -> SM traffic per flop.  The leader (cluster rank 0) issues; its barriers
+// collect the TMA bytes of both CTAs (peer bit of the barrier address cleared) and the epilogue arrivals of both.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: rank 0's copy of the same offset
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes complete on the LEADER's barrier (same offset in rank 0's shared memory)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar & kPeerBitMask)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tcgen05_commit_cg2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive on the LEADER's barrier from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
