@@ -428,7 +428,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
-    mbar_init(smem_u32(a_empty), 1);
+    mbar_init(smem_u32(a_empty), 2);  // both MMA-issuing threads commit it
     for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), CG2 ? 256 : 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -486,9 +486,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         if (PROF) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread; CG2: of the leader CTA only) =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuers (CG2: of the leader CTA only) =====================
+    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): even tiles / odd tiles.  One thread needs ~147 cycles
+    // per tcgen05.mma (descriptor arithmetic + R2UR moves into the uniform registers the instruction reads + the issue itself;
+    // measured: 77 % of the single issuer's time was issue, 23 % barrier waits, tensor pipe 33 % active) against 64 cycles of
+    // execution, so a single issuer starved the pipe.  Tile nt uses accumulator nt % 4 and the k-block stages that follow from
+    // the global k-block count, so each issuer derives its tiles' stages / phases independently; a stage's MMAs and its commit
+    // come from one thread, and both threads commit the end-of-block "A tile free" barrier (count 2).
     if (lane == 0 && crank == 0) {
+      const int issuer = warp == 1 ? 0 : 1;
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       uint32_t acc_bits = 0;  // bit a = parity of the number of times accumulator a has been filled
@@ -496,12 +503,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
       constexpr uint32_t kId = CG2 ? umma_idesc_bf16(2 * BM, BN) : kIdesc;
       const uint32_t idesc = f16 ? (kId & ~((1u << 7) | (1u << 10))) : kId;
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));  // + (byte offset >> 4) selects a sub-tile / k-slice (no carry out of the 14-bit field)
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
       for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
         mbar_wait_ctrl(smem_u32(a_full), a_phase);
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           const int acc = nt & (NACC - 1);
+          if ((nt & 1) != issuer) {  // the other thread's tile: only account for the stages it consumes
+            for (int kb = 0; kb < p.kb; ++kb)
+              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           long long t0 = now();
           mbar_wait_ctrl(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
           w_tempty += now() - t0;
@@ -512,15 +526,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             mbar_wait_ctrl(smem_u32(&full_bar[stage]), phase);
             w_full += now() - t0;
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE);
+            const uint64_t a_desc = a_desc0 + (uint64_t)((kb * A_SUB_BYTES) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE) >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               if constexpr (CG2)
-                tcgen05_mma_f16_cg2(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                tcgen05_mma_f16_cg2(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
                                     (uint32_t)((kb | k) != 0));
               else
-                tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
                                 (uint32_t)((kb | k) != 0));
             }
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
@@ -531,7 +545,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&tfull[acc])); else tcgen05_commit(smem_u32(&tfull[acc]));
           acc_bits ^= 1u << acc;
         }
-        if constexpr (CG2) tcgen05_commit_cg2(smem_u32(a_empty)); else tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
+        if constexpr (CG2) tcgen05_commit_cg2(smem_u32(a_empty)); else tcgen05_commit(smem_u32(a_empty));  // this thread's MMAs no longer read the A tile
         if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
@@ -568,7 +582,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       float2* buf = p.cand + (lrow * NACC + grp) * CAPG;
       bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
       for (int nt = grp; nt < p.n_tiles; nt += NACC) {
-        mbar_wait(smem_u32(&tfull[grp]), acc_phase);
+        mbar_wait_epi(smem_u32(&tfull[grp]), acc_phase);
         acc_phase ^= 1;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         tcgen05_fence_after();

@@ -63,6 +63,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// epilogue flavour: an explicit sleep between polls.  16 epilogue warps per SM poll for their accumulators; every poll is a
+// shared-memory access next to the tensor core's operand reads and the TMA writes, and the wake-up latency it buys is hidden
+// by the four accumulators in flight.
+#ifndef TMF_EPI_SLEEP_NS
+#define TMF_EPI_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
+  if constexpr (TMF_EPI_SLEEP_NS == 0) {
+    mbar_wait(bar, parity);
+  } else {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_h<0>(bar, parity)) {
+      __nanosleep(TMF_EPI_SLEEP_NS);
+      if (++spins > (1u << 24)) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_ctrl(uint32_t bar, uint32_t parity) {  // producer / MMA-issuer flavour
   uint32_t spins = 0;
   while (!mbar_try_wait_h<kSuspendHintCtrlNs>(bar, parity)) {
@@ -181,6 +198,50 @@ __device__ __forceinline__ void tcgen05_mma_f16_cg2(uint32_t d_tmem, uint64_t a_
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// ---- warp-uniform issue.  tcgen05.mma / tcgen05.commit take their descriptors from UNIFORM registers; when the issuing code runs
+// in one lane of a divergent branch every operand is first moved R -> UR (R2UR, ~25 cycles each, serialised): measured ~147
+// cycles of issue per MMA against 64 cycles of execution, i.e. the single issuing thread, not the tensor core, set the pace.
+// These forms are executed by the WHOLE warp (uniform control flow, uniform operands) and elect one lane only for the
+// instruction itself; elect.sync picks the same lane every time, so the commits track the MMAs of that lane.
+template <bool CG2>
+__device__ __forceinline__ void tcgen05_mma_f16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if constexpr (CG2) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+template <bool CG2>
+__device__ __forceinline__ void tcgen05_commit_warp(uint32_t bar) {
+  if constexpr (CG2) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(bar)
+        : "memory");
+  }
+}
+
 // arrive on the LEADER's barrier from either CTA of the pair
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
