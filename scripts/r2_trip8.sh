@@ -1,6 +1,6 @@
 #!/bin/bash
 cp teamoflow_b200/csrc/libtmf.so /tmp/libtmf_prod.so
-for v in dev s128 s512 s2000; do
+for v in dev; do
 cp variants/libtmf_$v.so teamoflow_b200/csrc/libtmf.so
 for cg in 1 0; do for d in 0 2; do
   echo -n "== $v CG2=$cg DEBUG=$d: "

@@ -228,41 +228,26 @@ __device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[16], float th
   return hm;
 }
 
-// Steady-state filter of one 128-column accumulator tile (rows with a threshold).  Pass 1 streams the tile through
-// registers once, 16 columns at a time through two buffers (the load of chunk c+1 is in flight while chunk c is reduced),
-// and keeps only the 16 group-maximum hit bits -- no votes, no branches.  One REDUX.OR of the per-lane hit masks then names the
-// 8-column groups in which ANY row of the warp has a survivor (about 3 of 16 per tile at 1M items); only those are re-read
-// from TMEM (x8) and their survivors queued with predicated stores, all lanes convergent.
+// Steady-state filter of one HALF tile (64 columns of an accumulator; the other half belongs to the partner group).  Pass 1
+// streams the 64 columns through registers once -- four x16 loads issued back to back, ONE wait -- and keeps only the 8
+// group-maximum hit bits: no votes, no branches.  One REDUX.OR of the per-lane hit masks then names the 8-column groups in which
+// ANY row of the warp has a survivor; only those are re-read from TMEM (x8) and their survivors queued with predicated stores,
+// all lanes convergent.
+constexpr int HALF_N = BN / 2;
+__device__ __forceinline__ void tmem_ld_wait_for16x4(uint32_t (&a)[16], uint32_t (&b)[16], uint32_t (&c)[16], uint32_t (&d)[16]) {
+  tmem_ld_wait_for16x2(a, b);   // the first wait::ld completes all four loads; the second pins c and d behind a wait as well
+  tmem_ld_wait_for16x2(c, d);
+}
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
                                               uint32_t thr_slot, const TopkParams& p) {
-  uint32_t ra[16], rb[16];
+  uint32_t ra[16], rb[16], rc[16], rd[16];
   const float thr = st.thr;  // invalid rows carry thr = +inf; NaN-padded columns never win a max or a compare
-  unsigned hm;
-  // tcgen05.wait::ld waits for EVERY outstanding load of the thread, so the overlap is: issue the load of chunk c+2 into the
-  // buffer just reduced, reduce the other buffer (chunk c+1, complete since the previous wait), then wait.
   tmem_ld16(t_base, ra);
   tmem_ld16(t_base + 16u, rb);
-  tmem_ld_wait_for16x2(ra, rb);
-  hm = chunk_hits(ra, thr);
-  tmem_ld16(t_base + 32u, ra);
-  hm |= chunk_hits(rb, thr) << 2;
-  tmem_ld_wait_for16(ra);
-  tmem_ld16(t_base + 48u, rb);
-  hm |= chunk_hits(ra, thr) << 4;
-  tmem_ld_wait_for16(rb);
-  tmem_ld16(t_base + 64u, ra);
-  hm |= chunk_hits(rb, thr) << 6;
-  tmem_ld_wait_for16(ra);
-  tmem_ld16(t_base + 80u, rb);
-  hm |= chunk_hits(ra, thr) << 8;
-  tmem_ld_wait_for16(rb);
-  tmem_ld16(t_base + 96u, ra);
-  hm |= chunk_hits(rb, thr) << 10;
-  tmem_ld_wait_for16(ra);
-  tmem_ld16(t_base + 112u, rb);
-  hm |= chunk_hits(ra, thr) << 12;
-  tmem_ld_wait_for16(rb);
-  hm |= chunk_hits(rb, thr) << 14;
+  tmem_ld16(t_base + 32u, rc);
+  tmem_ld16(t_base + 48u, rd);
+  tmem_ld_wait_for16x4(ra, rb, rc, rd);
+  const unsigned hm = chunk_hits(ra, thr) | (chunk_hits(rb, thr) << 2) | (chunk_hits(rc, thr) << 4) | (chunk_hits(rd, thr) << 6);
   unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
   if (TMF_DBG(p) == 1) gmask = 0;
   const int id0 = p.item_offset + col0;
@@ -429,7 +414,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_empty), 2);  // both MMA-issuing threads commit it
-    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), CG2 ? 256 : 128); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), CG2 ? 512 : 256); }  // tempty: both groups of the pair (of both CTAs) arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
@@ -510,7 +495,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
-          const int acc = nt & (NACC - 1);
+          const int acc = 2 * (nt & 1) + ((nt >> 1) & 1);  // pair nt % 2 alternates between its two accumulators
           if ((nt & 1) != issuer) {  // the other thread's tile: only account for the stages it consumes
             for (int kb = 0; kb < p.kb; ++kb)
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
@@ -551,12 +536,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
-    const int grp = (warp - 4) >> 2;  // epilogue group = accumulator = tile residue mod NACC
+    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Groups 2P and 2P + 1 form PAIR P: the pair takes the tiles
+    // nt = P (mod 2) and ALTERNATES between its two accumulators (2P, 2P + 1), each group filtering one 64-column half of the tile
+    // -- so while a pair filters one accumulator the MMA warps fill its other one.  (With one accumulator per group, the group's
+    // filtering and the refill of its accumulator were serialised: 875 cycles per tile against 512 of tensor work.)
+    const int grp = (warp - 4) >> 2;
+    const int pair = grp >> 1, half = grp & 1;
     const int q = warp & 3;           // TMEM lane quarter == warp % 4
     const int trow = q * 32 + lane;   // row of the CTA's user tile
     const uint32_t queue = smem_u32(queues + (grp * BM + trow) * QCAP);
     const int n_items = (int)p.n_items;
-    uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
+    uint32_t acc_bits = 0;   // bit j = parity of the number of tiles this pair has consumed from its accumulator j
     int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
     for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step, ++n_ub) {
       const int par = n_ub & 1;
@@ -581,63 +571,80 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       if (valid) st.thr = st.thr_ext;
       float2* buf = p.cand + (lrow * NACC + grp) * CAPG;
       bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
-      for (int nt = grp; nt < p.n_tiles; nt += NACC) {
-        mbar_wait_epi(smem_u32(&tfull[grp]), acc_phase);
-        acc_phase ^= 1;
+      for (int nt = pair; nt < p.n_tiles; nt += 2) {
+        const int j = (nt >> 1) & 1, acc = 2 * pair + j;
+        mbar_wait_epi(smem_u32(&tfull[acc]), (acc_bits >> j) & 1u);
+        acc_bits ^= 1u << j;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         tcgen05_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
+        const int col0 = nt * BN + half * HALF_N;
         if (DUMP) {
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = 0; ch < HALF_N / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
-            dump_chunk(ra, nt * BN + ch * 32, n_items, valid, row, p);
+            dump_chunk(ra, col0 + ch * 32, n_items, valid, row, p);
           }
         } else if (nt == 0) {
-          // ---- the row's FIRST tile (group 0): everything at or above the external floor is appended; its mean and maximum set
-          // the histogram's bin range; a second read of the (still resident) accumulator bins the appended scores.
-          // The buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that.
-          if (lane < NACC)
-            while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
-          __syncwarp();
+          // ---- the row's FIRST tile (pair 0): everything at or above the external floor is appended by both groups (in clamp
+          // mode the k lowest item ids -- the zero-score fillers -- are thereby always listed).  Group 0 also sets the row up:
+          // mean and maximum of its 64 columns give the histogram's bin range; group 1 waits for that before it bins its half.
+          // A second read of the (still resident) accumulator bins the appended scores.
+          if (half == 0) {
+            // the buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that
+            if (lane < NACC)
+              while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
+            __syncwarp();
+          }
           float mx = -INFINITY, sum = 0.f;
           int nv = 0;
-          const int id0 = p.item_offset;
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = 0; ch < HALF_N / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = ch * 32 + j;
-              const float x = __uint_as_float(ra[j]);
+            for (int jj = 0; jj < 32; ++jj) {
+              const int col = col0 + ch * 32 + jj;
+              const float x = __uint_as_float(ra[jj]);
               if (col < n_items) {
                 mx = fmaxf(mx, x);
                 sum += x;
                 ++nv;
                 if (valid && x >= st.thr_ext) {
-                  __stcg(buf + st.cnt, make_float2(x, __int_as_float(id0 + col)));
+                  __stcg(buf + st.cnt, make_float2(x, __int_as_float(p.item_offset + col)));
                   ++st.cnt;
                 }
               }
             }
           }
-          const float mean = nv > 0 ? sum / (float)nv : 0.f;
-          float W = 2.5f * (mx - mean);
-          if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(mean), 1.0f) * 1e-3f;
-          st.lo = mean; st.w = W / (float)NBINS; st.inv_w = (float)NBINS / W;
-          for (int b2 = 0; b2 < HSTRIDE; ++b2) sts_u32(hrow + 4u * (uint32_t)b2, 0u);
+          if (half == 0) {
+            const float mean = nv > 0 ? sum / (float)nv : 0.f;
+            float W = 2.5f * (mx - mean);
+            if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(mean), 1.0f) * 1e-3f;
+            st.lo = mean; st.w = W / (float)NBINS; st.inv_w = (float)NBINS / W;
+            for (int b2 = 0; b2 < HSTRIDE; ++b2) sts_u32(hrow + 4u * (uint32_t)b2, 0u);
+            rowp[par * BM + trow] = make_float4(st.lo, st.w, st.inv_w, 0.f);
+            __threadfence_block();
+            thr_sh[par * BM + trow] = make_uint2(f2key(st.thr), (uint32_t)ub);  // publishes the row: the other groups may start
+          } else {
+            while (lds_u32_volatile(thr_slot + 4u) != (uint32_t)ub) __nanosleep(32);
+            __syncwarp();
+            __threadfence_block();
+            const float4 rp = rowp[par * BM + trow];
+            st.lo = rp.x; st.w = rp.y; st.inv_w = rp.z;
+          }
+          ready = true;
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = 0; ch < HALF_N / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = __uint_as_float(ra[j]);
-              if (ch * 32 + j < n_items && valid && x >= st.thr_ext && x >= st.lo) {
+            for (int jj = 0; jj < 32; ++jj) {
+              const float x = __uint_as_float(ra[jj]);
+              if (col0 + ch * 32 + jj < n_items && valid && x >= st.thr_ext && x >= st.lo) {
                 const int b2 = (int)fminf((x - st.lo) * st.inv_w, (float)(NBINS - 1));
                 asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hrow + 4u * (uint32_t)b2) : "memory");
               }
@@ -645,12 +652,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           }
           {
             const int bthr = hist_threshold_bin(hrow, p.k);  // warp-collective (votes): every lane calls it, `valid` only masks the use
-            if (valid && bthr >= 0) st.thr = fmaxf(st.thr, edge_threshold(st.lo, st.w, bthr, st.E, p.clamp));
+            if (valid && bthr >= 0) {
+              const float t = fmaxf(edge_threshold(st.lo, st.w, bthr, st.E, p.clamp), st.thr_ext);
+              if (t > st.thr) {
+                st.thr = t;
+                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
+              }
+            }
           }
-          rowp[par * BM + trow] = make_float4(st.lo, st.w, st.inv_w, 0.f);
-          __threadfence_block();
-          thr_sh[par * BM + trow] = make_uint2(f2key(st.thr), (uint32_t)ub);  // publishes the row: the other groups may start
-          ready = true;
         } else {
           if (!ready) {  // first own tile of this user block: wait for group 0 to publish the row, adopt its bin range
             while (lds_u32_volatile(thr_slot + 4u) != (uint32_t)ub) __nanosleep(32);
@@ -661,11 +670,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             ready = true;
           }
           if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));  // the row's best threshold so far
-          if (TMF_DBG(p) < 2) epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, thr_slot, p);
+          if (TMF_DBG(p) < 2) epilogue_tile(t_base, col0, st, queue, buf, hrow, thr_slot, p);
         }
-        // accumulator drained: hand it back to the MMA warp before any list maintenance
+        // accumulator half drained: hand it back to the MMA warps before any list maintenance
         tcgen05_fence_before();
-        if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[grp])); else mbar_arrive(smem_u32(&tempty[grp]));
+        if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[acc])); else mbar_arrive(smem_u32(&tempty[acc]));
         if (!DUMP) {
           if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
           // a list about to fill: drop what the row's threshold has overtaken
