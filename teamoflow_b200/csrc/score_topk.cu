@@ -25,23 +25,25 @@
 namespace tmf {
 
 constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
-constexpr int BN = 128;        // items per accumulator tile (TMEM columns)
+constexpr int BN = 256;        // items per MMA tile = per accumulator buffer (TMEM columns); tcgen05.mma with N = 256
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 12; // B-operand ring (16 KB stages, 8 KB per CTA of a pair); the launch uses as many as shared memory allows (>= 2)
-// ONE CTA per SM owns all 512 TMEM columns = four 128x128 fp32 accumulators, and runs four epilogue GROUPS of four warps:
-// group g filters the tiles nt = g (mod 4) out of accumulator g.  16 epilogue warps per SM (four per sub-partition) where the
-// previous layout (two CTAs x four warps) had eight: a tile's epilogue is a chain of TMEM round trips at IPC ~0.2 per warp, so
-// the sub-partitions' issue slots were 60 % idle and the tensor pipe waited for accumulators (46 % active).
-constexpr int NACC = 4;
-constexpr int TMEM_COLS = NACC * BN;
+constexpr int MAX_STAGES = 12; // B-operand ring (32 KB stages, 16 KB per CTA of a pair); the launch uses as many as shared memory allows (>= 2)
+// ONE CTA per SM owns all 512 TMEM columns = two 128 x 256 fp32 accumulator buffers, and runs four epilogue GROUPS of four warps
+// (16 epilogue warps per SM, four per sub-partition, where round 1's two-CTA layout had eight).  The MMAs are N = 256 wide:
+// at N = 128 every MMA reads 4 KB of A and 4 KB of B from shared memory per 64 cycles -- the whole 128 B/clk of the SM's shared
+// memory, before the TMA writes -- and costs the issuing thread as much as an N = 256 one.
+constexpr int NBUF = 2;         // accumulator buffers of BN columns: the MMA warps fill one while the epilogue filters the other
+constexpr int NGRP = 4;         // epilogue groups (4 warps each): group g filters columns [g * QN, (g + 1) * QN) of every tile
+constexpr int QN = BN / NGRP;   // 64
+constexpr int TMEM_COLS = NBUF * BN;
 // A row's candidates are appended per group (group g sees every fourth tile of the row): CAPG slots each.  The running
 // threshold is per ROW: one score histogram per row in shared memory, fed by all four groups (red.shared), from which any
 // group derives "the highest bin edge with >= k entries at or above it" -- a lower bound of the row's k-th best score so far.
 // (A first version kept a private histogram per group: each group then tracks the k-th best of ITS quarter of the items,
 // roughly the 4k-th best overall, 3.4x the survivors and 525 ms where the two-CTA kernel took 322.)
 constexpr int CAPG = 1024;
-constexpr int CAP = NACC * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
+constexpr int CAP = NGRP * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
 constexpr int NBINS = 48;      // per-row score histogram bins (32-bit counts)
 #ifndef TMF_QCAP
 #define TMF_QCAP 16
@@ -52,9 +54,9 @@ constexpr int NBINS = 48;      // per-row score histogram bins (32-bit counts)
 constexpr int QCAP = TMF_QCAP;       // per-(row, group) survivor queue slots in shared memory (drained warp-wide)
 constexpr int HSTRIDE = NBINS + 1;  // words per row: odd, so the lanes' rows fall into different banks
 constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
-constexpr int TOPK_THREADS = 128 + NACC * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
+constexpr int TOPK_THREADS = 128 + NGRP * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2; // 32 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
 // Error bound of the tensor-core score s~ = fl32(sum u~_c v~_c) against the real score s = sum u_c v_c, with u~ = bf16(u),
 // du = u - u~ (both known exactly):  s - sum u~_c v~_c = du.v + u~.dv  =>  |s~ - s| <= |du||v| + |u~||dv| + accumulation.
@@ -96,9 +98,9 @@ struct TopkParams {
   int nstages;                  // B-operand ring depth of this launch
   int k, clamp, item_offset;
   const float* erow;            // [n_users_pad] error bound E of each user row against this item slab (global row index)
-  float2* cand;                 // [batch rows][NACC][CAPG] (approx score, item id bits), batch-local row index
-  int* cnt;                     // [batch rows][NACC] candidates per (row, group), -1 = overflow (the rerank hands the row to the exact path)
-  float* thr_out;               // [batch rows][NACC] final keep-threshold of each group (each is valid for the whole row)
+  float2* cand;                 // [batch rows][NGRP][CAPG] (approx score, item id bits), batch-local row index
+  int* cnt;                     // [batch rows][NGRP] candidates per (row, group), -1 = overflow (the rerank hands the row to the exact path)
+  float* thr_out;               // [batch rows][NGRP] final keep-threshold of each group (each is valid for the whole row)
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
   const float* fmt_stats;       // operand statistics (see use_fp16); NULL with force_fmt >= 0
@@ -228,12 +230,11 @@ __device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[16], float th
   return hm;
 }
 
-// Steady-state filter of one HALF tile (64 columns of an accumulator; the other half belongs to the partner group).  Pass 1
+// Steady-state filter of one group's QUARTER of a tile (64 of the accumulator buffer's 256 columns).  Pass 1
 // streams the 64 columns through registers once -- four x16 loads issued back to back, ONE wait -- and keeps only the 8
 // group-maximum hit bits: no votes, no branches.  One REDUX.OR of the per-lane hit masks then names the 8-column groups in which
 // ANY row of the warp has a survivor; only those are re-read from TMEM (x8) and their survivors queued with predicated stores,
 // all lanes convergent.
-constexpr int HALF_N = BN / 2;
 __device__ __forceinline__ void tmem_ld_wait_for16x4(uint32_t (&a)[16], uint32_t (&b)[16], uint32_t (&c)[16], uint32_t (&d)[16]) {
   tmem_ld_wait_for16x2(a, b);   // the first wait::ld completes all four loads; the second pins c and d behind a wait as well
   tmem_ld_wait_for16x2(c, d);
@@ -367,7 +368,7 @@ __device__ __noinline__ int warp_compact_row(float2* buf, int n, float thr, int 
 // queues, published thresholds, rebuild outputs
 static size_t topk_smem_fixed_bytes(int kb) {
   return 1024 + (size_t)kb * A_SUB_BYTES + 320 + (size_t)2 * BM * HSTRIDE * 4 + 16 + (size_t)2 * BM * 16 + (size_t)2 * BM * 8 +
-         (size_t)NACC * 4 * 4 + (size_t)NACC * BM * QCAP * 8;
+         (size_t)NGRP * 4 * 4 + (size_t)NGRP * BM * QCAP * 8;
 }
 
 // CG2: the CTAs of a 2-CTA cluster work as a pair (tcgen05 cta_group::2): CTA r scores user block 2j + r, holds its own A tile
@@ -394,14 +395,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
   uint64_t* empty_bar = bars + MAX_STAGES;          // [MAX_STAGES]
   uint64_t* a_full = bars + 2 * MAX_STAGES;         // [1]
   uint64_t* a_empty = a_full + 1;                   // [1]
-  uint64_t* tfull = a_empty + 1;                    // [NACC]
-  uint64_t* tempty = tfull + NACC;                  // [NACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
+  uint64_t* tfull = a_empty + 1;                    // [NBUF]
+  uint64_t* tempty = tfull + NBUF;                  // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NBUF);
   uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 40);                  // [2][BM][HSTRIDE] per-row score histograms (by user-block parity)
   float4* rowp = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(hist_rows + 2 * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [2][BM] (lo, w, 1/w, -)
   uint2* thr_sh = reinterpret_cast<uint2*>(rowp + 2 * BM);                       // [2][BM] (threshold key, user block it belongs to)
-  int* done_sh = reinterpret_cast<int*>(thr_sh + 2 * BM);                        // [NACC][4] last user block each epilogue warp has finished
-  float2* queues = reinterpret_cast<float2*>(done_sh + NACC * 4);                // [NACC * BM][QCAP]
+  int* done_sh = reinterpret_cast<int*>(thr_sh + 2 * BM);                        // [NGRP][4] last user block each epilogue warp has finished
+  float2* queues = reinterpret_cast<float2*>(done_sh + NGRP * 4);                // [NGRP * BM][QCAP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto now = [] () -> long long { return PROF ? clock64() : 0ll; };  // cycle counters only in the profiling build
@@ -414,7 +415,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_empty), 2);  // both MMA-issuing threads commit it
-    for (int s = 0; s < NACC; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), CG2 ? 512 : 256); }  // tempty: both groups of the pair (of both CTAs) arrive
+    for (int s = 0; s < NBUF; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), (CG2 ? 2 : 1) * NGRP * 128); }  // tempty: all four groups (of both CTAs) arrive
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
@@ -427,7 +428,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   }
   for (int i = threadIdx.x; i < 2 * BM; i += TOPK_THREADS) thr_sh[i] = make_uint2(0u, 0xffffffffu);
-  if (threadIdx.x < NACC * 4) done_sh[threadIdx.x] = -1;
+  if (threadIdx.x < NGRP * 4) done_sh[threadIdx.x] = -1;
   tcgen05_fence_before();
   __syncthreads();
   if constexpr (CG2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them remotely
@@ -454,7 +455,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             t0 = now();
             mbar_wait_ctrl(smem_u32(&empty_bar[stage]), phase ^ 1);
             w_empty += now() - t0;
-            if constexpr (CG2) {  // this CTA's half of the tile (items nt * 128 + 64 * rank ...), bytes of both halves land on the leader's barrier
+            if constexpr (CG2) {  // this CTA's half of the tile (items nt * 256 + 128 * rank ...), bytes of both halves land on the leader's barrier
               if (crank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
               tma_load_2d_cg2(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN + (int)crank * (BN / 2), smem_u32(&full_bar[stage]));
             } else {
@@ -473,12 +474,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (CG2: of the leader CTA only) =====================
-    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): even tiles / odd tiles.  One thread needs ~147 cycles
-    // per tcgen05.mma (descriptor arithmetic + R2UR moves into the uniform registers the instruction reads + the issue itself;
-    // measured: 77 % of the single issuer's time was issue, 23 % barrier waits, tensor pipe 33 % active) against 64 cycles of
-    // execution, so a single issuer starved the pipe.  Tile nt uses accumulator nt % 4 and the k-block stages that follow from
-    // the global k-block count, so each issuer derives its tiles' stages / phases independently; a stage's MMAs and its commit
-    // come from one thread, and both threads commit the end-of-block "A tile free" barrier (count 2).
+    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): even tiles / odd tiles = accumulator buffer 0 / 1.  One
+    // thread needs ~147 cycles per tcgen05.mma (descriptor arithmetic + R2UR moves into the uniform registers the instruction
+    // reads + the issue itself; measured with N = 128: 77 % of a single issuer's time was issue, 23 % barrier waits, tensor pipe
+    // 33 % active), so a single issuer of narrow MMAs starved the pipe.  The k-block stages a tile uses follow from the global
+    // k-block count, so each issuer derives its tiles' stages / phases independently; a stage's MMAs and its commit come from one
+    // thread, and both threads commit the end-of-block "A tile free" barrier (count 2).
     if (lane == 0 && crank == 0) {
       const int issuer = warp == 1 ? 0 : 1;
       int stage = 0;
@@ -495,8 +496,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
-          const int acc = 2 * (nt & 1) + ((nt >> 1) & 1);  // pair nt % 2 alternates between its two accumulators
-          if ((nt & 1) != issuer) {  // the other thread's tile: only account for the stages it consumes
+          const int acc = nt & (NBUF - 1);  // = issuer: each thread fills its own accumulator buffer
+          if (acc != issuer) {  // the other thread's tile: only account for the stages it consumes
             for (int kb = 0; kb < p.kb; ++kb)
               if (++stage == p.nstages) { stage = 0; phase ^= 1; }
             continue;
@@ -536,17 +537,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
-    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Groups 2P and 2P + 1 form PAIR P: the pair takes the tiles
-    // nt = P (mod 2) and ALTERNATES between its two accumulators (2P, 2P + 1), each group filtering one 64-column half of the tile
-    // -- so while a pair filters one accumulator the MMA warps fill its other one.  (With one accumulator per group, the group's
-    // filtering and the refill of its accumulator were serialised: 875 cycles per tile against 512 of tensor work.)
+    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Every group works on EVERY tile: group g filters the 64-column
+    // quarter g of the 256-column accumulator buffer (tile nt is in buffer nt % 2), so while the groups filter one buffer the MMA
+    // warps fill the other.
     const int grp = (warp - 4) >> 2;
-    const int pair = grp >> 1, half = grp & 1;
     const int q = warp & 3;           // TMEM lane quarter == warp % 4
     const int trow = q * 32 + lane;   // row of the CTA's user tile
     const uint32_t queue = smem_u32(queues + (grp * BM + trow) * QCAP);
     const int n_items = (int)p.n_items;
-    uint32_t acc_bits = 0;   // bit j = parity of the number of tiles this pair has consumed from its accumulator j
+    uint32_t acc_bits = 0;   // bit b = parity of the number of tiles consumed from accumulator buffer b
     int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
     for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step, ++n_ub) {
       const int par = n_ub & 1;
@@ -569,40 +568,40 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
       }
       if (valid) st.thr = st.thr_ext;
-      float2* buf = p.cand + (lrow * NACC + grp) * CAPG;
+      float2* buf = p.cand + (lrow * NGRP + grp) * CAPG;
       bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
-      for (int nt = pair; nt < p.n_tiles; nt += 2) {
-        const int j = (nt >> 1) & 1, acc = 2 * pair + j;
-        mbar_wait_epi(smem_u32(&tfull[acc]), (acc_bits >> j) & 1u);
-        acc_bits ^= 1u << j;
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        const int acc = nt & (NBUF - 1);
+        mbar_wait_epi(smem_u32(&tfull[acc]), (acc_bits >> acc) & 1u);
+        acc_bits ^= 1u << acc;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         tcgen05_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * HALF_N);
-        const int col0 = nt * BN + half * HALF_N;
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + grp * QN);
+        const int col0 = nt * BN + grp * QN;
         if (DUMP) {
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < HALF_N / 32; ++ch) {
+          for (int ch = 0; ch < QN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
             dump_chunk(ra, col0 + ch * 32, n_items, valid, row, p);
           }
         } else if (nt == 0) {
-          // ---- the row's FIRST tile (pair 0): everything at or above the external floor is appended by both groups (in clamp
-          // mode the k lowest item ids -- the zero-score fillers -- are thereby always listed).  Group 0 also sets the row up:
-          // mean and maximum of its 64 columns give the histogram's bin range; group 1 waits for that before it bins its half.
-          // A second read of the (still resident) accumulator bins the appended scores.
-          if (half == 0) {
+          // ---- the row's FIRST tile: everything at or above the external floor is appended by all groups (in clamp mode the k
+          // lowest item ids -- the zero-score fillers -- are thereby always listed).  Group 0 also sets the row up: mean and
+          // standard deviation of its 64 columns give the histogram's bin range; the other groups wait for that before they bin
+          // their quarters.  A second read of the (still resident) accumulator bins the appended scores.
+          if (grp == 0) {
             // the buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that
-            if (lane < NACC)
+            if (lane < NGRP)
               while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
             __syncwarp();
           }
-          float mx = -INFINITY, sum = 0.f;
+          float mx = -INFINITY, sum = 0.f, sumsq = 0.f;
           int nv = 0;
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < HALF_N / 32; ++ch) {
+          for (int ch = 0; ch < QN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
@@ -612,6 +611,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               if (col < n_items) {
                 mx = fmaxf(mx, x);
                 sum += x;
+                sumsq = fmaf(x, x, sumsq);
                 ++nv;
                 if (valid && x >= st.thr_ext) {
                   __stcg(buf + st.cnt, make_float2(x, __int_as_float(p.item_offset + col)));
@@ -620,9 +620,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               }
             }
           }
-          if (half == 0) {
+          if (grp == 0) {
+            // bin range [mean, mean + W): W = 6.5 standard deviations of the sample (the k-th best of 10^6 .. 10^9 Gaussian scores
+            // sits 3.7 .. 5.5 sigma above the mean), and never less than 2.5 x (sample maximum - mean) for heavy-tailed rows.  A
+            // range from the sample maximum alone is fragile: one row in ~10^5 has a 64-sample maximum below 1 sigma, its top bin
+            // then saturates far below the k-th best score, its lists fill up and the row falls back to the exact path.
             const float mean = nv > 0 ? sum / (float)nv : 0.f;
-            float W = 2.5f * (mx - mean);
+            const float var = nv > 1 ? fmaxf(sumsq / (float)nv - mean * mean, 0.f) : 0.f;
+            float W = fmaxf(6.5f * sqrtf(var), 2.5f * (mx - mean));
             if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(mean), 1.0f) * 1e-3f;
             st.lo = mean; st.w = W / (float)NBINS; st.inv_w = (float)NBINS / W;
             for (int b2 = 0; b2 < HSTRIDE; ++b2) sts_u32(hrow + 4u * (uint32_t)b2, 0u);
@@ -638,7 +643,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           }
           ready = true;
 #pragma unroll 1
-          for (int ch = 0; ch < HALF_N / 32; ++ch) {
+          for (int ch = 0; ch < QN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
@@ -672,7 +677,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));  // the row's best threshold so far
           if (TMF_DBG(p) < 2) epilogue_tile(t_base, col0, st, queue, buf, hrow, thr_slot, p);
         }
-        // accumulator half drained: hand it back to the MMA warps before any list maintenance
+        // this group's quarter of the buffer is drained: hand it back to the MMA warps before any list maintenance
         tcgen05_fence_before();
         if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[acc])); else mbar_arrive(smem_u32(&tempty[acc]));
         if (!DUMP) {
@@ -689,7 +694,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             need &= need - 1;
             const int n_o = __shfl_sync(0xffffffffu, st.cnt, owner);
             const float thr_o = __shfl_sync(0xffffffffu, st.thr, owner);
-            float2* obuf = p.cand + (((long long)ub * BM + q * 32 + owner) * NACC + grp) * CAPG;
+            float2* obuf = p.cand + (((long long)ub * BM + q * 32 + owner) * NGRP + grp) * CAPG;
             const int n_new = warp_compact_row(obuf, n_o, thr_o, p.k, p.clamp, p.item_offset);
             if (lane == owner) {
               st.cnt = n_new;
@@ -707,8 +712,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         const bool ovf = st.cnt > CAPG;
         float thr_fin = st.thr;
         if (ready && !ovf) thr_fin = fmaxf(thr_fin, key2f(lds_u32_volatile(thr_slot)));
-        p.cnt[lrow * NACC + grp] = valid ? (ovf ? -1 : st.cnt) : 0;
-        p.thr_out[lrow * NACC + grp] = ovf ? -INFINITY : thr_fin;
+        p.cnt[lrow * NGRP + grp] = valid ? (ovf ? -1 : st.cnt) : 0;
+        p.thr_out[lrow * NGRP + grp] = ovf ? -INFINITY : thr_fin;
       }
       __syncwarp();
       if (lane == 0) { __threadfence_block(); done_sh[grp * 4 + q] = n_ub; }  // this warp no longer touches the buffers of this parity
@@ -821,18 +826,18 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   const long long lrow = (long long)blockIdx.x * RR_WARPS + w;
   if (lrow >= p.n_rows) return;
   const long long row = p.row0 + lrow;
-  // the row's candidates: one list per epilogue group of the main kernel ([row][NACC][CAPG]); each group's final threshold is
+  // the row's candidates: one list per epilogue group of the main kernel ([row][NGRP][CAPG]); each group's final threshold is
   // a valid keep-threshold for the whole row, so the highest one applies to all lists
-  int ng[NACC];
+  int ng[NGRP];
   int n = 0;
   bool overflowed = false;
   float thr = -INFINITY;
 #pragma unroll
-  for (int g = 0; g < NACC; ++g) {
-    ng[g] = p.cnt[lrow * NACC + g];
+  for (int g = 0; g < NGRP; ++g) {
+    ng[g] = p.cnt[lrow * NGRP + g];
     overflowed |= ng[g] < 0;
     n += max(ng[g], 0);
-    thr = fmaxf(thr, p.thr[lrow * NACC + g]);
+    thr = fmaxf(thr, p.thr[lrow * NGRP + g]);
   }
   if (overflowed) {  // a list saturated in the main kernel (massive ties): the exact path ranks this row
     if (lane == 0) {
@@ -849,7 +854,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   // ---- 1. superset by the main kernel's final threshold (or the clamp-mode filler rule)
   int m = 0;
 #pragma unroll 1
-  for (int g = 0; g < NACC; ++g) {
+  for (int g = 0; g < NGRP; ++g) {
     const float2* buf = rowbuf + g * CAPG;
     for (int b0 = 0; b0 < ng[g]; b0 += 256) {
       float2 x[8];
@@ -878,7 +883,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
     } else {  // loose running thresholds (badly placed histograms): make the row's lists one contiguous list in place, select over it
       int off = ng[0];
 #pragma unroll 1
-      for (int g = 1; g < NACC; ++g) {
+      for (int g = 1; g < NGRP; ++g) {
         const float2* src = rowbuf + g * CAPG;
         for (int b0 = 0; b0 < ng[g]; b0 += 32) {  // destination <= source: forward copy, reads of a batch precede its writes
           const int e = b0 + lane;
@@ -1258,8 +1263,8 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   L.off_vnorm = o; o = align_up(o + (size_t)L.ni_pad * 4, 256);
   L.off_vmax = o; o += 256;
   L.off_cand = o; o = align_up(o + (size_t)L.batch_rows * CAP * 8, 256);
-  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * NACC * 4, 256);
-  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * NACC * 4, 256);
+  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * NGRP * 4, 256);
+  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * NGRP * 4, 256);
   L.off_ovfc = o; o += 256;
   L.off_ovfr = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.scratch_rows = (int)std::min<long long>(32, n_users);
