@@ -25,7 +25,7 @@
 namespace tmf {
 
 constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
-constexpr int BN = 256;        // items per MMA tile = per accumulator buffer (TMEM columns); tcgen05.mma with N = 256
+constexpr int BN = 128;        // items per MMA tile = per accumulator buffer (TMEM columns)
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 12; // B-operand ring (32 KB stages, 16 KB per CTA of a pair); the launch uses as many as shared memory allows (>= 2)
@@ -33,9 +33,9 @@ constexpr int MAX_STAGES = 12; // B-operand ring (32 KB stages, 16 KB per CTA of
 // (16 epilogue warps per SM, four per sub-partition, where round 1's two-CTA layout had eight).  The MMAs are N = 256 wide:
 // at N = 128 every MMA reads 4 KB of A and 4 KB of B from shared memory per 64 cycles -- the whole 128 B/clk of the SM's shared
 // memory, before the TMA writes -- and costs the issuing thread as much as an N = 256 one.
-constexpr int NBUF = 2;         // accumulator buffers of BN columns: the MMA warps fill one while the epilogue filters the other
-constexpr int NGRP = 4;         // epilogue groups (4 warps each): group g filters columns [g * QN, (g + 1) * QN) of every tile
-constexpr int QN = BN / NGRP;   // 64
+constexpr int NBUF = 4;         // accumulator buffers of BN columns (all 512 TMEM columns); buffer b holds the tiles nt % 4 == b
+constexpr int NGRP = NBUF;      // epilogue groups (4 warps each): group g owns buffer g, i.e. filters the tiles nt % 4 == g
+constexpr int QN = 64;          // columns per filter pass (four x16 TMEM loads, one wait)
 constexpr int TMEM_COLS = NBUF * BN;
 // A row's candidates are appended per group (group g sees every fourth tile of the row): CAPG slots each.  The running
 // threshold is per ROW: one score histogram per row in shared memory, fed by all four groups (red.shared), from which any
@@ -56,7 +56,7 @@ constexpr int HSTRIDE = NBINS + 1;  // words per row: odd, so the lanes' rows fa
 constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
 constexpr int TOPK_THREADS = 128 + NGRP * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2; // 32 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
 // Error bound of the tensor-core score s~ = fl32(sum u~_c v~_c) against the real score s = sum u_c v_c, with u~ = bf16(u),
 // du = u - u~ (both known exactly):  s - sum u~_c v~_c = du.v + u~.dv  =>  |s~ - s| <= |du||v| + |u~||dv| + accumulation.
@@ -151,11 +151,19 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
 // all lanes, each for its own row: highest bin with >= k entries at or above it (-1 when the row has fewer than k binned
 // entries).  Walks down from the top bin; the warp stops when every lane has its answer.
 __device__ __forceinline__ int hist_threshold_bin(uint32_t hrow, int k) {
+  static_assert(NBINS % 16 == 0, "scanned in chunks of 16 bins");
   int cum = 0, found = -1;
-  for (int b = NBINS - 1; b >= 0; --b) {
-    cum += (int)lds_u32_volatile(hrow + 4u * (uint32_t)b);
-    if (found < 0 && cum >= k) found = b;
-    if ((b & 7) == 0 && __all_sync(0xffffffffu, found >= 0)) break;
+#pragma unroll 1
+  for (int c = NBINS / 16 - 1; c >= 0; --c) {
+    uint32_t v[16];  // 16 independent loads in flight (a bin-by-bin walk pays the shared-memory latency 48 times: ~2500 cycles)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = lds_u32_volatile(hrow + 4u * (uint32_t)(c * 16 + j));
+#pragma unroll
+    for (int j = 15; j >= 0; --j) {
+      cum += (int)v[j];
+      if (found < 0 && cum >= k) found = c * 16 + j;
+    }
+    if (__all_sync(0xffffffffu, found >= 0)) break;
   }
   return found;
 }
@@ -201,6 +209,40 @@ __device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float
   DrainRet r;
   r.thr = thr; r.cnt = cnt;
   return r;
+}
+// Per-tile share of the list maintenance: every lane moves (at most) the newest entry of its queue to its list, branch-free.  In
+// steady state a lane queues a survivor every ~10 tiles, so this keeps the queues near empty at a FIXED cost per tile -- the
+// accumulator buffers are handed back only when all epilogue warps (of both CTAs of a pair) are through with them, so a warp that
+// every ~50 tiles spends a whole tile period in a full drain stalls the MMA threads and every other warp with it.
+__device__ __forceinline__ void pop_one(RowState& st, uint32_t queue, float2* buf, uint32_t hrow) {
+  const bool has = st.cq > 0;
+  const float2 e = lds_f2(queue + 8u * (uint32_t)max(st.cq - 1, 0));
+  const bool ok = has && (e.x >= st.thr);
+  const bool okh = ok && (e.x >= st.lo);
+  const int b = (int)fminf(fmaxf((e.x - st.lo) * st.inv_w, 0.f), (float)(NBINS - 1));
+  const int st_ok = ok && (st.cnt < CAPG);
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.s32 p, %0, 0;\n\t"
+      "setp.ne.s32 q, %1, 0;\n\t"
+      "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
+      "@q red.shared.add.u32 [%5], 1;\n\t}"
+      ::"r"(st_ok), "r"((int)okh), "l"(buf + st.cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)b)
+      : "memory");
+  st.cnt += ok ? 1 : 0;
+  st.cq -= has ? 1 : 0;
+}
+// the row's threshold from its histogram (warp-collective), published when it rose
+__device__ __noinline__ float refresh_threshold(float thr, float thr_ext, float lo, float w, float E, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
+  const int bthr = hist_threshold_bin(hrow, k);
+  if (bthr >= 0) {
+    const float t = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
+    if (t > thr && thr < INFINITY) {
+      thr = t;
+      asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
+    }
+  }
+  return thr;
 }
 __device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
   const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, queue, buf, hrow, thr_slot, k, clamp);
@@ -248,10 +290,35 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowStat
   tmem_ld16(t_base + 32u, rc);
   tmem_ld16(t_base + 48u, rd);
   tmem_ld_wait_for16x4(ra, rb, rc, rd);
+  if (TMF_DBG(p) == 5) return;  // diagnostic: accumulator reads only
   const unsigned hm = chunk_hits(ra, thr) | (chunk_hits(rb, thr) << 2) | (chunk_hits(rc, thr) << 4) | (chunk_hits(rd, thr) << 6);
   unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
   if (TMF_DBG(p) == 1) gmask = 0;
   const int id0 = p.item_offset + col0;
+  if (gmask == 0) return;
+  // Pass 2, common case: every lane's queue has room for all it can add (8 per hit group of its own row), so the survivors are
+  // pushed straight from the registers pass 1 holds -- the loop is unrolled, each hit group is its own warp-uniform block with
+  // static register indices, no call sites (nothing is live across a call) and no second accumulator read (each of those cost a
+  // serialised ~300-cycle round trip while the MMA threads wait for the buffer).
+  if (__all_sync(0xffffffffu, st.cq + 8 * __popc(hm) <= QCAP)) {
+    int cq = st.cq;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (gmask & (1u << g)) {  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = (g & 1) * 8 + j;
+          const float x = __uint_as_float(g < 2 ? ra[e] : g < 4 ? rb[e] : g < 6 ? rc[e] : rd[e]);
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
+                       ::"f"(x), "f"(thr), "r"(queue + 8u * (uint32_t)cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
+          cq += (x >= thr) ? 1 : 0;
+        }
+      }
+    }
+    st.cq = cq;
+    return;
+  }
+  // some lane may overflow its queue: re-read the hit groups from TMEM one at a time, draining the queues in between
   while (gmask) {  // warp-uniform
     const int g = __ffs(gmask) - 1;
     gmask &= gmask - 1;
@@ -415,7 +482,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
     mbar_init(smem_u32(a_empty), 2);  // both MMA-issuing threads commit it
-    for (int s = 0; s < NBUF; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), (CG2 ? 2 : 1) * NGRP * 128); }  // tempty: all four groups (of both CTAs) arrive
+    for (int s = 0; s < NBUF; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), (CG2 ? 2 : 1) * 4); }  // tempty: ONE arrival per epilogue warp (of both CTAs): 32 per-lane arrivals on one barrier word serialise (~300 cycles per warp and tile)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
@@ -437,9 +504,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // The B stages form TWO rings of nstages / 2: ring r carries the tiles nt % 2 == r, the tiles of MMA thread r.  With one ring and
+    // two consumers that each skip the other's stages, a consumer that is held up (its epilogue group is busy) could be lapped
+    // twice by the ring and would then mistake a later phase of a stage's barrier for the one it waits for.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, a_phase = 0;
+      const int hs = p.nstages >> 1;
+      int st_r[2] = {0, 0};
+      uint32_t ph_r[2] = {0, 0};
+      uint32_t a_phase = 0;
       for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
         long long t0 = now();
         mbar_wait_ctrl(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
@@ -451,11 +523,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         }
         a_phase ^= 1;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
+          const int r = nt & 1;
+          int rs = r ? st_r[1] : st_r[0];
+          uint32_t phase = r ? ph_r[1] : ph_r[0];
           for (int kb = 0; kb < p.kb; ++kb) {
+            const int stage = r * hs + rs;
             t0 = now();
             mbar_wait_ctrl(smem_u32(&empty_bar[stage]), phase ^ 1);
             w_empty += now() - t0;
-            if constexpr (CG2) {  // this CTA's half of the tile (items nt * 256 + 128 * rank ...), bytes of both halves land on the leader's barrier
+            if (TMF_DBG(p) == 3) {  // diagnostic: no B loads at all (MMAs read whatever the stage holds)
+              if (!CG2 || crank == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+            } else if constexpr (CG2) {  // this CTA's half of the tile (items nt * 128 + 64 * rank ...), bytes of both halves land on the leader's barrier
               if (crank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
               tma_load_2d_cg2(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN + (int)crank * (BN / 2), smem_u32(&full_bar[stage]));
             } else {
@@ -466,28 +544,29 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             if (nt + TMF_PF_TILES < p.n_tiles)  // warm the L2 for a tile further down the sweep (no shared memory needed)
               asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmapV), "r"(kb * BK), "r"((nt + TMF_PF_TILES) * BN) : "memory");
 #endif
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            if (++rs == hs) { rs = 0; phase ^= 1; }
           }
+          if (r) { st_r[1] = rs; ph_r[1] = phase; } else { st_r[0] = rs; ph_r[0] = phase; }
         }
         if (PROF) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
       }
     }
   } else if (warp == 1 || warp == 3) {
     // ===================== MMA issuers (CG2: of the leader CTA only) =====================
-    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): even tiles / odd tiles = accumulator buffer 0 / 1.  One
-    // thread needs ~147 cycles per tcgen05.mma (descriptor arithmetic + R2UR moves into the uniform registers the instruction
-    // reads + the issue itself; measured with N = 128: 77 % of a single issuer's time was issue, 23 % barrier waits, tensor pipe
-    // 33 % active), so a single issuer of narrow MMAs starved the pipe.  The k-block stages a tile uses follow from the global
-    // k-block count, so each issuer derives its tiles' stages / phases independently; a stage's MMAs and its commit come from one
-    // thread, and both threads commit the end-of-block "A tile free" barrier (count 2).
+    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): thread r issues the tiles nt % 2 == r (accumulator
+    // buffers r and r + 2) from its own stage ring.  One thread needs ~150 cycles per tcgen05.mma (descriptor arithmetic, the moves
+    // into the uniform registers the instruction reads, the issue itself -- measured: a single issuer spent 77 % of its time
+    // issuing with the tensor pipe 33 % active) against 64 cycles of execution, so one issuer starves the pipe.  Both threads
+    // commit the end-of-block "A tile free" barrier (count 2).
     if (lane == 0 && crank == 0) {
       const int issuer = warp == 1 ? 0 : 1;
-      int stage = 0;
+      const int hs = p.nstages >> 1;
+      int rs = 0;  // position in this thread's stage ring
       uint32_t phase = 0, a_phase = 0;
       uint32_t acc_bits = 0;  // bit a = parity of the number of times accumulator a has been filled
       // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
-      constexpr uint32_t kId = CG2 ? umma_idesc_bf16(2 * BM, BN) : kIdesc;
+      constexpr uint32_t kId = umma_idesc_bf16(CG2 ? 2 * BM : BM, BN);
       const uint32_t idesc = f16 ? (kId & ~((1u << 7) | (1u << 10))) : kId;
       const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));  // + (byte offset >> 4) selects a sub-tile / k-slice (no carry out of the 14-bit field)
       const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
@@ -495,19 +574,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
         mbar_wait_ctrl(smem_u32(a_full), a_phase);
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
-        for (int nt = 0; nt < p.n_tiles; ++nt) {
-          const int acc = nt & (NBUF - 1);  // = issuer: each thread fills its own accumulator buffer
-          if (acc != issuer) {  // the other thread's tile: only account for the stages it consumes
-            for (int kb = 0; kb < p.kb; ++kb)
-              if (++stage == p.nstages) { stage = 0; phase ^= 1; }
-            continue;
-          }
+        const long long cb = now();
+        for (int nt = issuer; nt < p.n_tiles; nt += 2) {
+          const int acc = nt & (NBUF - 1);
           long long t0 = now();
           mbar_wait_ctrl(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
           w_tempty += now() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
+            const int stage = issuer * hs + rs;
             t0 = now();
             mbar_wait_ctrl(smem_u32(&full_bar[stage]), phase);
             w_full += now() - t0;
@@ -516,6 +592,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE) >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (TMF_DBG(p) == 4 && (kb | k) != 0) continue;  // diagnostic: one MMA per tile (loads at full rate)
               if constexpr (CG2)
                 tcgen05_mma_f16_cg2(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
                                     (uint32_t)((kb | k) != 0));
@@ -525,27 +602,32 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             }
             // frees the smem slot (in both CTAs of a pair) when these MMAs retire
             if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&empty_bar[stage])); else tcgen05_commit(smem_u32(&empty_bar[stage]));
-            if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+            if (++rs == hs) { rs = 0; phase ^= 1; }
           }
           // accumulator ready for its epilogue group (of both CTAs of a pair)
           if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&tfull[acc])); else tcgen05_commit(smem_u32(&tfull[acc]));
           acc_bits ^= 1u << acc;
         }
         if constexpr (CG2) tcgen05_commit_cg2(smem_u32(a_empty)); else tcgen05_commit(smem_u32(a_empty));  // this thread's MMAs no longer read the A tile
-        if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
+        if (PROF) {
+          atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full);
+          atomicAdd(p.prof + 21, (unsigned long long)(now() - cb)); atomicAdd(p.prof + 22, (unsigned long long)((p.n_tiles - issuer + 1) / 2));
+        }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
-    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Every group works on EVERY tile: group g filters the 64-column
-    // quarter g of the 256-column accumulator buffer (tile nt is in buffer nt % 2), so while the groups filter one buffer the MMA
-    // warps fill the other.
+    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Group g owns accumulator buffer g: it filters the tiles
+    // nt % 4 == g, 128 columns in two 64-column passes.  A buffer is handed back when the 4 warps of its group (8 in a CTA pair) are
+    // through with it and three other buffers are in flight meanwhile, so one slow warp (a queue drain, a list compaction) does not
+    // stall the MMA threads.  (Measured alternative: two 256-column buffers with all 16 warps on every tile -- each hand-over then
+    // waits for the slowest of 32 warps with one tile of slack, and the MMA threads waited for buffers half of the time.)
     const int grp = (warp - 4) >> 2;
     const int q = warp & 3;           // TMEM lane quarter == warp % 4
     const int trow = q * 32 + lane;   // row of the CTA's user tile
     const uint32_t queue = smem_u32(queues + (grp * BM + trow) * QCAP);
     const int n_items = (int)p.n_items;
-    uint32_t acc_bits = 0;   // bit b = parity of the number of tiles consumed from accumulator buffer b
+    uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
     int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
     for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step, ++n_ub) {
       const int par = n_ub & 1;
@@ -570,38 +652,39 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       if (valid) st.thr = st.thr_ext;
       float2* buf = p.cand + (lrow * NGRP + grp) * CAPG;
       bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
-      for (int nt = 0; nt < p.n_tiles; ++nt) {
-        const int acc = nt & (NBUF - 1);
-        mbar_wait_epi(smem_u32(&tfull[acc]), (acc_bits >> acc) & 1u);
-        acc_bits ^= 1u << acc;
+      long long w_tfull = 0, w_work = 0, w_maint = 0;
+      int n_own = 0;
+      for (int nt = grp; nt < p.n_tiles; nt += NGRP, ++n_own) {
+        const long long c0 = now();
+        mbar_wait_epi(smem_u32(&tfull[grp]), acc_phase);
+        const long long c1 = now();
+        w_tfull += c1 - c0;
+        acc_phase ^= 1u;
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
         tcgen05_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + grp * QN);
-        const int col0 = nt * BN + grp * QN;
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
+        const int col0 = nt * BN;
         if (DUMP) {
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < QN / 32; ++ch) {
+          for (int ch = 0; ch < BN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
             dump_chunk(ra, col0 + ch * 32, n_items, valid, row, p);
           }
         } else if (nt == 0) {
-          // ---- the row's FIRST tile: everything at or above the external floor is appended by all groups (in clamp mode the k
-          // lowest item ids -- the zero-score fillers -- are thereby always listed).  Group 0 also sets the row up: mean and
-          // standard deviation of its 64 columns give the histogram's bin range; the other groups wait for that before they bin
-          // their quarters.  A second read of the (still resident) accumulator bins the appended scores.
-          if (grp == 0) {
-            // the buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that
-            if (lane < NGRP)
-              while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
-            __syncwarp();
-          }
+          // ---- the row's FIRST tile (group 0): everything at or above the external floor is appended; mean and standard
+          // deviation of its 128 scores give the histogram's bin range; a second read of the (still resident) accumulator bins
+          // the appended scores.  The other groups wait for the published row before their first tile.
+          // The buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that.
+          if (lane < NGRP)
+            while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
+          __syncwarp();
           float mx = -INFINITY, sum = 0.f, sumsq = 0.f;
           int nv = 0;
           uint32_t ra[32];
 #pragma unroll 1
-          for (int ch = 0; ch < QN / 32; ++ch) {
+          for (int ch = 0; ch < BN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
@@ -620,10 +703,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
               }
             }
           }
-          if (grp == 0) {
+          {
             // bin range [mean, mean + W): W = 6.5 standard deviations of the sample (the k-th best of 10^6 .. 10^9 Gaussian scores
             // sits 3.7 .. 5.5 sigma above the mean), and never less than 2.5 x (sample maximum - mean) for heavy-tailed rows.  A
-            // range from the sample maximum alone is fragile: one row in ~10^5 has a 64-sample maximum below 1 sigma, its top bin
+            // range from the sample maximum alone is fragile: one row in ~10^5 has a sample maximum below 1 sigma, its top bin
             // then saturates far below the k-th best score, its lists fill up and the row falls back to the exact path.
             const float mean = nv > 0 ? sum / (float)nv : 0.f;
             const float var = nv > 1 ? fmaxf(sumsq / (float)nv - mean * mean, 0.f) : 0.f;
@@ -634,16 +717,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             rowp[par * BM + trow] = make_float4(st.lo, st.w, st.inv_w, 0.f);
             __threadfence_block();
             thr_sh[par * BM + trow] = make_uint2(f2key(st.thr), (uint32_t)ub);  // publishes the row: the other groups may start
-          } else {
-            while (lds_u32_volatile(thr_slot + 4u) != (uint32_t)ub) __nanosleep(32);
-            __syncwarp();
-            __threadfence_block();
-            const float4 rp = rowp[par * BM + trow];
-            st.lo = rp.x; st.w = rp.y; st.inv_w = rp.z;
           }
           ready = true;
 #pragma unroll 1
-          for (int ch = 0; ch < QN / 32; ++ch) {
+          for (int ch = 0; ch < BN / 32; ++ch) {
             tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
             tmem_ld_wait_for(ra);
 #pragma unroll
@@ -675,13 +752,26 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             ready = true;
           }
           if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));  // the row's best threshold so far
-          if (TMF_DBG(p) < 2) epilogue_tile(t_base, col0, st, queue, buf, hrow, thr_slot, p);
+          if (TMF_DBG(p) < 2 || TMF_DBG(p) == 5) {
+            epilogue_tile(t_base, col0, st, queue, buf, hrow, thr_slot, p);
+            epilogue_tile(t_base + (uint32_t)QN, col0 + QN, st, queue, buf, hrow, thr_slot, p);
+          }
         }
-        // this group's quarter of the buffer is drained: hand it back to the MMA warps before any list maintenance
+        // the buffer is drained: hand it back to the MMA thread before any list maintenance (one arrival per warp)
         tcgen05_fence_before();
-        if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[acc])); else mbar_arrive(smem_u32(&tempty[acc]));
+        __syncwarp();  // every lane's accumulator reads are complete
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[grp])); else mbar_arrive(smem_u32(&tempty[grp]));
+        }
+        const long long c2 = now();
+        w_work += c2 - c1;
         if (!DUMP) {
-          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
+          if (ready) {
+            pop_one(st, queue, buf, hrow);
+            // threshold refresh every 16th own tile, staggered over the warps
+            if (((n_own + (warp - 4)) & 15) == 0) st.thr = refresh_threshold(st.thr, st.thr_ext, st.lo, st.w, st.E, hrow, thr_slot, p.k, p.clamp);
+          }
+          if (__any_sync(0xffffffffu, st.cq > QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
           // a list about to fill: drop what the row's threshold has overtaken
           unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && st.cnt > CAPG - 4 * QCAP);
           if (need) {
@@ -706,6 +796,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
             __syncwarp();
           }
         }
+        w_maint += now() - c2;
+      }
+      if (PROF && lane == 0) {
+        atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
+        atomicAdd(p.prof + 6, (unsigned long long)w_maint); atomicAdd(p.prof + 7, (unsigned long long)n_own);
       }
       if (!DUMP) {
         drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
@@ -1380,6 +1475,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   const size_t stage_bytes = cg2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
   TMF_REQUIRE(fixed + 2 * stage_bytes <= smem_max, "tmf_score_topk: shared memory exhausted (n_components too large)");
   p.nstages = (int)std::min<size_t>(MAX_STAGES, (smem_max - fixed) / stage_bytes);
+  p.nstages &= ~1;  // two rings of nstages / 2 (even / odd item tiles)
   const size_t smem = fixed + (size_t)p.nstages * stage_bytes;
   auto launch_main = [&](int grid) -> int {
     void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
@@ -1429,8 +1525,9 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
     TMF_CUDA(cudaStreamSynchronize(st));
     TMF_CUDA(cudaMemcpy(h, p.prof, 192, cudaMemcpyDeviceToHost));
     TMF_CUDA(cudaMemcpy(&novf, ovfc, 4, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-sweep, n=%llu) "
-                    "wait tfull %.3g, work %.3g, init %.3g cycles | overflow rows %d (main %llu, rerank %llu) | tile-end drains: %llu, %.0f cycles each\n",
+    fprintf(stderr, "[tmf prof] per tile: MMA thread total %.0f, wait tempty %.0f, wait full %.0f cycles\n", (double)h[21] / h[22], (double)h[2] / h[22], (double)h[3] / h[22]);
+    fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-tile, n=%llu) "
+                    "wait tfull %.3g, work %.3g, maintenance %.3g cycles | overflow rows %d (main %llu, rerank %llu) | tile-end drains: %llu, %.0f cycles each\n",
             (double)h[0], (double)h[1], (double)h[2], (double)h[3], h[7], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], novf, h[8], h[9], h[11], h[11] ? (double)h[10] / h[11] : 0.0);
     fprintf(stderr, "[tmf prof] rebuilds: first %llu x %.0f cycles, saturated %llu x %.0f, generic %llu x %.0f | pre-rebuild drains %llu x %.0f | appended entries %.4g (%.1f per row-sweep)\n",
             h[12], h[12] ? (double)h[13] / h[12] : 0.0, h[14], h[14] ? (double)h[15] / h[14] : 0.0, h[16], h[16] ? (double)h[17] / h[16] : 0.0,
