@@ -3,14 +3,10 @@
 // per-row running threshold and appends the few survivors to a candidate list; an fp64-accumulated
 // rerank of the candidates then makes the returned indices exact (ties -> lower item id).
 //
-// Exactness argument (DESIGN.md "top-k"): with u~ = fl16(u), du = u - u~ (both known exactly) the tensor-core
-// score s~ of a pair differs from the canonical score s by at most E = |du| max|v| + |u~| max|dv| + accumulation
-// slack (row_error_kernel; rigorous, computed from the data -- the worst case for bf16 is 2^-7 |u||v|).  With t~ a
-// lower bound of the k-th largest s~ seen so far in a row, every item of the final top-k satisfies s~ >= t~ - 2E,
-// so the candidate list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
-//
-// Developer switches (TMF_TOPK_DEBUG / TMF_TOPK_FMT / TMF_TOPK_PROF environment variables) exist only in builds
-// compiled with -DTMF_DEVTOOLS (scripts/build_variant.sh); the product library reads no environment variable.
+// Exactness argument (DESIGN.md "top-k"): the bf16 GEMM score s~ of a pair differs from the canonical
+// score s by at most e = 2^-8 * 1.05 * |u| * |v|.  With t~ the k-th largest s~ seen so far in a row,
+// every item of the final top-k satisfies s~ >= t~ - 2E (E = e with |v| := max |v|), so the candidate
+// list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -20,41 +16,33 @@
 #include <algorithm>
 
 #include "common.cuh"
-#include "tc_common.cuh"
 
 namespace tmf {
 
+#ifndef TMF_PASS2_REGS
+#define TMF_PASS2_REGS 0
+#endif
+// Development switches (TMF_TOPK_DEBUG / TMF_TOPK_FMT / TMF_TOPK_PROF) exist only in builds compiled with -DTMF_DEVTOOLS
+// (scripts/build_variant.sh); the product library reads no environment variable.
+#ifdef TMF_DEVTOOLS
+#define TMF_DBG(p) ((p).dbg)
+#else
+#define TMF_DBG(p) 0
+#endif
 constexpr int BM = 128;        // users per CTA tile (TMEM lanes)
-constexpr int BN = 128;        // items per MMA tile = per accumulator buffer (TMEM columns)
+constexpr int BN = 128;        // items per accumulator tile (TMEM columns); two CTAs share an SM
 constexpr int BK = 64;         // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int MAX_STAGES = 12; // B-operand ring (32 KB stages, 16 KB per CTA of a pair); the launch uses as many as shared memory allows (>= 2)
-// ONE CTA per SM owns all 512 TMEM columns = two 128 x 256 fp32 accumulator buffers, and runs four epilogue GROUPS of four warps
-// (16 epilogue warps per SM, four per sub-partition, where round 1's two-CTA layout had eight).  The MMAs are N = 256 wide:
-// at N = 128 every MMA reads 4 KB of A and 4 KB of B from shared memory per 64 cycles -- the whole 128 B/clk of the SM's shared
-// memory, before the TMA writes -- and costs the issuing thread as much as an N = 256 one.
-constexpr int NBUF = 4;         // accumulator buffers of BN columns (all 512 TMEM columns); buffer b holds the tiles nt % 4 == b
-constexpr int NGRP = NBUF;      // epilogue groups (4 warps each): group g owns buffer g, i.e. filters the tiles nt % 4 == g
-constexpr int QN = 64;          // columns per filter pass (four x16 TMEM loads, one wait)
-constexpr int TMEM_COLS = NBUF * BN;
-// A row's candidates are appended per group (group g sees every fourth tile of the row): CAPG slots each.  The running
-// threshold is per ROW: one score histogram per row in shared memory, fed by all four groups (red.shared), from which any
-// group derives "the highest bin edge with >= k entries at or above it" -- a lower bound of the row's k-th best score so far.
-// (A first version kept a private histogram per group: each group then tracks the k-th best of ITS quarter of the items,
-// roughly the 4k-th best overall, 3.4x the survivors and 525 ms where the two-CTA kernel took 322.)
-constexpr int CAPG = 1024;
-constexpr int CAP = NGRP * CAPG;  // candidate slots per row in the workspace: [row][group][CAPG]
-constexpr int NBINS = 48;      // per-row score histogram bins (32-bit counts)
-#ifndef TMF_QCAP
-#define TMF_QCAP 16
-#endif
-#ifndef TMF_PF_TILES
-#define TMF_PF_TILES 0
-#endif
-constexpr int QCAP = TMF_QCAP;       // per-(row, group) survivor queue slots in shared memory (drained warp-wide)
-constexpr int HSTRIDE = NBINS + 1;  // words per row: odd, so the lanes' rows fall into different banks
-constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 8.6 GB
-constexpr int TOPK_THREADS = 128 + NGRP * 128;  // TMA, MMA, TMEM-alloc, (idle) warps + 4 groups x 4 epilogue warps
+constexpr int NSTAGES = 3;     // B-operand ring (16 KB stages)
+constexpr int TMEM_COLS = 2 * BN;  // two accumulators per CTA, double-buffered against the epilogue
+constexpr int CAP = 2048;      // candidate slots per row (appended, never compacted; saturation -> exact path)
+constexpr int INIT_N = 512;    // a row's threshold state is initialised from its first <= INIT_N entries
+constexpr int CPL = INIT_N / 32;  // entries per lane in the warp-cooperative initial selection
+constexpr int NBINS = 48;      // per-row score histogram bins (16-bit counts, two per word)
+constexpr int QCAP = 16;       // per-row survivor queue slots in shared memory (drained warp-wide)
+constexpr int HSTRIDE = NBINS / 2 + 1;  // words per row, padded against bank conflicts
+constexpr int UB_BATCH = 2048; // user blocks (x128 rows) per main-kernel launch: bounds the candidate workspace to 4 GB
+constexpr int TOPK_THREADS = 256;
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2; // 16 KB
 constexpr int MAX_KB = 4;                  // n_components <= 256
@@ -66,12 +54,103 @@ constexpr int MAX_KB = 4;                  // n_components <= 256
 constexpr float ACC_UNIT = 2.4e-7f;
 constexpr float NORM_SLACK = 1.0001f;  // rounding of the fp32 norm arithmetic itself
 
-#ifdef TMF_DEVTOOLS
-#define TMF_DBG(p) ((p).dbg)
-#else
-#define TMF_DBG(p) 0
-#endif
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// suspend-time hint: without it try_wait returns after ~30 cycles and the single-thread TMA / MMA waiters spin at full
+// issue rate (ncu: 550 M TRYWAITs per 17 ms), stealing issue slots from the epilogue warps of their SM sub-partition
+constexpr uint32_t kSuspendHintNs = 4000;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_for8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait that also pins the loaded registers behind it (consumers cannot be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -95,12 +174,13 @@ struct TopkParams {
   long long n_users, n_items;   // real sizes
   int ub0, n_ublocks;           // this launch covers user blocks [ub0, ub0 + n_ublocks)
   int n_tiles, kb;              // item tiles of BN, k-blocks of BK
-  int nstages;                  // B-operand ring depth of this launch
   int k, clamp, item_offset;
   const float* erow;            // [n_users_pad] error bound E of each user row against this item slab (global row index)
-  float2* cand;                 // [batch rows][NGRP][CAPG] (approx score, item id bits), batch-local row index
-  int* cnt;                     // [batch rows][NGRP] candidates per (row, group), -1 = overflow (the rerank hands the row to the exact path)
-  float* thr_out;               // [batch rows][NGRP] final keep-threshold of each group (each is valid for the whole row)
+  float2* cand;                 // [batch rows][CAP] (approx score, item id bits), batch-local row index
+  int* cnt;                     // [batch rows] candidates per row, -1 = overflow (exact path)
+  float* thr_out;               // [batch rows] final keep-threshold of the row
+  int* ovf_count;               // [1]
+  int* ovf_rows;                // [n_users_pad] global rows handed to the exact path
   float* dump;                  // optional [n_users][dump_ld]: raw bf16-GEMM scores (bring-up / error-bound tests)
   long long dump_ld;
   const float* fmt_stats;       // operand statistics (see use_fp16); NULL with force_fmt >= 0
@@ -117,30 +197,30 @@ __device__ __forceinline__ float keep_threshold(float kth, float E, int clamp) {
   return clamp ? fmaxf(kth - E, 0.f) - E : kth - 2.f * E;
 }
 
-// ---- per-row running threshold: a 48-bin histogram of the appended scores per ROW in shared memory (32-bit counts),
-// shared by the row's four epilogue groups and double-buffered by user-block parity.  "The highest bin whose at-or-above
-// count is >= k" gives a lower bound of the k-th largest score seen so far: a scan that races with other groups'
-// increments can only UNDER-count, so every threshold it yields is valid; the published threshold (ordered uint32 key,
-// red.shared.max) only rises.  The bin range is set once per row from the row's first tile: [mean, mean + 2.5 (max - mean)).
+// ---- per-row running threshold: a lane-private 48-bin histogram of the appended scores (16-bit counts, two
+// bins per shared-memory word).  bthr = the highest bin whose "at or above" count A is still >= k, so the lower
+// edge of bin bthr is a valid lower bound of the k-th largest score seen so far; it only ever rises.
 //
 // ---- SIMD list maintenance.  A lane that finds a survivor only pushes (score, item) onto its own small
 // shared-memory queue (3 instructions, no dependent loads).  When a queue is about to fill, the WHOLE warp
-// drains: iteration s handles entry s of every lane at once, each lane appending to its own (row, group) list and
-// counting the entry in its row's histogram -- the append code runs once per queue slot for 32 rows instead of
+// drains: iteration s handles entry s of every lane at once, each lane appending to its own row's list and
+// updating its own histogram -- the ~40-instruction append runs once per queue slot for 32 rows instead of
 // once per survivor with 1-3 active lanes (measured: 400-600 cycles per survivor in the divergent versions).
 struct RowState {
-  float thr;      // current keep-threshold (+inf for padded rows and for lists handed to the exact path)
+  float thr;      // current keep-threshold (+inf for padded rows)
   float thr_ext;  // externally supplied floor of the threshold (-inf when there is none)
   float lo, w, inv_w, E;
-  int cnt;        // list length; > CAPG = saturated (-> exact path)
+  int cnt;        // list length; > CAP = saturated (-> exact path)
   int cq;         // entries waiting in the lane's queue
+  int bthr, A;    // threshold bin and # entries with bin >= bthr
 };
 
+__device__ __forceinline__ int hist_get(const uint32_t* hrow, int b) { return (int)((hrow[b >> 1] >> ((b & 1) * 16)) & 0xffffu); }
 // explicit shared-space accesses: through generic pointers these compile to the slower ST.E/LD.E with 64-bit addressing
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ float2 lds_f2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ int hist_get_s(uint32_t hrow, int b) { return (int)((lds_u32(hrow + 4u * (uint32_t)(b >> 1)) >> ((b & 1) * 16)) & 0xffffu); }
 
 __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, float E, int clamp) {
   const float edge = lo + (float)bthr * w;
@@ -148,33 +228,13 @@ __device__ __forceinline__ float edge_threshold(float lo, float w, int bthr, flo
   return keep_threshold(edge - slack, E, clamp);
 }
 
-// all lanes, each for its own row: highest bin with >= k entries at or above it (-1 when the row has fewer than k binned
-// entries).  Walks down from the top bin; the warp stops when every lane has its answer.
-__device__ __forceinline__ int hist_threshold_bin(uint32_t hrow, int k) {
-  static_assert(NBINS % 16 == 0, "scanned in chunks of 16 bins");
-  int cum = 0, found = -1;
-#pragma unroll 1
-  for (int c = NBINS / 16 - 1; c >= 0; --c) {
-    uint32_t v[16];  // 16 independent loads in flight (a bin-by-bin walk pays the shared-memory latency 48 times: ~2500 cycles)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = lds_u32_volatile(hrow + 4u * (uint32_t)(c * 16 + j));
-#pragma unroll
-    for (int j = 15; j >= 0; --j) {
-      cum += (int)v[j];
-      if (found < 0 && cum >= k) found = c * 16 + j;
-    }
-    if (__all_sync(0xffffffffu, found >= 0)) break;
-  }
-  return found;
-}
-
-// warp-wide drain of the per-lane queues (all lanes must call; cq may differ per lane): appends the queued survivors that
-// still pass the row's threshold to the lane's list and counts them in the row's histogram (fire-and-forget red.shared),
-// then re-derives the row's threshold from the histogram and publishes it.  Returns the new list length.
+// warp-wide drain of the per-lane queues (all lanes must call; st.cq may differ per lane).  Iterations are
+// independent of each other -- fire-and-forget histogram increments (red.shared), list stores that nobody waits
+// for, threshold fixed for the duration -- so they pipeline; the threshold advances once at the end.
+struct DrainRet { float thr; int cnt, bthr, A; };
 // (out of line, state by value in registers: inlining it at every call site costs registers in the tile loop)
-struct DrainRet { float thr; int cnt; };
-__device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float lo, float w, float inv_w, float E, int cnt, int cq,
-                                                 uint32_t queue, float2* buf, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
+__device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float lo, float w, float inv_w, float E, int cnt, int cq, int bthr, int A,
+                                                 uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
   int maxq = cq;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, o));
@@ -184,131 +244,117 @@ __device__ __noinline__ DrainRet drain_queues_nl(float thr, float thr_ext, float
     const bool ok = (s < cq) && (e.x >= thr);
     const bool okh = ok && (e.x >= lo);
     const int b = (int)fminf(fmaxf((e.x - lo) * inv_w, 0.f), (float)(NBINS - 1));
-    const int st_ok = ok && (cnt < CAPG);
+    const int st_ok = ok && (cnt < CAP);
     asm volatile(
         "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.s32 p, %0, 0;\n\t"
         "setp.ne.s32 q, %1, 0;\n\t"
         "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
-        "@q red.shared.add.u32 [%5], 1;\n\t}"
-        ::"r"(st_ok), "r"((int)okh), "l"(buf + cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)b)
+        "@q red.shared.add.u32 [%5], %6;\n\t"
+        "@q red.shared.max.u32 [%7], %8;\n\t}"
+        ::"r"(st_ok), "r"((int)okh), "l"(buf + cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)(b >> 1)),
+          "r"(1u << ((b & 1) * 16)), "r"(hrow + 4u * (uint32_t)(NBINS / 2)), "r"(f2key(e.x))
         : "memory");
     cnt += ok ? 1 : 0;
+    A += (okh && b >= bthr) ? 1 : 0;
   }
   __syncwarp();
-  if (maxq > 0) {  // warp-uniform: something may have been counted (queues only fill once the row state is live: lo is finite)
-    const int bthr = hist_threshold_bin(hrow, k);
-    if (bthr >= 0) {
-      const float t = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
-      if (t > thr && thr < INFINITY) {
-        thr = t;
-        asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
-      }
-    }
+  bool moved = false;
+  while (bthr < NBINS - 1) {
+    const int hb = hist_get_s(hrow, bthr);
+    if (A - hb < k) break;
+    A -= hb;
+    ++bthr;
+    moved = true;
   }
+  if (moved) thr = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
   DrainRet r;
-  r.thr = thr; r.cnt = cnt;
+  r.thr = thr; r.cnt = cnt; r.bthr = bthr; r.A = A;
   return r;
 }
-// Per-tile share of the list maintenance: every lane moves (at most) the newest entry of its queue to its list, branch-free.  In
-// steady state a lane queues a survivor every ~10 tiles, so this keeps the queues near empty at a FIXED cost per tile -- the
-// accumulator buffers are handed back only when all epilogue warps (of both CTAs of a pair) are through with them, so a warp that
-// every ~50 tiles spends a whole tile period in a full drain stalls the MMA threads and every other warp with it.
-__device__ __forceinline__ void pop_one(RowState& st, uint32_t queue, float2* buf, uint32_t hrow) {
-  const bool has = st.cq > 0;
-  const float2 e = lds_f2(queue + 8u * (uint32_t)max(st.cq - 1, 0));
-  const bool ok = has && (e.x >= st.thr);
-  const bool okh = ok && (e.x >= st.lo);
-  const int b = (int)fminf(fmaxf((e.x - st.lo) * st.inv_w, 0.f), (float)(NBINS - 1));
-  const int st_ok = ok && (st.cnt < CAPG);
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.s32 p, %0, 0;\n\t"
-      "setp.ne.s32 q, %1, 0;\n\t"
-      "@p st.global.cg.v2.f32 [%2], {%3, %4};\n\t"
-      "@q red.shared.add.u32 [%5], 1;\n\t}"
-      ::"r"(st_ok), "r"((int)okh), "l"(buf + st.cnt), "f"(e.x), "f"(e.y), "r"(hrow + 4u * (uint32_t)b)
-      : "memory");
-  st.cnt += ok ? 1 : 0;
-  st.cq -= has ? 1 : 0;
-}
-// the row's threshold from its histogram (warp-collective), published when it rose
-__device__ __noinline__ float refresh_threshold(float thr, float thr_ext, float lo, float w, float E, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
-  const int bthr = hist_threshold_bin(hrow, k);
-  if (bthr >= 0) {
-    const float t = fmaxf(edge_threshold(lo, w, bthr, E, clamp), thr_ext);
-    if (t > thr && thr < INFINITY) {
-      thr = t;
-      asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
-    }
-  }
-  return thr;
-}
-__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, uint32_t thr_slot, int k, int clamp) {
-  const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, queue, buf, hrow, thr_slot, k, clamp);
-  st.thr = r.thr; st.cnt = r.cnt;
+__device__ __forceinline__ void drain_queues(RowState& st, uint32_t queue, float2* buf, uint32_t hrow, int k, int clamp) {
+  const DrainRet r = drain_queues_nl(st.thr, st.thr_ext, st.lo, st.w, st.inv_w, st.E, st.cnt, st.cq, st.bthr, st.A, queue, buf, hrow, k, clamp);
+  st.thr = r.thr; st.cnt = r.cnt; st.bthr = r.bthr; st.A = r.A;
   st.cq = 0;
 }
 
-// dense-score dump of one 32-column slice (bring-up / error-bound tests and tmf_score_dense_*)
-__device__ __forceinline__ void dump_chunk(const uint32_t (&r)[32], int col0, int n_items, bool valid, long long row, const TopkParams& p) {
-  if (valid) {
+// One 32-column slice of a row's accumulator BEFORE the row's threshold exists (first 3 tiles): every column is
+// appended directly.  (Clamp-mode "filler" items -- the k <= 128 lowest ids -- therefore need no special case.)
+template <bool DUMP>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], int col0, int n_items, bool tail_tile, bool valid, bool warp_inited,
+                                               RowState& st, uint32_t queue, float2* buf, uint32_t hrow, long long row,
+                                               const TopkParams& p) {
+  if (DUMP) {
+    if (valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < n_items) p.dump[row * p.dump_ld + col0 + j] = __uint_as_float(r[j]);
+    }
+    return;
+  }
+  if (TMF_DBG(p) == 2 || TMF_DBG(p) == 3) return;
+  const int id0 = p.item_offset + col0;
+  if (!warp_inited) {  // warp-uniform: no threshold yet, keep everything (coalesced per lane, no queue)
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < n_items) {
+          __stcg(buf + st.cnt, make_float2(__uint_as_float(r[j]), __int_as_float(id0 + j)));
+          ++st.cnt;
+        }
+      }
+    }
+    return;
   }
 }
 
-// hit bits of the two 8-column groups of one 16-column chunk: group maximum (3-input max tree, no branches) >= threshold
-__device__ __forceinline__ unsigned chunk_hits(const uint32_t (&r)[16], float thr) {
-  unsigned hm = 0;
+// 8-column group maxima of one 32-column slice (3-input max tree, no branches)
+__device__ __forceinline__ void group_max4(const uint32_t (&r)[32], float* m8) {
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < 4; ++g) {
     const float a = fmaxf(fmaxf(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
     const float b = fmaxf(fmaxf(a, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
     const float c = fmaxf(fmaxf(b, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
-    hm |= (fmaxf(c, __uint_as_float(r[8 * g + 7])) >= thr) ? (1u << g) : 0u;
+    m8[g] = fmaxf(c, __uint_as_float(r[8 * g + 7]));
   }
-  return hm;
 }
 
-// Steady-state filter of one group's QUARTER of a tile (64 of the accumulator buffer's 256 columns).  Pass 1
-// streams the 64 columns through registers once -- four x16 loads issued back to back, ONE wait -- and keeps only the 8
-// group-maximum hit bits: no votes, no branches.  One REDUX.OR of the per-lane hit masks then names the 8-column groups in which
-// ANY row of the warp has a survivor; only those are re-read from TMEM (x8) and their survivors queued with predicated stores,
-// all lanes convergent.
-__device__ __forceinline__ void tmem_ld_wait_for16x4(uint32_t (&a)[16], uint32_t (&b)[16], uint32_t (&c)[16], uint32_t (&d)[16]) {
-  tmem_ld_wait_for16x2(a, b);   // the first wait::ld completes all four loads; the second pins c and d behind a wait as well
-  tmem_ld_wait_for16x2(c, d);
-}
-__device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
-                                              uint32_t thr_slot, const TopkParams& p) {
-  uint32_t ra[16], rb[16], rc[16], rd[16];
+// Steady-state filter of one 64-column HALF of an accumulator tile (rows with a threshold).  Pass 1 brings the 64 columns into
+// registers (two x32 TMEM loads, one wait) and reduces them to 8 group-maximum hit bits -- no votes, no branches.  One REDUX.OR
+// of the per-lane hit masks then names the 8-column groups in which ANY row of the warp has a survivor (about 2 of 8 at 1M items).
+// Pass 2 queues those groups' survivors with predicated stores, all lanes convergent, STRAIGHT FROM THE REGISTERS of pass 1: the
+// loop over the groups is unrolled, so every hit group is its own warp-uniform block with static register indices.  (Round 1
+// re-read each hit group from TMEM: ~4.6 serialised ~300-cycle round trips per tile and warp, with 4 epilogue warps per CTA
+// nothing hides them.)  Only when some lane's queue could overflow are the groups re-read one at a time with drains in between.
+__device__ __forceinline__ void epilogue_half(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
+                                              const TopkParams& p) {
+  uint32_t ra[32], rb[32];
+  float m8[4];
   const float thr = st.thr;  // invalid rows carry thr = +inf; NaN-padded columns never win a max or a compare
-  tmem_ld16(t_base, ra);
-  tmem_ld16(t_base + 16u, rb);
-  tmem_ld16(t_base + 32u, rc);
-  tmem_ld16(t_base + 48u, rd);
-  tmem_ld_wait_for16x4(ra, rb, rc, rd);
-  if (TMF_DBG(p) == 5) return;  // diagnostic: accumulator reads only
-  const unsigned hm = chunk_hits(ra, thr) | (chunk_hits(rb, thr) << 2) | (chunk_hits(rc, thr) << 4) | (chunk_hits(rd, thr) << 6);
+  unsigned hm = 0;
+  tmem_ld32(t_base, ra);
+  tmem_ld32(t_base + 32u, rb);
+  tmem_ld_wait_for(ra);   // wait::ld covers both loads; the second call pins rb behind a wait as well
+  tmem_ld_wait_for(rb);
+  group_max4(ra, m8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (1u << g) : 0u;
+  group_max4(rb, m8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) hm |= (m8[g] >= thr) ? (16u << g) : 0u;
   unsigned gmask = __reduce_or_sync(0xffffffffu, hm);
   if (TMF_DBG(p) == 1) gmask = 0;
-  const int id0 = p.item_offset + col0;
   if (gmask == 0) return;
-  // Pass 2, common case: every lane's queue has room for all it can add (8 per hit group of its own row), so the survivors are
-  // pushed straight from the registers pass 1 holds -- the loop is unrolled, each hit group is its own warp-uniform block with
-  // static register indices, no call sites (nothing is live across a call) and no second accumulator read (each of those cost a
-  // serialised ~300-cycle round trip while the MMA threads wait for the buffer).
-  if (__all_sync(0xffffffffu, st.cq + 8 * __popc(hm) <= QCAP)) {
+  const int id0 = p.item_offset + col0;
+#if TMF_PASS2_REGS
+  if (__all_sync(0xffffffffu, st.cq + 8 * __popc(hm) <= QCAP)) {  // every lane's queue has room for all it can add
     int cq = st.cq;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       if (gmask & (1u << g)) {  // warp-uniform
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int e = (g & 1) * 8 + j;
-          const float x = __uint_as_float(g < 2 ? ra[e] : g < 4 ? rb[e] : g < 6 ? rc[e] : rd[e]);
+          const float x = __uint_as_float(g < 4 ? ra[8 * g + j] : rb[8 * (g & 3) + j]);
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
                        ::"f"(x), "f"(thr), "r"(queue + 8u * (uint32_t)cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
           cq += (x >= thr) ? 1 : 0;
@@ -318,13 +364,13 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowStat
     st.cq = cq;
     return;
   }
-  // some lane may overflow its queue: re-read the hit groups from TMEM one at a time, draining the queues in between
+#endif
   while (gmask) {  // warp-uniform
     const int g = __ffs(gmask) - 1;
     gmask &= gmask - 1;
     uint32_t v[8];
     tmem_ld8(t_base + (uint32_t)(8 * g), v);
-    if (__any_sync(0xffffffffu, st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
+    if (__any_sync(0xffffffffu, st.cq > QCAP - 8)) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
     tmem_ld_wait_for8(v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -334,6 +380,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowStat
       st.cq += (x >= thr) ? 1 : 0;
     }
   }
+}
+__device__ __forceinline__ void epilogue_tile(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
+                                              const TopkParams& p) {
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h)  // one copy of the code: the unrolled pass 2 is ~4 KB of sparsely executed instructions
+    epilogue_half(t_base + (uint32_t)(64 * h), col0 + 64 * h, st, queue, buf, hrow, p);
 }
 
 // exact k-th largest approximate score of a row's list (n entries in global memory, streamed through L2) by an
@@ -401,13 +453,27 @@ __device__ __noinline__ float warp_select_kth(const float2* buf, int n, int k, i
   return key2f(prefix);
 }
 
-// Warp-cooperative compaction of one (row, group) list that is about to fill: entries below the row's current threshold
-// (they can no longer be in the answer) are dropped in place, in ONE streaming pass (clamp mode also keeps the k lowest item
-// ids: the zero-score fillers).  The histogram is not touched: dropped entries sit below the threshold bin, which the
-// threshold scan never reaches again.  Returns the new length (all lanes).
-__device__ __noinline__ int warp_compact_row(float2* buf, int n, float thr, int k, int clamp, int item_offset) {
+// Warp-cooperative (re)build of one row's threshold state from its list of n (<= CAP) entries, streamed from L2:
+// exact k-th largest by radix select, histogram re-centred on [kth, kth + 4 (max - kth)), list compacted in place
+// against the new threshold (clamp mode also keeps the k lowest item ids).  Used once when a row has seen its first
+// 3 tiles and again whenever its list is about to saturate, so a badly placed histogram range heals itself.
+// Results in out[0..5] (shared memory): lo, w, inv_w, bthr, A, n_new.
+__device__ __noinline__ void warp_rebuild_row(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
+                                              int* radix, float* out) {
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  float mx;
+  const float kth = warp_select_kth(buf, n, k, radix, mx);
+  float W = 4.0f * (mx - kth);
+  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(kth), 1.0f) * 1e-3f;
+  const float lo = kth;
+  const float w = W / (float)NBINS;
+  const float inv_w = (float)NBINS / W;
+  const float thr = keep_threshold(kth, E, clamp);  // exact k-th: the tightest valid threshold
+  // ---- compact in place against thr and rebuild the histogram from the kept entries >= lo
+  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
+  __syncwarp();
+  if (lane == 0) hrow[NBINS / 2] = f2key(mx);
   int base = 0;
   for (int b0 = 0; b0 < n; b0 += 32 * 8) {
     float2 x[8];
@@ -422,54 +488,243 @@ __device__ __noinline__ int warp_compact_row(float2* buf, int n, float thr, int 
       const int e = b0 + 32 * t + lane;
       const bool keep = e < n && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
-      if (keep) __stcg(buf + base + __popc(bal & lt), x[t]);
+      if (keep) {
+        __stcg(buf + base + __popc(bal & lt), x[t]);
+        if (x[t].x >= lo) {
+          const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
+        }
+      }
       base += __popc(bal);
     }
     __syncwarp();
   }
-  return base;
+  if (lane == 0) {
+    // highest bin with at least k entries at or above it (bin 0 qualifies: >= k entries are >= kth)
+    int A = 0, bthr = 0;
+    for (int b = NBINS - 1; b >= 0; --b) {
+      A += hist_get(hrow, b);
+      if (A >= k) { bthr = b; break; }
+    }
+    out[0] = lo; out[1] = w; out[2] = inv_w; out[3] = __int_as_float(bthr); out[4] = __int_as_float(A);
+    out[5] = __int_as_float(base);
+  }
+  __syncwarp();
+}
+
+// all lanes: highest bin with at least k entries at or above it (bin 0 qualifies whenever >= k entries are >= lo).
+// Lane L owns histogram word L (bins 2L, 2L+1); a suffix scan over the lanes replaces a 48-step serial walk.
+__device__ __forceinline__ void finish_rebuild(const uint32_t* hrow, int k, float lo, float w, float inv_w, int n_new, float* out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t word = lane < NBINS / 2 ? hrow[lane] : 0u;
+  const int c0 = (int)(word & 0xffffu), c1 = (int)(word >> 16);
+  int incl = c0 + c1;  // entries in bins >= 2 * lane after the scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += v;
+  }
+  const int at_hi = incl - c0;  // entries in bins >= 2 * lane + 1
+  const unsigned hit_hi = __ballot_sync(0xffffffffu, at_hi >= k);
+  const unsigned hit_lo = __ballot_sync(0xffffffffu, incl >= k);
+  int bthr = 0, A = __shfl_sync(0xffffffffu, incl, 0);
+  const int Lh = hit_hi ? 31 - __clz(hit_hi) : -1, Ll = hit_lo ? 31 - __clz(hit_lo) : -1;
+  if (Lh >= 0 && 2 * Lh + 1 >= 2 * Ll) {
+    bthr = 2 * Lh + 1;
+    A = __shfl_sync(0xffffffffu, at_hi, Lh);
+  } else if (Ll >= 0) {
+    bthr = 2 * Ll;
+    A = __shfl_sync(0xffffffffu, incl, Ll);
+  }
+  if (lane == 0) {
+    out[0] = lo; out[1] = w; out[2] = inv_w; out[3] = __int_as_float(bthr); out[4] = __int_as_float(A);
+    out[5] = __int_as_float(n_new);
+  }
+}
+
+// ---- FIRST (re)build of a row (n <= INIT_N entries), entirely in registers.  The entries are loaded once (CPL per lane,
+// one L2 round trip) and bucketed linearly over [min, max] into 256 shared-memory counters -- low contention, where the
+// radix passes of warp_select_kth pile most keys onto one exponent bucket; the bucket holding the k-th largest is
+// re-bucketed once over its own [min, max].  The smallest member of the final bucket is the bound: by construction at
+// least k entries are >= it, and it lies within 2^-16 of the score range of the exact k-th.  ~400 instructions per row
+// where the four streaming radix passes took ~42 k cycles (25 % of a 125k-item sweep, measured with TMF_TOPK_PROF).
+// Outputs as warp_rebuild_row; word NBINS/2 of the histogram row receives the key of the row maximum.
+__device__ __noinline__ void warp_rebuild_first(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
+                                                int* cnt256, float* out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  float2 x[CPL];
+#pragma unroll
+  for (int t = 0; t < CPL; ++t) {
+    const int e = lane + 32 * t;
+    x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+  }
+  unsigned mem = 0;  // bit t: entry t can still be the k-th largest
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < CPL; ++t) {
+    if (lane + 32 * t < n) { mem |= 1u << t; mn = fminf(mn, x[t].x); mx = fmaxf(mx, x[t].x); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const float row_max = mx;
+  float lo_b = mn, hi_b = mx;
+  int krem = min(k, n);
+#pragma unroll 1
+  for (int level = 0; level < 2 && hi_b > lo_b; ++level) {
+    const float scale = 256.0f / (hi_b - lo_b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt256[lane * 8 + i] = 0;
+    __syncwarp();
+    int bk[CPL];
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      bk[t] = (int)fminf(fmaxf((x[t].x - lo_b) * scale, 0.f), 255.f);
+      if ((mem >> t) & 1u) smem_inc(&cnt256[bk[t]]);
+    }
+    __syncwarp();
+    int c[8];
+    int lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // lane L owns buckets 255-8L .. 248-8L, visited in descending order
+      c[i] = cnt256[255 - 8 * lane - i];
+      lsum += c[i];
+    }
+    int incl = lsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned reach = __ballot_sync(0xffffffffu, incl >= krem);
+    const int F = reach ? __ffs(reach) - 1 : 31;  // reach != 0: the members number >= krem
+    int bin = 0, knew = 1;
+    if (lane == F) {
+      int cum = incl - lsum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (cum + c[i] >= krem) { bin = 255 - 8 * lane - i; knew = krem - cum; break; }
+        cum += c[i];
+      }
+    }
+    bin = __shfl_sync(0xffffffffu, bin, F);
+    krem = __shfl_sync(0xffffffffu, knew, F);
+    float nlo = INFINITY, nhi = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < CPL; ++t) {
+      if (((mem >> t) & 1u) && bk[t] == bin) { nlo = fminf(nlo, x[t].x); nhi = fmaxf(nhi, x[t].x); }
+      else mem &= ~(1u << t);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nlo = fminf(nlo, __shfl_xor_sync(0xffffffffu, nlo, o));
+      nhi = fmaxf(nhi, __shfl_xor_sync(0xffffffffu, nhi, o));
+    }
+    lo_b = nlo; hi_b = nhi;
+    __syncwarp();
+  }
+  const float kth = lo_b;  // >= k entries are >= kth
+  float W = 4.0f * (row_max - kth);
+  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(kth), 1.0f) * 1e-3f;
+  const float lo = kth;
+  const float w = W / (float)NBINS;
+  const float inv_w = (float)NBINS / W;
+  const float thr = keep_threshold(kth, E, clamp);
+  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
+  __syncwarp();
+  if (lane == 0) hrow[NBINS / 2] = f2key(row_max);
+  int base = 0;
+#pragma unroll
+  for (int t = 0; t < CPL; ++t) {
+    const bool keep = (lane + 32 * t < n) && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      __stcg(buf + base + __popc(bal & lt), x[t]);
+      if (x[t].x >= lo) {
+        const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
+      }
+    }
+    base += __popc(bal);
+  }
+  __syncwarp();
+  finish_rebuild(hrow, k, lo, w, inv_w, base, out);
+  __syncwarp();
+}
+
+// ---- SATURATION rebuild of a row whose histogram is live: ONE streaming pass.  The current bin edge is already a valid
+// lower bound of the k-th largest, so no selection is needed: the list is compacted against the current threshold and the
+// kept entries are re-binned into a histogram re-centred on [edge, edge + 2 (row max - edge)) -- finer bins, hence a tighter
+// running threshold from here on.  (The select-based rebuild streamed the ~2000 entries five times.)
+__device__ __noinline__ void warp_rebuild_saturated(float2* buf, int n, int k, int clamp, int item_offset, float E, uint32_t* hrow,
+                                                    float lo_old, float w_old, int bthr_old, float thr_floor, float* out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const float slack = 4e-7f * (fabsf(lo_old) + (float)NBINS * w_old);
+  const float edge = lo_old + (float)bthr_old * w_old - slack;   // >= k entries are >= edge (histogram invariant)
+  const float row_max = key2f(hrow[NBINS / 2]);
+  const float thr = fmaxf(keep_threshold(edge, E, clamp), thr_floor);
+  float W = 2.0f * (row_max - edge);
+  if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(edge), 1.0f) * 1e-3f;
+  const float lo = edge;
+  const float w = W / (float)NBINS;
+  const float inv_w = (float)NBINS / W;
+  __syncwarp();
+  for (int i = lane; i < HSTRIDE; i += 32) hrow[i] = 0u;
+  __syncwarp();
+  if (lane == 0) hrow[NBINS / 2] = f2key(row_max);
+  int base = 0;
+  for (int b0 = 0; b0 < n; b0 += 32 * 8) {
+    float2 x[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+    }
+    __syncwarp();  // every read of this batch precedes its writes (writes land at or below b0)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      const bool keep = e < n && (x[t].x >= thr || (clamp && __float_as_int(x[t].y) - item_offset < k));
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        __stcg(buf + base + __popc(bal & lt), x[t]);
+        if (x[t].x >= lo) {
+          const int b = (int)fminf((x[t].x - lo) * inv_w, (float)(NBINS - 1));
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(&hrow[b >> 1])), "r"(1u << ((b & 1) * 16)) : "memory");
+        }
+      }
+      base += __popc(bal);
+    }
+    __syncwarp();
+  }
+  finish_rebuild(hrow, k, lo, w, inv_w, base, out);
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ the fused kernel
-// dynamic shared memory besides the B ring: alignment slack, A tile, 320 B of barriers + TMEM slot, per-virtual-row histograms,
-// queues, published thresholds, rebuild outputs
-static size_t topk_smem_fixed_bytes(int kb) {
-  return 1024 + (size_t)kb * A_SUB_BYTES + 320 + (size_t)2 * BM * HSTRIDE * 4 + 16 + (size_t)2 * BM * 16 + (size_t)2 * BM * 8 +
-         (size_t)NGRP * 4 * 4 + (size_t)NGRP * BM * QCAP * 8;
-}
-
-// CG2: the CTAs of a 2-CTA cluster work as a pair (tcgen05 cta_group::2): CTA r scores user block 2j + r, holds its own A tile
-// and HALF of every B stage (64 of the tile's 128 items), and one M = 256 MMA issued by the leader fills both CTAs' TMEM.  A B
-// stage is then 8 KB per SM for a full tile's worth of tensor work: with one CTA per SM the stage ring is what limits the
-// pipe (measured: 4 x 16 KB stages in flight per SM and a ~1.5 us load round trip = 43 GB/s per SM, tensor pipe 33 % active).
-template <bool DUMP, bool PROF, bool CG2>
-__global__ void __launch_bounds__(TOPK_THREADS, 1)
+template <bool DUMP, bool PROF>
+__global__ void __launch_bounds__(TOPK_THREADS, 2)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_constant__ CUtensorMap tmapV, const TopkParams p) {
-  constexpr int B_STAGE = CG2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;  // bytes of a B stage in THIS CTA's shared memory
-  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs)
-  const int cta_stride = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int cta_first = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  // user blocks of this CTA: first_ub, first_ub + ub_step, ...   (CG2: pair j takes blocks 2j and 2j + 1)
-  const int first_ub = CG2 ? 2 * cta_first + (int)crank : cta_first;
-  const int ub_step = CG2 ? 2 * cta_stride : cta_stride;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve (1024-byte aligned operand tiles first)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] 16-bit
-  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // nstages x [BN (CG2: BN/2)][64] 16-bit
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.nstages * B_STAGE);
-  uint64_t* full_bar = bars;                        // [MAX_STAGES]
-  uint64_t* empty_bar = bars + MAX_STAGES;          // [MAX_STAGES]
-  uint64_t* a_full = bars + 2 * MAX_STAGES;         // [1]
-  uint64_t* a_empty = a_full + 1;                   // [1]
-  uint64_t* tfull = a_empty + 1;                    // [NBUF]
-  uint64_t* tempty = tfull + NBUF;                  // [NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NBUF);
-  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(bars + 40);                  // [2][BM][HSTRIDE] per-row score histograms (by user-block parity)
-  float4* rowp = reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(hist_rows + 2 * BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [2][BM] (lo, w, 1/w, -)
-  uint2* thr_sh = reinterpret_cast<uint2*>(rowp + 2 * BM);                       // [2][BM] (threshold key, user block it belongs to)
-  int* done_sh = reinterpret_cast<int*>(thr_sh + 2 * BM);                        // [NGRP][4] last user block each epilogue warp has finished
-  float2* queues = reinterpret_cast<float2*>(done_sh + NGRP * 4);                // [NGRP * BM][QCAP]
+  unsigned char* sA = smem;                                   // kb sub-tiles of [128][64] bf16
+  unsigned char* sB = sA + p.kb * A_SUB_BYTES;                // NSTAGES x [BN][64] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + NSTAGES * B_STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [NSTAGES]
+  uint64_t* empty_bar = bars + NSTAGES;       // [NSTAGES]
+  uint64_t* a_full = bars + 2 * NSTAGES;      // [1]
+  uint64_t* a_empty = a_full + 1;             // [1]
+  uint64_t* tfull = a_empty + 1;              // [2]
+  uint64_t* tempty = tfull + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint32_t* hist_rows = reinterpret_cast<uint32_t*>(tmem_slot + 4);             // [BM][HSTRIDE] per-row score histograms
+  float2* queues = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(hist_rows + BM * HSTRIDE) + 15) & ~(uintptr_t)15);  // [BM][QCAP]
+  float* init_out = reinterpret_cast<float*>(queues + BM * QCAP);  // [4 warps][8]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto now = [] () -> long long { return PROF ? clock64() : 0ll; };  // cycle counters only in the profiling build
@@ -479,348 +734,236 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapV) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.nstages; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
     mbar_init(smem_u32(a_full), 1);
-    mbar_init(smem_u32(a_empty), 2);  // both MMA-issuing threads commit it
-    for (int s = 0; s < NBUF; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), (CG2 ? 2 : 1) * 4); }  // tempty: ONE arrival per epilogue warp (of both CTAs): 32 per-lane arrivals on one barrier word serialise (~300 cycles per warp and tile)
+    mbar_init(smem_u32(a_empty), 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull[s]), 1); mbar_init(smem_u32(&tempty[s]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {  // TMEM: all 512 columns = four 128x128 fp32 accumulators (one CTA per SM)
-    if constexpr (CG2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+  if (warp == 2) {  // TMEM: 256 columns = two 128x128 fp32 accumulators (the SM's other CTA takes the other half)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * BM; i += TOPK_THREADS) thr_sh[i] = make_uint2(0u, 0xffffffffu);
-  if (threadIdx.x < NGRP * 4) done_sh[threadIdx.x] = -1;
   tcgen05_fence_before();
   __syncthreads();
-  if constexpr (CG2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    // The B stages form TWO rings of nstages / 2: ring r carries the tiles nt % 2 == r, the tiles of MMA thread r.  With one ring and
-    // two consumers that each skip the other's stages, a consumer that is held up (its epilogue group is busy) could be lapped
-    // twice by the ring and would then mistake a later phase of a stage's barrier for the one it waits for.
     if (lane == 0) {
-      const int hs = p.nstages >> 1;
-      int st_r[2] = {0, 0};
-      uint32_t ph_r[2] = {0, 0};
-      uint32_t a_phase = 0;
-      for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
         long long t0 = now();
-        mbar_wait_ctrl(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
+        mbar_wait(smem_u32(a_empty), a_phase ^ 1);  // previous user block's MMAs retired
         long long w_empty = 0, w_aempty = now() - t0;
-        if (!CG2 || crank == 0) mbar_expect_tx(smem_u32(a_full), (CG2 ? 2 : 1) * p.kb * A_SUB_BYTES);  // the pair's A tiles complete on the leader's barrier
-        for (int kb = 0; kb < p.kb; ++kb) {
-          if constexpr (CG2) tma_load_2d_cg2(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
-          else tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
-        }
+        mbar_expect_tx(smem_u32(a_full), p.kb * A_SUB_BYTES);
+        for (int kb = 0; kb < p.kb; ++kb)
+          tma_load_2d(smem_u32(sA + kb * A_SUB_BYTES), &tmapU, kb * BK, (p.ub0 + ub) * BM, smem_u32(a_full));
         a_phase ^= 1;
         for (int nt = 0; nt < p.n_tiles; ++nt) {
-          const int r = nt & 1;
-          int rs = r ? st_r[1] : st_r[0];
-          uint32_t phase = r ? ph_r[1] : ph_r[0];
           for (int kb = 0; kb < p.kb; ++kb) {
-            const int stage = r * hs + rs;
             t0 = now();
-            mbar_wait_ctrl(smem_u32(&empty_bar[stage]), phase ^ 1);
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             w_empty += now() - t0;
-            if (TMF_DBG(p) == 3) {  // diagnostic: no B loads at all (MMAs read whatever the stage holds)
-              if (!CG2 || crank == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-            } else if constexpr (CG2) {  // this CTA's half of the tile (items nt * 128 + 64 * rank ...), bytes of both halves land on the leader's barrier
-              if (crank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
-              tma_load_2d_cg2(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN + (int)crank * (BN / 2), smem_u32(&full_bar[stage]));
-            } else {
-              mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
-              tma_load_2d(smem_u32(sB + stage * B_STAGE), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
-            }
-#if TMF_PF_TILES > 0
-            if (nt + TMF_PF_TILES < p.n_tiles)  // warm the L2 for a tile further down the sweep (no shared memory needed)
-              asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmapV), "r"(kb * BK), "r"((nt + TMF_PF_TILES) * BN) : "memory");
-#endif
-            if (++rs == hs) { rs = 0; phase ^= 1; }
+            mbar_expect_tx(smem_u32(&full_bar[stage]), B_STAGE_BYTES);
+            tma_load_2d(smem_u32(sB + stage * B_STAGE_BYTES), &tmapV, kb * BK, nt * BN, smem_u32(&full_bar[stage]));
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
-          if (r) { st_r[1] = rs; ph_r[1] = phase; } else { st_r[0] = rs; ph_r[0] = phase; }
         }
         if (PROF) { atomicAdd(p.prof + 0, (unsigned long long)w_empty); atomicAdd(p.prof + 1, (unsigned long long)w_aempty); }
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ===================== MMA issuers (CG2: of the leader CTA only) =====================
-    // TWO issuing threads (warps 1 and 3, on different SM sub-partitions): thread r issues the tiles nt % 2 == r (accumulator
-    // buffers r and r + 2) from its own stage ring.  One thread needs ~150 cycles per tcgen05.mma (descriptor arithmetic, the moves
-    // into the uniform registers the instruction reads, the issue itself -- measured: a single issuer spent 77 % of its time
-    // issuing with the tensor pipe 33 % active) against 64 cycles of execution, so one issuer starves the pipe.  Both threads
-    // commit the end-of-block "A tile free" barrier (count 2).
-    if (lane == 0 && crank == 0) {
-      const int issuer = warp == 1 ? 0 : 1;
-      const int hs = p.nstages >> 1;
-      int rs = 0;  // position in this thread's stage ring
-      uint32_t phase = 0, a_phase = 0;
-      uint32_t acc_bits = 0;  // bit a = parity of the number of times accumulator a has been filled
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, a_phase = 0;
       // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
-      constexpr uint32_t kId = umma_idesc_bf16(CG2 ? 2 * BM : BM, BN);
-      const uint32_t idesc = f16 ? (kId & ~((1u << 7) | (1u << 10))) : kId;
-      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));  // + (byte offset >> 4) selects a sub-tile / k-slice (no carry out of the 14-bit field)
-      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
-      for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step) {
-        mbar_wait_ctrl(smem_u32(a_full), a_phase);
+      const uint32_t idesc = f16 ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;
+      for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+        mbar_wait(smem_u32(a_full), a_phase);
         a_phase ^= 1;
         long long w_tempty = 0, w_full = 0;
-        const long long cb = now();
-        for (int nt = issuer; nt < p.n_tiles; nt += 2) {
-          const int acc = nt & (NBUF - 1);
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
           long long t0 = now();
-          mbar_wait_ctrl(smem_u32(&tempty[acc]), ((acc_bits >> acc) & 1u) ^ 1u);  // the group drained this accumulator's previous tile
+          mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
           w_tempty += now() - t0;
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
-            const int stage = issuer * hs + rs;
             t0 = now();
-            mbar_wait_ctrl(smem_u32(&full_bar[stage]), phase);
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
             w_full += now() - t0;
             tcgen05_fence_after();
-            const uint64_t a_desc = a_desc0 + (uint64_t)((kb * A_SUB_BYTES) >> 4);
-            const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE) >> 4);
+            const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
+            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              if (TMF_DBG(p) == 4 && (kb | k) != 0) continue;  // diagnostic: one MMA per tile (loads at full rate)
-              if constexpr (CG2)
-                tcgen05_mma_f16_cg2(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
-                                    (uint32_t)((kb | k) != 0));
-              else
-                tcgen05_mma_f16(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
-                                (uint32_t)((kb | k) != 0));
+              tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
+                              (uint32_t)((kb | k) != 0));
             }
-            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-            if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&empty_bar[stage])); else tcgen05_commit(smem_u32(&empty_bar[stage]));
-            if (++rs == hs) { rs = 0; phase ^= 1; }
+            tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
-          // accumulator ready for its epilogue group (of both CTAs of a pair)
-          if constexpr (CG2) tcgen05_commit_cg2(smem_u32(&tfull[acc])); else tcgen05_commit(smem_u32(&tfull[acc]));
-          acc_bits ^= 1u << acc;
+          tcgen05_commit(smem_u32(&tfull[acc]));  // accumulator ready for the epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
         }
-        if constexpr (CG2) tcgen05_commit_cg2(smem_u32(a_empty)); else tcgen05_commit(smem_u32(a_empty));  // this thread's MMAs no longer read the A tile
-        if (PROF) {
-          atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full);
-          atomicAdd(p.prof + 21, (unsigned long long)(now() - cb)); atomicAdd(p.prof + 22, (unsigned long long)((p.n_tiles - issuer + 1) / 2));
-        }
+        tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
+        if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: threshold filter + survivor queues + SIMD list maintenance =====================
-    // 16 warps = 4 groups of 4 (one warp per TMEM lane quarter).  Group g owns accumulator buffer g: it filters the tiles
-    // nt % 4 == g, 128 columns in two 64-column passes.  A buffer is handed back when the 4 warps of its group (8 in a CTA pair) are
-    // through with it and three other buffers are in flight meanwhile, so one slow warp (a queue drain, a list compaction) does not
-    // stall the MMA threads.  (Measured alternative: two 256-column buffers with all 16 warps on every tile -- each hand-over then
-    // waits for the slowest of 32 warps with one tile of slack, and the MMA threads waited for buffers half of the time.)
-    const int grp = (warp - 4) >> 2;
-    const int q = warp & 3;           // TMEM lane quarter == warp % 4
-    const int trow = q * 32 + lane;   // row of the CTA's user tile
-    const uint32_t queue = smem_u32(queues + (grp * BM + trow) * QCAP);
+    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    int* radix = reinterpret_cast<int*>(queues + q * 32 * QCAP);  // radix-select scratch aliases the warp's (empty) queues
+    const uint32_t hrow = smem_u32(hist_rows + (q * 32 + lane) * HSTRIDE);
+    const uint32_t queue = smem_u32(queues + (q * 32 + lane) * QCAP);
+    float* iout = init_out + q * 8;
     const int n_items = (int)p.n_items;
-    uint32_t acc_phase = 0;  // parity of the number of tiles this group has consumed
-    int n_ub = 0;            // user blocks this CTA has started: parity selects the histogram / threshold buffers
-    for (int ub = first_ub; ub < p.n_ublocks; ub += ub_step, ++n_ub) {
-      const int par = n_ub & 1;
-      const uint32_t hrow = smem_u32(hist_rows + (par * BM + trow) * HSTRIDE);
-      const uint32_t thr_slot = smem_u32(thr_sh + par * BM + trow);  // .x = threshold key, .y = tag
-      const long long lrow = (long long)ub * BM + trow;                // batch-local row (candidate buffers)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
+      const long long lrow = (long long)ub * BM + q * 32 + lane;       // batch-local row (candidate buffers)
       const long long row = (long long)p.ub0 * BM + lrow;              // global row
       const bool valid = row < p.n_users;
       RowState st;
       st.thr = valid ? -INFINITY : INFINITY;
-      st.lo = INFINITY; st.w = 0.f; st.inv_w = 0.f;
+      st.lo = 0.f; st.w = 0.f; st.inv_w = 0.f;
       st.E = p.erow[row];
-      st.cnt = 0; st.cq = 0;
+      st.cnt = 0; st.cq = 0; st.bthr = 0; st.A = 0;
+      bool warp_inited = false;
       // External bound (item-sharded scoring): B = a lower bound of the row's k-th best CANONICAL score over all
       // slabs, so a member of the global top-k has s~ >= B - E.  Clamp mode: only a positive bound says anything
-      // (with B <= 0 the zero-score fillers matter).  Such a row filters at that floor from its first tile on.
+      // (with B <= 0 the zero-score fillers matter).  When every valid row of the warp has such a floor the
+      // warm-up (3 unfiltered tiles + radix-select rebuild per row) is skipped: the rows start filtering at the
+      // floor with an idle histogram (lo = +inf); a list that still fills up heals through the usual rebuild.
       st.thr_ext = -INFINITY;
-      if (!DUMP && p.row_bound != nullptr && valid) {
-        const float B = p.row_bound[row];
-        if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
+      if (!DUMP && p.row_bound != nullptr) {
+        if (valid) {
+          const float B = p.row_bound[row];
+          if (B > -INFINITY && (!p.clamp || B > 0.f)) st.thr_ext = B - st.E;
+        }
+        if (__all_sync(0xffffffffu, !valid || st.thr_ext > -INFINITY)) {
+          warp_inited = true;
+          if (valid) st.thr = st.thr_ext;
+          st.lo = INFINITY;
+        }
       }
-      if (valid) st.thr = st.thr_ext;
-      float2* buf = p.cand + (lrow * NGRP + grp) * CAPG;
-      bool ready = false;  // this warp holds the row state of this user block (bin range, shared threshold)
-      long long w_tfull = 0, w_work = 0, w_maint = 0;
-      int n_own = 0;
-      for (int nt = grp; nt < p.n_tiles; nt += NGRP, ++n_own) {
-        const long long c0 = now();
-        mbar_wait_epi(smem_u32(&tfull[grp]), acc_phase);
-        const long long c1 = now();
-        w_tfull += c1 - c0;
-        acc_phase ^= 1u;
+      float2* buf = p.cand + lrow * CAP;
+      long long w_tfull = 0, w_work = 0, w_init = 0;
+      for (int nt = 0; nt < p.n_tiles; ++nt) {
+        long long t0 = now();
+        mbar_wait(smem_u32(&tfull[acc]), acc_phase);
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-lane spin
+        long long t1 = now();
+        w_tfull += t1 - t0;
         tcgen05_fence_after();
-        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
-        const int col0 = nt * BN;
-        if (DUMP) {
-          uint32_t ra[32];
+        const uint32_t t_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const bool tail_tile = (nt + 1) * BN > n_items;
+        if (!DUMP && warp_inited && TMF_DBG(p) < 2) {
+          epilogue_tile(t_base, nt * BN, st, queue, buf, hrow, p);
+        } else if (TMF_DBG(p) < 3) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(t_base, ra);
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
-            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
+          for (int ch = 0; ch < BN / 32; ch += 2) {
+            // chunk ch is in ra; chunk ch+1 is fetched into rb while ra is filtered (and vice versa)
             tmem_ld_wait_for(ra);
-            dump_chunk(ra, col0 + ch * 32, n_items, valid, row, p);
-          }
-        } else if (nt == 0) {
-          // ---- the row's FIRST tile (group 0): everything at or above the external floor is appended; mean and standard
-          // deviation of its 128 scores give the histogram's bin range; a second read of the (still resident) accumulator bins
-          // the appended scores.  The other groups wait for the published row before their first tile.
-          // The buffers of this parity were last used two user blocks ago: every warp of this lane quarter must be past that.
-          if (lane < NGRP)
-            while ((int)lds_u32_volatile(smem_u32(done_sh + lane * 4 + q)) < n_ub - 2) __nanosleep(64);
-          __syncwarp();
-          float mx = -INFINITY, sum = 0.f, sumsq = 0.f;
-          int nv = 0;
-          uint32_t ra[32];
-#pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
-            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
-            tmem_ld_wait_for(ra);
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const int col = col0 + ch * 32 + jj;
-              const float x = __uint_as_float(ra[jj]);
-              if (col < n_items) {
-                mx = fmaxf(mx, x);
-                sum += x;
-                sumsq = fmaf(x, x, sumsq);
-                ++nv;
-                if (valid && x >= st.thr_ext) {
-                  __stcg(buf + st.cnt, make_float2(x, __int_as_float(p.item_offset + col)));
-                  ++st.cnt;
-                }
-              }
-            }
-          }
-          {
-            // bin range [mean, mean + W): W = 6.5 standard deviations of the sample (the k-th best of 10^6 .. 10^9 Gaussian scores
-            // sits 3.7 .. 5.5 sigma above the mean), and never less than 2.5 x (sample maximum - mean) for heavy-tailed rows.  A
-            // range from the sample maximum alone is fragile: one row in ~10^5 has a sample maximum below 1 sigma, its top bin
-            // then saturates far below the k-th best score, its lists fill up and the row falls back to the exact path.
-            const float mean = nv > 0 ? sum / (float)nv : 0.f;
-            const float var = nv > 1 ? fmaxf(sumsq / (float)nv - mean * mean, 0.f) : 0.f;
-            float W = fmaxf(6.5f * sqrtf(var), 2.5f * (mx - mean));
-            if (!(W > 0.f) || !(W < 3e38f)) W = fmaxf(fabsf(mean), 1.0f) * 1e-3f;
-            st.lo = mean; st.w = W / (float)NBINS; st.inv_w = (float)NBINS / W;
-            for (int b2 = 0; b2 < HSTRIDE; ++b2) sts_u32(hrow + 4u * (uint32_t)b2, 0u);
-            rowp[par * BM + trow] = make_float4(st.lo, st.w, st.inv_w, 0.f);
-            __threadfence_block();
-            thr_sh[par * BM + trow] = make_uint2(f2key(st.thr), (uint32_t)ub);  // publishes the row: the other groups may start
-          }
-          ready = true;
-#pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
-            tmem_ld32(t_base + (uint32_t)(ch * 32), ra);
-            tmem_ld_wait_for(ra);
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) {
-              const float x = __uint_as_float(ra[jj]);
-              if (col0 + ch * 32 + jj < n_items && valid && x >= st.thr_ext && x >= st.lo) {
-                const int b2 = (int)fminf((x - st.lo) * st.inv_w, (float)(NBINS - 1));
-                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hrow + 4u * (uint32_t)b2) : "memory");
-              }
-            }
-          }
-          {
-            const int bthr = hist_threshold_bin(hrow, p.k);  // warp-collective (votes): every lane calls it, `valid` only masks the use
-            if (valid && bthr >= 0) {
-              const float t = fmaxf(edge_threshold(st.lo, st.w, bthr, st.E, p.clamp), st.thr_ext);
-              if (t > st.thr) {
-                st.thr = t;
-                asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(thr_slot), "r"(f2key(t)) : "memory");
-              }
-            }
-          }
-        } else {
-          if (!ready) {  // first own tile of this user block: wait for group 0 to publish the row, adopt its bin range
-            while (lds_u32_volatile(thr_slot + 4u) != (uint32_t)ub) __nanosleep(32);
-            __syncwarp();
-            __threadfence_block();
-            const float4 rp = rowp[par * BM + trow];
-            st.lo = rp.x; st.w = rp.y; st.inv_w = rp.z;
-            ready = true;
-          }
-          if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));  // the row's best threshold so far
-          if (TMF_DBG(p) < 2 || TMF_DBG(p) == 5) {
-            epilogue_tile(t_base, col0, st, queue, buf, hrow, thr_slot, p);
-            epilogue_tile(t_base + (uint32_t)QN, col0 + QN, st, queue, buf, hrow, thr_slot, p);
+            tmem_ld32(t_base + (uint32_t)((ch + 1) * 32), rb);
+            epilogue_chunk<DUMP>(ra, nt * BN + ch * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
+            tmem_ld_wait_for(rb);
+            if (ch + 2 < BN / 32) tmem_ld32(t_base + (uint32_t)((ch + 2) * 32), ra);
+            epilogue_chunk<DUMP>(rb, nt * BN + (ch + 1) * 32, n_items, tail_tile, valid, warp_inited, st, queue, buf, hrow, row, p);
           }
         }
-        // the buffer is drained: hand it back to the MMA thread before any list maintenance (one arrival per warp)
+        // accumulator drained: hand it back to the MMA warp before any list maintenance
         tcgen05_fence_before();
-        __syncwarp();  // every lane's accumulator reads are complete
-        if (lane == 0) {
-          if constexpr (CG2) mbar_arrive_leader(smem_u32(&tempty[grp])); else mbar_arrive(smem_u32(&tempty[grp]));
-        }
-        const long long c2 = now();
-        w_work += c2 - c1;
+        mbar_arrive(smem_u32(&tempty[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        long long t2 = now();
+        w_work += t2 - t1;
         if (!DUMP) {
-          if (ready) {
-            pop_one(st, queue, buf, hrow);
-            // threshold refresh every 16th own tile, staggered over the warps
-            if (((n_own + (warp - 4)) & 15) == 0) st.thr = refresh_threshold(st.thr, st.thr_ext, st.lo, st.w, st.E, hrow, thr_slot, p.k, p.clamp);
+          if (__any_sync(0xffffffffu, st.cq >= QCAP / 2)) {
+            const long long td = now();
+            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+            if (PROF && lane == 0) { atomicAdd(p.prof + 10, (unsigned long long)(now() - td)); atomicAdd(p.prof + 11, 1ull); }
           }
-          if (__any_sync(0xffffffffu, st.cq > QCAP / 2)) drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
-          // a list about to fill: drop what the row's threshold has overtaken
-          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && st.cnt > CAPG - 4 * QCAP);
-          if (need) {
-            drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
-            if (st.thr < INFINITY) st.thr = fmaxf(st.thr, key2f(lds_u32_volatile(thr_slot)));
-            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAPG && st.cnt > CAPG - 4 * QCAP);
+          // (re)build: the first time once a row holds INIT_N - BN entries (all valid rows of a warp get there at
+          // the same tile because everything is appended until then), later whenever a list is about to saturate
+          const bool first = !warp_inited && __any_sync(0xffffffffu, valid && st.cnt >= INIT_N - BN);
+          unsigned need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
+          if (need) {  // the radix scratch aliases the queues: empty them first (lengths may grow a little)
+            const long long tq = now();
+            drain_queues(st, queue, buf, hrow, p.k, p.clamp);
+            if (PROF && lane == 0) { atomicAdd(p.prof + 19, (unsigned long long)(now() - tq)); atomicAdd(p.prof + 18, 1ull); }
+            need = __ballot_sync(0xffffffffu, valid && st.cnt <= CAP && (first || (warp_inited && st.cnt > CAP - 4 * QCAP)));
           }
           while (need) {
             const int owner = __ffs(need) - 1;
             need &= need - 1;
             const int n_o = __shfl_sync(0xffffffffu, st.cnt, owner);
-            const float thr_o = __shfl_sync(0xffffffffu, st.thr, owner);
-            float2* obuf = p.cand + (((long long)ub * BM + q * 32 + owner) * NGRP + grp) * CAPG;
-            const int n_new = warp_compact_row(obuf, n_o, thr_o, p.k, p.clamp, p.item_offset);
+            const float E_o = __shfl_sync(0xffffffffu, st.E, owner);
+            __syncwarp();
+            float2* obuf = p.cand + ((long long)ub * BM + q * 32 + owner) * CAP;
+            uint32_t* ohist = hist_rows + (q * 32 + owner) * HSTRIDE;
+            const float lo_o = __shfl_sync(0xffffffffu, st.lo, owner);
+            const long long tr = now();
+            int which = 0;
+            if (first && n_o <= INIT_N) {
+              warp_rebuild_first(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, radix, iout);
+            } else if (lo_o < INFINITY && !first) {  // live histogram: compaction + re-centring in one pass
+              which = 1;
+              const float w_o = __shfl_sync(0xffffffffu, st.w, owner);
+              const int bthr_o = __shfl_sync(0xffffffffu, st.bthr, owner);
+              const float ext_o = __shfl_sync(0xffffffffu, st.thr_ext, owner);
+              warp_rebuild_saturated(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, lo_o, w_o, bthr_o, ext_o, iout);
+            } else {  // a bounded row (idle histogram) that filled up anyway: full selection
+              which = 2;
+              warp_rebuild_row(obuf, n_o, p.k, p.clamp, p.item_offset, E_o, ohist, radix, iout);
+            }
+            if (PROF && lane == 0) { atomicAdd(p.prof + 13 + 2 * which, (unsigned long long)(now() - tr)); atomicAdd(p.prof + 12 + 2 * which, 1ull); }
             if (lane == owner) {
-              st.cnt = n_new;
-              if (st.cnt > CAPG - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
-                st.cnt = CAPG + 1;
+              st.lo = iout[0]; st.w = iout[1]; st.inv_w = iout[2];
+              st.bthr = __float_as_int(iout[3]); st.A = __float_as_int(iout[4]);
+              st.cnt = __float_as_int(iout[5]);
+              st.thr = fmaxf(edge_threshold(st.lo, st.w, st.bthr, st.E, p.clamp), st.thr_ext);
+              if (st.cnt > CAP - 8 * QCAP) {  // cannot shrink (massive ties): hand the row to the exact path
+                st.cnt = CAP + 1;
                 st.thr = INFINITY;
               }
             }
             __syncwarp();
           }
+          if (first) warp_inited = true;
         }
-        w_maint += now() - c2;
+        w_init += now() - t2;
       }
+      if (!DUMP) drain_queues(st, queue, buf, hrow, p.k, p.clamp);
       if (PROF && lane == 0) {
         atomicAdd(p.prof + 4, (unsigned long long)w_tfull); atomicAdd(p.prof + 5, (unsigned long long)w_work);
-        atomicAdd(p.prof + 6, (unsigned long long)w_maint); atomicAdd(p.prof + 7, (unsigned long long)n_own);
+        atomicAdd(p.prof + 6, (unsigned long long)w_init); atomicAdd(p.prof + 7, 1ull);
       }
-      if (!DUMP) {
-        drain_queues(st, queue, buf, hrow, thr_slot, p.k, p.clamp);
-        const bool ovf = st.cnt > CAPG;
-        float thr_fin = st.thr;
-        if (ready && !ovf) thr_fin = fmaxf(thr_fin, key2f(lds_u32_volatile(thr_slot)));
-        p.cnt[lrow * NGRP + grp] = valid ? (ovf ? -1 : st.cnt) : 0;
-        p.thr_out[lrow * NGRP + grp] = ovf ? -INFINITY : thr_fin;
+      if (PROF) atomicAdd(p.prof + 20, (unsigned long long)(valid ? min(st.cnt, CAP) : 0));
+      const bool ovf = st.cnt > CAP;
+      if (valid && ovf) {
+        const int slot = atomicAdd(p.ovf_count, 1);
+        p.ovf_rows[slot] = (int)row;
+        if (PROF) atomicAdd(p.prof + 8, 1ull);
       }
+      p.cnt[lrow] = valid ? (ovf ? -1 : st.cnt) : 0;
+      p.thr_out[lrow] = st.thr;
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); done_sh[grp * 4 + q] = n_ub; }  // this warp no longer touches the buffers of this parity
     }
   }
 
-  tcgen05_fence_before();
   __syncthreads();
-  if constexpr (CG2) cluster_sync_all();  // the peer may still signal this CTA's barriers / read its shared memory until here
   if (warp == 2) {
-    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -921,52 +1064,31 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
   const long long lrow = (long long)blockIdx.x * RR_WARPS + w;
   if (lrow >= p.n_rows) return;
   const long long row = p.row0 + lrow;
-  // the row's candidates: one list per epilogue group of the main kernel ([row][NGRP][CAPG]); each group's final threshold is
-  // a valid keep-threshold for the whole row, so the highest one applies to all lists
-  int ng[NGRP];
-  int n = 0;
-  bool overflowed = false;
-  float thr = -INFINITY;
-#pragma unroll
-  for (int g = 0; g < NGRP; ++g) {
-    ng[g] = p.cnt[lrow * NGRP + g];
-    overflowed |= ng[g] < 0;
-    n += max(ng[g], 0);
-    thr = fmaxf(thr, p.thr[lrow * NGRP + g]);
-  }
-  if (overflowed) {  // a list saturated in the main kernel (massive ties): the exact path ranks this row
-    if (lane == 0) {
-      const int slot = atomicAdd(p.ovf_count, 1);
-      p.ovf_rows[slot] = (int)row;
-    }
-    return;
-  }
-  float2* rowbuf = const_cast<float2*>(p.cand) + lrow * CAP;
+  const int n = p.cnt[lrow];
+  if (n < 0) return;  // overflowed in the main kernel: exact_rows_kernel owns it
+  const float2* buf = p.cand + lrow * CAP;
   const int k = p.k;
   const unsigned lt = (1u << lane) - 1u;
   if (lane == 0) mbar_init(smem_u32(bar), 1);
   for (int c = lane; c < p.ld; c += 32) ud[c] = (double)p.U[row * p.ld + c];
+  float thr = p.thr[lrow];
   // ---- 1. superset by the main kernel's final threshold (or the clamp-mode filler rule)
   int m = 0;
-#pragma unroll 1
-  for (int g = 0; g < NGRP; ++g) {
-    const float2* buf = rowbuf + g * CAPG;
-    for (int b0 = 0; b0 < ng[g]; b0 += 256) {
-      float2 x[8];
+  for (int b0 = 0; b0 < n; b0 += 256) {
+    float2 x[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int e = b0 + 32 * t + lane;
-        x[t] = (e < ng[g]) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
-      }
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
+    }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int e = b0 + 32 * t + lane;
-        const bool keep = e < ng[g] && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        const int pos = m + __popc(bal & lt);
-        if (keep && pos < SEL_CAP) pr[pos] = x[t];
-        m += __popc(bal);
-      }
+    for (int t = 0; t < 8; ++t) {
+      const int e = b0 + 32 * t + lane;
+      const bool keep = e < n && (x[t].x >= thr || (p.clamp && __float_as_int(x[t].y) - p.item_offset < k));
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      const int pos = m + __popc(bal & lt);
+      if (keep && pos < SEL_CAP) pr[pos] = x[t];
+      m += __popc(bal);
     }
   }
   __syncwarp();
@@ -975,23 +1097,9 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
     float kth;
     if (m <= SEL_CAP) {
       kth = smem_select_kth(pr, m, k, radix);
-    } else {  // loose running thresholds (badly placed histograms): make the row's lists one contiguous list in place, select over it
-      int off = ng[0];
-#pragma unroll 1
-      for (int g = 1; g < NGRP; ++g) {
-        const float2* src = rowbuf + g * CAPG;
-        for (int b0 = 0; b0 < ng[g]; b0 += 32) {  // destination <= source: forward copy, reads of a batch precede its writes
-          const int e = b0 + lane;
-          const float2 x = e < ng[g] ? __ldcg(src + e) : make_float2(0.f, 0.f);
-          __syncwarp();
-          if (e < ng[g]) __stcg(rowbuf + off + e, x);
-        }
-        off += ng[g];
-        __syncwarp();
-      }
-      __threadfence_block();
+    } else {  // loose running threshold (badly placed histogram): select over the whole list in global memory
       float mx;
-      kth = warp_select_kth(rowbuf, n, k, radix, mx);
+      kth = warp_select_kth(buf, n, k, radix, mx);
     }
     thr = fmaxf(thr, keep_threshold(kth, p.erow[row], p.clamp));
     if (m <= SEL_CAP) {
@@ -1013,7 +1121,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32) rerank_kernel(const RerankParam
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int e = b0 + 32 * t + lane;
-          x[t] = (e < n) ? __ldcg(rowbuf + e) : make_float2(-INFINITY, 0.f);
+          x[t] = (e < n) ? __ldcg(buf + e) : make_float2(-INFINITY, 0.f);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -1329,8 +1437,33 @@ __global__ void row_error_kernel(const float* __restrict__ unorm_bf, const float
 }
 
 // ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
 static int make_tmap(CUtensorMap* map, void* base, long long rows, int k_pad, int box_rows) {
-  return make_tmap_k64(map, base, rows, k_pad, box_rows);
+  EncodeTiledFn enc = get_encode_fn();
+  TMF_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TMF_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
+  return TMF_OK;
 }
 
 struct TopkLayout {
@@ -1344,7 +1477,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   TopkLayout L{};
-  L.nu_pad = cdiv(n_users, 2 * BM) * (2 * BM);  // whole PAIRS of user blocks (the CTA pair of cta_group::2 takes two at a time)
+  L.nu_pad = cdiv(n_users, BM) * BM;
   L.ni_pad = cdiv(n_items, BN) * BN;
   L.batch_rows = std::min<long long>(L.nu_pad, (long long)UB_BATCH * BM);
   L.k_pad = (int)(cdiv(r, BK) * BK);
@@ -1358,8 +1491,8 @@ static TopkLayout topk_layout(long long n_users, long long n_items, int r) {
   L.off_vnorm = o; o = align_up(o + (size_t)L.ni_pad * 4, 256);
   L.off_vmax = o; o += 256;
   L.off_cand = o; o = align_up(o + (size_t)L.batch_rows * CAP * 8, 256);
-  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * NGRP * 4, 256);
-  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * NGRP * 4, 256);
+  L.off_cnt = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
+  L.off_thr = o; o = align_up(o + (size_t)L.batch_rows * 4, 256);
   L.off_ovfc = o; o += 256;
   L.off_ovfr = o; o = align_up(o + (size_t)L.nu_pad * 4, 256);
   L.scratch_rows = (int)std::min<long long>(32, n_users);
@@ -1438,12 +1571,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   CUtensorMap tmapU, tmapV;
   int rc = make_tmap(&tmapU, Ub, L.nu_pad, L.k_pad, BM);
   if (rc) return rc;
-  // CTA pairs (cta_group::2) unless switched off for an A/B (development builds only)
-  bool cg2 = true;
-#ifdef TMF_DEVTOOLS
-  { const char* e = getenv("TMF_TOPK_CG2"); if (e) cg2 = atoi(e) != 0; }
-#endif
-  rc = make_tmap(&tmapV, Vb, L.ni_pad, L.k_pad, cg2 ? BN / 2 : BN);  // a pair's CTA loads its half of every item tile
+  rc = make_tmap(&tmapV, Vb, L.ni_pad, L.k_pad, BN);
   if (rc) return rc;
 
   TopkParams p{};
@@ -1451,7 +1579,7 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   p.n_tiles = (int)(L.ni_pad / BN); p.kb = L.kb;
   p.k = k; p.clamp = clamp ? 1 : 0; p.item_offset = item_offset;
   p.erow = erow;
-  p.cand = cand; p.cnt = cnt; p.thr_out = thr;
+  p.cand = cand; p.cnt = cnt; p.thr_out = thr; p.ovf_count = ovfc; p.ovf_rows = ovfr;
   p.dump = dump; p.dump_ld = n_items;
   p.row_bound = row_bound;
   p.fmt_stats = fmt_stats; p.force_fmt = force_fmt;
@@ -1470,34 +1598,11 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   q.U = U; q.V = V; q.erow = erow; q.prof = p.prof; q.cand = cand; q.cnt = cnt; q.thr = thr; q.ovf_count = ovfc; q.ovf_rows = ovfr;
   q.out_idx = out_idx; q.out_score = out_score;
 
-  const size_t smem_max = 227 * 1024;
-  const size_t fixed = topk_smem_fixed_bytes(L.kb);
-  const size_t stage_bytes = cg2 ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-  TMF_REQUIRE(fixed + 2 * stage_bytes <= smem_max, "tmf_score_topk: shared memory exhausted (n_components too large)");
-  p.nstages = (int)std::min<size_t>(MAX_STAGES, (smem_max - fixed) / stage_bytes);
-  p.nstages &= ~1;  // two rings of nstages / 2 (even / odd item tiles)
-  const size_t smem = fixed + (size_t)p.nstages * stage_bytes;
-  auto launch_main = [&](int grid) -> int {
-    void (*kern)(const CUtensorMap, const CUtensorMap, const TopkParams);
-    if (dump != nullptr) kern = cg2 ? score_topk_kernel<true, false, true> : score_topk_kernel<true, false, false>;
-    else if (p.prof) kern = cg2 ? score_topk_kernel<false, true, true> : score_topk_kernel<false, true, false>;
-    else kern = cg2 ? score_topk_kernel<false, false, true> : score_topk_kernel<false, false, false>;
-    TMF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TOPK_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cg2 ? 2 : 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TMF_CUDA(cudaLaunchKernelEx(&cfg, kern, tmapU, tmapV, p));
-    return TMF_OK;
-  };
+  const size_t smem = 1024 + (size_t)L.kb * A_SUB_BYTES + (size_t)NSTAGES * B_STAGE_BYTES + 256 +
+                      (size_t)BM * HSTRIDE * sizeof(uint32_t) + 16 + (size_t)BM * QCAP * 8 + 4 * 8 * sizeof(float);
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TMF_CUDA(cudaFuncSetAttribute(score_topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t rr_smem = (size_t)RR_WARPS * ((size_t)ld * sizeof(double) + SEL_CAP * 8 + 32 * STG_STRIDE * 4 + 16);
   TMF_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
 
@@ -1506,10 +1611,10 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
   for (int ub0 = 0; ub0 < total_ublocks; ub0 += UB_BATCH) {
     p.ub0 = ub0;
     p.n_ublocks = std::min(UB_BATCH, total_ublocks - ub0);
-    // one persistent CTA per SM (all of its TMEM, ~220 KB of its shared memory); n_ublocks is even, CTA pairs need an even grid
-    const int grid = std::min(kNumSMs, p.n_ublocks) & ~1;
-    rc = launch_main(grid);
-    if (rc) return rc;
+    const int grid = std::min(2 * kNumSMs, p.n_ublocks);  // two CTAs per SM (smem- and TMEM-limited)
+    if (dump != nullptr) score_topk_kernel<true, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    else if (p.prof) score_topk_kernel<false, true><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
+    else score_topk_kernel<false, false><<<grid, TOPK_THREADS, smem, st>>>(tmapU, tmapV, p);
     TMF_LAUNCH_CHECK();
     if (dump != nullptr) continue;
     q.row0 = (long long)ub0 * BM;
@@ -1525,9 +1630,8 @@ static int score_topk_impl(const float* U, int64_t n_users, const float* V, int6
     TMF_CUDA(cudaStreamSynchronize(st));
     TMF_CUDA(cudaMemcpy(h, p.prof, 192, cudaMemcpyDeviceToHost));
     TMF_CUDA(cudaMemcpy(&novf, ovfc, 4, cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[tmf prof] per tile: MMA thread total %.0f, wait tempty %.0f, wait full %.0f cycles\n", (double)h[21] / h[22], (double)h[2] / h[22], (double)h[3] / h[22]);
-    fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-tile, n=%llu) "
-                    "wait tfull %.3g, work %.3g, maintenance %.3g cycles | overflow rows %d (main %llu, rerank %llu) | tile-end drains: %llu, %.0f cycles each\n",
+    fprintf(stderr, "[tmf prof] producer wait empty %.3g, a_empty %.3g | mma wait tempty %.3g, full %.3g | epilogue (per warp-sweep, n=%llu) "
+                    "wait tfull %.3g, work %.3g, init %.3g cycles | overflow rows %d (main %llu, rerank %llu) | tile-end drains: %llu, %.0f cycles each\n",
             (double)h[0], (double)h[1], (double)h[2], (double)h[3], h[7], (double)h[4] / h[7], (double)h[5] / h[7], (double)h[6] / h[7], novf, h[8], h[9], h[11], h[11] ? (double)h[10] / h[11] : 0.0);
     fprintf(stderr, "[tmf prof] rebuilds: first %llu x %.0f cycles, saturated %llu x %.0f, generic %llu x %.0f | pre-rebuild drains %llu x %.0f | appended entries %.4g (%.1f per row-sweep)\n",
             h[12], h[12] ? (double)h[13] / h[12] : 0.0, h[14], h[14] ? (double)h[15] / h[14] : 0.0, h[16], h[16] ? (double)h[17] / h[16] : 0.0,
