@@ -43,6 +43,27 @@ def balanced_user_bounds(row_lengths, world_size):
     return [int(max(b, a)) for a, b in zip([0] + bounds[:-1], bounds)]
 
 
+def rebalanced_user_bounds(row_weights, bounds, rank_times):
+    """Measure-and-rebalance pass for a user-sharded split.  ``bounds``: the current contiguous user ranges, ``rank_times``: the
+    compute time each rank measured for its range (same unit for all), ``row_weights``: the per-user weights the first split
+    used (interactions + sampled negatives).  What a unit of weight costs differs between the ranges -- the heaviest users'
+    ranges gather from a user table that fits the L2, the lightest users' ranges pay a fixed cost per user -- so each range is
+    taken to have its own constant cost per unit of weight, and the new boundaries sit at equal shares of the total cost."""
+    w = np.asarray(row_weights, dtype=np.float64)
+    world = len(bounds) - 1
+    cost = np.empty_like(w)
+    for rk in range(world):
+        a, b = bounds[rk], bounds[rk + 1]
+        if b > a:
+            cost[a:b] = w[a:b] * (float(rank_times[rk]) / max(float(w[a:b].sum()), 1e-30))
+    ccost = np.concatenate([[0.0], np.cumsum(cost)])
+    new = [0]
+    for rk in range(1, world):
+        new.append(int(np.searchsorted(ccost, ccost[-1] * rk / world, side="left")))
+    new.append(len(w))
+    return [int(max(b, a)) for a, b in zip([0] + new[:-1], new)]
+
+
 class GradientSync:
     """Gradient exchange used by ``TrainPlan`` for user-sharded data-parallel training.
 

@@ -262,3 +262,24 @@ def _bounded_protocol(rank, world):
 
 def test_item_sharded_bounded_protocol_host_logic():
     _spawn(_bounded_protocol)
+
+
+def test_rebalanced_user_bounds_equalises_measured_cost():
+    """Ranges with different cost per unit of weight: after one pass the boundaries sit at equal shares of the measured cost."""
+    import numpy as np
+    from teamoflow_b200.mf import dist as tdist
+    rng = np.random.default_rng(0)
+    w = np.sort(rng.pareto(1.2, 20000) * 10 + 1)[::-1].astype(np.int64) + 32   # heavy users first, like the Zipf generators
+    world = 4
+    b0 = tdist.balanced_user_bounds(w, world)
+    assert b0[0] == 0 and b0[-1] == w.size and all(x <= y for x, y in zip(b0, b0[1:]))
+    density = np.array([1.0, 1.4, 0.9, 0.6])                                 # cost per unit of weight of each CURRENT range
+    times = [density[r] * w[b0[r]:b0[r + 1]].sum() for r in range(world)]
+    b1 = tdist.rebalanced_user_bounds(w, b0, times)
+    assert b1[0] == 0 and b1[-1] == w.size and all(x <= y for x, y in zip(b1, b1[1:]))
+    cost = np.concatenate([w[b0[r]:b0[r + 1]] * density[r] for r in range(world)])  # the model the pass assumes
+    new_t = np.array([cost[b1[r]:b1[r + 1]].sum() for r in range(world)])
+    assert new_t.max() / new_t.mean() < 1.01 < max(times) / np.mean(times)
+    # equal times are a fixed point
+    assert tdist.rebalanced_user_bounds(w, b1, list(new_t)) == b1 or \
+        np.abs(np.array(tdist.rebalanced_user_bounds(w, b1, list(new_t))) - np.array(b1)).max() <= 2
