@@ -293,6 +293,35 @@ def profile_phases(plan, lr, reps=3):
     return acc
 
 
+def gather_rate_denominator(plan, kernel_gbs, reps=5):
+    """The embedding-row gathers of the user pass, alone (tmf_gather_rate: the same item rows in the same order -- every
+    interaction's row, then every user's sampled negatives -- read as float4 and summed in registers).  Where the item table fits
+    the L2 the HBM peak is no bound of that kernel; this measured rate is."""
+    from teamoflow_b200 import _abi
+    ip = plan.ip
+    Ei = plan.i.forward()
+    idx = ip.col_idx.reshape(-1).to(torch.int32)
+    if getattr(ip, "samp", None) is not None and ip.S:
+        idx = torch.cat([idx, ip.samp.reshape(-1).to(torch.int32)])
+    ld = Ei.shape[1]
+    if ld not in (64, 128):
+        return None
+    outb = torch.empty(148 * 8 * 256, dtype=torch.float32, device=Ei.device)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for it in range(2):  # warm-up, then the timed repetitions
+        ev[0].record()
+        for _ in range(reps):
+            _abi.call("tmf_gather_rate", _abi.ptr(Ei), Ei.shape[0], ld, _abi.ptr(idx), idx.numel(), _abi.ptr(outb), outb.numel())
+        ev[1].record(); torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    gbs = idx.numel() * ld * 4 / (ms * 1e-3) / 1e9
+    table_mb = Ei.shape[0] * ld * 4 / 1e6
+    return {"rows_gathered": int(idx.numel()), "row_bytes": ld * 4, "table_MB": round(table_mb, 1), "ms": ms, "gather_GBps": gbs,
+            "kernel_alg_GBps": kernel_gbs,
+            "note": "rate of the bare item-row gathers of one user pass (same rows, same order); the user pass moves "
+                    "alg_bytes_per_launch in ms_per_launch while also computing hinges, coefficients and dE_u"}
+
+
 KERNEL_OF = {"user_pass": "user_pass_kernel", "item_pass": "spmm_seg_kernel (item-major)", "embed_fwd": "spmm_seg_kernel (X.W)",
              "embed_bwd": "spmm_seg_kernel (X^T.dE)", "adam": "adam1_kernel"}
 
@@ -1074,6 +1103,11 @@ def main():
                              "frac": tb["step_gbs"] / hbm_peak},
            "phases_ms": tb["phases"], "clocks": tb["clocks"], "e2e": e2e, "gpu_launches": tb["launches"]}
 
+    if dom == "user_pass":
+        try:
+            out["roofline"]["gather_rate"] = gather_rate_denominator(plan, tb["dom_gbs"])
+        except Exception as e:  # a measurement aid must not take the line down
+            out["roofline"]["gather_rate"] = {"error": f"{type(e).__name__}: {e}"}
     plans = [plan, getattr(model, "_plan", None)]
     # ---- BASELINE configs[3]: one 10M x 2M problem, strong scaling over the ranks
     run_c4 = args.c4 == "on" or (args.c4 == "auto" and args.workload == "c3")

@@ -242,6 +242,13 @@ TMF_API int tmf_filter_seen(const int32_t* cand_idx, const float* cand_score, in
                     const int32_t* a_ptr, const int32_t* a_idx, int32_t* out_idx, float* out_score, int32_t* short_rows,
                     tmf_stream_t stream);
 
+/* Measurement aid (no reference counterpart): reads the rows table[idx[e]] (ld = 64 or 128 floats) for e < n the way
+ * tmf_user_pass gathers embedding rows, folds them into per-thread sums written to out[148 * 8 * 256].  bench.py times it on
+ * the workload's own index stream: the achievable gather rate is tmf_user_pass's roofline denominator when the table fits
+ * the L2.  Indices must lie in [0, n_rows). */
+TMF_API int tmf_gather_rate(const float* table, int64_t n_rows, int32_t ld, const int32_t* idx, int64_t n, float* out,
+                    int64_t out_len, tmf_stream_t stream);
+
 /* hits[u] = #{i in topk[u] : A[u,i] != 0}, relevant[u] = #{i : A[u,i] > 0} for CSR A (:248-254). */
 TMF_API int tmf_metrics_hits(const int32_t* topk, int64_t n_users, int32_t k, const int32_t* a_ptr, const int32_t* a_idx,
                      const float* a_val, float* hits, float* relevant, tmf_stream_t stream);

@@ -64,6 +64,7 @@ SIGNATURES = {
     "tmf_rank_rows": (_i32, [_p, _i64, _i64, _i32, _p, _p, _sz, _p]),
     "tmf_gather_unobserved": (_i32, [_p, _i64, _i64, _p, _p, _p, _p]),
     "tmf_filter_seen": (_i32, [_p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "tmf_gather_rate": (_i32, [_p, _i64, _i32, _p, _i64, _p, _i64, _p]),
     "tmf_metrics_hits": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p, _p]),
     "tmf_dcg": (_i32, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "tmf_idcg": (_i32, [_i64, _i64, _i32, _p, _p, _p, _p, _p]),

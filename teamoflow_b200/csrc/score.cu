@@ -229,6 +229,47 @@ extern "C" int tmf_filter_seen(const int32_t* cand_idx, const float* cand_score,
   return TMF_OK;
 }
 
+// ------------------------------------------------------------------ measurement aid: embedding-row gather rate
+// What user_pass_kernel does to memory, and nothing else: every group of `ld / 4` lanes reads whole rows table[idx[e]] as
+// float4 and folds them into registers (one fmaf per element keeps the loads alive).  Timed by bench.py on the workload's own
+// index stream, it is the denominator of that kernel's roofline when the table fits the L2 (C3: 6.9 MB), where the HBM
+// peak says nothing.
+template <int TPR>
+__global__ void __launch_bounds__(256) gather_rate_kernel(const float* __restrict__ table, int ld, const int32_t* __restrict__ idx,
+                                                          long long n, float* __restrict__ out) {
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+  const long long n_grp = (long long)gridDim.x * blockDim.x / TPR;
+  const int l = threadIdx.x % TPR;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long e = grp;
+  for (; e + 3 * n_grp < n; e += 4 * n_grp) {  // four independent rows in flight per lane
+    const int i0 = idx[e], i1 = idx[e + n_grp], i2 = idx[e + 2 * n_grp], i3 = idx[e + 3 * n_grp];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(table + (long long)i0 * ld) + l);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(table + (long long)i1 * ld) + l);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(table + (long long)i2 * ld) + l);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(table + (long long)i3 * ld) + l);
+    acc.x += a.x + b.x + c.x + d.x; acc.y += a.y + b.y + c.y + d.y;
+    acc.z += a.z + b.z + c.z + d.z; acc.w += a.w + b.w + c.w + d.w;
+  }
+  for (; e < n; e += n_grp) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(table + (long long)idx[e] * ld) + l);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y + acc.z + acc.w;
+}
+
+extern "C" int tmf_gather_rate(const float* table, int64_t n_rows, int32_t ld, const int32_t* idx, int64_t n, float* out,
+                               int64_t out_len, tmf_stream_t stream) {
+  TMF_REQUIRE(table && idx && out && n_rows > 0, "tmf_gather_rate: bad arguments");
+  TMF_REQUIRE(ld == 64 || ld == 128, "tmf_gather_rate: rows of 64 or 128 floats");
+  const int grid = kNumSMs * 8;
+  TMF_REQUIRE(out_len >= (int64_t)grid * 256, "tmf_gather_rate: out too small (needs 148 * 8 * 256 floats)");
+  if (ld == 64) gather_rate_kernel<16><<<grid, 256, 0, as_stream(stream)>>>(table, ld, idx, n, out);
+  else gather_rate_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(table, ld, idx, n, out);
+  TMF_LAUNCH_CHECK();
+  return TMF_OK;
+}
+
 extern "C" int tmf_predict_dense(const float* U, int64_t n_users, const float* V, int64_t n_items, int32_t n_comp, int32_t ld,
                                  float* P, tmf_stream_t stream) {
   TMF_REQUIRE(n_comp > 0 && n_comp <= ld && n_comp <= 1024, "tmf_predict_dense: bad n_components");

@@ -3,10 +3,19 @@
 // per-row running threshold and appends the few survivors to a candidate list; an fp64-accumulated
 // rerank of the candidates then makes the returned indices exact (ties -> lower item id).
 //
-// Exactness argument (DESIGN.md "top-k"): the bf16 GEMM score s~ of a pair differs from the canonical
-// score s by at most e = 2^-8 * 1.05 * |u| * |v|.  With t~ the k-th largest s~ seen so far in a row,
-// every item of the final top-k satisfies s~ >= t~ - 2E (E = e with |v| := max |v|), so the candidate
-// list is a superset of the answer; the rerank sorts it by (canonical score desc, item id asc).
+// Exactness argument (DESIGN.md "top-k"): with u~, v~ the 16-bit operands (bf16 or fp16, chosen from the data) and du = u - u~,
+// dv = v - v~, the tensor-core score s~ of a pair differs from the canonical score s by at most
+//   E[row] = |du| max_items|v| + |u~| max_items|dv| + accumulation slack          (Cauchy-Schwarz; norms from pack_bf16_kernel,
+// measured on the data, not a format constant -- row_error_kernel).  With t~ the k-th largest s~ seen so far in a row, every item
+// of the final top-k satisfies s~ >= t~ - 2E, so the candidate list is a superset of the answer; the rerank sorts it by
+// (canonical score desc, item id asc).
+//
+// Structure (round 2 re-measured the alternatives, profiles/r02_summary.md): two CTAs per SM, each with its own TMA producer,
+// MMA-issuing thread, two 128-column TMEM accumulators and FOUR epilogue warps that own their rows outright -- list, queue,
+// histogram and threshold of a row are private to one lane, so the filter needs no atomics and no cross-warp hand-shakes.  The
+// epilogue is bound by instruction issue, not by latency: designs with 16 epilogue warps per SM on shared per-row state (one
+// CTA per SM, cta_group::2 pairs, two issuing threads) ran the bare MMA pipeline at the sustained tensor peak but spent more
+// instructions per score on the shared state and were 10 % slower end to end.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>

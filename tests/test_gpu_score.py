@@ -464,3 +464,18 @@ def test_peer_alloc_export_and_barrier_single_rank():
     torch.cuda.synchronize()
     del pad
     _abi.call_nostream("tmf_peer_free", base)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ld", [64, 128])
+def test_gather_rate_aid_reads_every_row(ld):
+    """tmf_gather_rate (bench.py's roofline denominator of the user pass) folds exactly the rows it was given."""
+    import torch
+    from teamoflow_b200 import _abi
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    table = torch.randint(-8, 9, (1000, ld), generator=g, device="cuda").float() / 8     # grid values: any summation order is exact
+    idx = torch.randint(0, 1000, (50_003,), generator=g, device="cuda", dtype=torch.int32)
+    out = torch.empty(148 * 8 * 256, dtype=torch.float32, device="cuda")
+    _abi.call("tmf_gather_rate", _abi.ptr(table), 1000, ld, _abi.ptr(idx), idx.numel(), _abi.ptr(out), out.numel())
+    torch.cuda.synchronize()
+    assert float(out.double().sum()) == float(table[idx.long()].double().sum())
