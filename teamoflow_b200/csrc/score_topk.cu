@@ -28,9 +28,6 @@
 
 namespace tmf {
 
-#ifndef TMF_PASS2_REGS
-#define TMF_PASS2_REGS 0
-#endif
 // Development switches (TMF_TOPK_DEBUG / TMF_TOPK_FMT / TMF_TOPK_PROF) exist only in builds compiled with -DTMF_DEVTOOLS
 // (scripts/build_variant.sh); the product library reads no environment variable.
 #ifdef TMF_DEVTOOLS
@@ -329,12 +326,13 @@ __device__ __forceinline__ void group_max4(const uint32_t (&r)[32], float* m8) {
 }
 
 // Steady-state filter of one 64-column HALF of an accumulator tile (rows with a threshold).  Pass 1 brings the 64 columns into
-// registers (two x32 TMEM loads, one wait) and reduces them to 8 group-maximum hit bits -- no votes, no branches.  One REDUX.OR
-// of the per-lane hit masks then names the 8-column groups in which ANY row of the warp has a survivor (about 2 of 8 at 1M items).
-// Pass 2 queues those groups' survivors with predicated stores, all lanes convergent, STRAIGHT FROM THE REGISTERS of pass 1: the
-// loop over the groups is unrolled, so every hit group is its own warp-uniform block with static register indices.  (Round 1
-// re-read each hit group from TMEM: ~4.6 serialised ~300-cycle round trips per tile and warp, with 4 epilogue warps per CTA
-// nothing hides them.)  Only when some lane's queue could overflow are the groups re-read one at a time with drains in between.
+// registers (two x32 TMEM loads in flight, one wait) and reduces them to 8 group-maximum hit bits -- no votes, no branches.  One
+// REDUX.OR of the per-lane hit masks then names the 8-column groups in which ANY row of the warp has a survivor (about 2 of 8 at
+// 1M items); only those are re-read from TMEM (x8) and their survivors queued with predicated stores, all lanes convergent.
+// Measured alternatives for pass 2, all slower on the 151,552 x 1M slice (45.9 ms with this version): pushing from the pass-1
+// registers through an unrolled chain of warp-uniform blocks (51.0 ms: 16 extra branches per tile) or an indexed jump (register
+// arrays spill); issuing the next group's TMEM load under the current group's pushes (48.4 ms); slot indices from a survivor
+// mask + popc instead of the running count (47.4 ms).  The epilogue pays per instruction, not per round trip.
 __device__ __forceinline__ void epilogue_half(uint32_t t_base, int col0, RowState& st, uint32_t queue, float2* buf, uint32_t hrow,
                                               const TopkParams& p) {
   uint32_t ra[32], rb[32];
@@ -355,25 +353,6 @@ __device__ __forceinline__ void epilogue_half(uint32_t t_base, int col0, RowStat
   if (TMF_DBG(p) == 1) gmask = 0;
   if (gmask == 0) return;
   const int id0 = p.item_offset + col0;
-#if TMF_PASS2_REGS
-  if (__all_sync(0xffffffffu, st.cq + 8 * __popc(hm) <= QCAP)) {  // every lane's queue has room for all it can add
-    int cq = st.cq;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (gmask & (1u << g)) {  // warp-uniform
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = __uint_as_float(g < 4 ? ra[8 * g + j] : rb[8 * (g & 3) + j]);
-          asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %0, %1;\n\t@p st.shared.v2.f32 [%2], {%0, %3};\n\t}"
-                       ::"f"(x), "f"(thr), "r"(queue + 8u * (uint32_t)cq), "f"(__int_as_float(id0 + 8 * g + j)) : "memory");
-          cq += (x >= thr) ? 1 : 0;
-        }
-      }
-    }
-    st.cq = cq;
-    return;
-  }
-#endif
   while (gmask) {  // warp-uniform
     const int g = __ffs(gmask) - 1;
     gmask &= gmask - 1;
