@@ -712,6 +712,16 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak, us
             del shards
         except Exception as e:
             parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        # rank 0 checks rows of the merged result against the oracle; the other ranks check that they hold the same merged result
+        # (position-weighted checksum of all n_users x k indices)
+        wts = torch.arange(1, k + 1, device=dev, dtype=torch.int64)
+        chk = torch.stack([idx.long().sum(), (idx.long() * wts).sum()])
+        gl = [torch.empty_like(chk) for _ in range(world)]
+        torch.distributed.all_gather(gl, chk)
+        if rank != 0:
+            same = bool(torch.equal(gl[rank], gl[0]))
+            parity = {"ok": same, "method": "merged result identical to rank 0's (checksum over all rows); rank 0 checks rows against the oracle"}
     # the recall_at_k path at the same scale (clamped scores, CSR interaction table; single GPU only)
     recall = None
     if world == 1:
@@ -757,6 +767,7 @@ def bench_topk(n_u, n_i, r, k, steps, warmup, world, rank, hbm_peak, tf_peak, us
         torch.distributed.all_reduce(dt, op=torch.distributed.ReduceOp.MAX)
     traffic, traffic_src = _topk_traffic(n_u, n_i, world)
     return {"metric": "top-k scored user-item pairs/sec", "value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "step_ms": [round(t, 3) for t in times], "warmup": warmup,
             "config": {"workload": f"{n_u} users x {n_i} items rank-{r} top-{k} (raw scores), item-sharded x{world}", "k": k,
                        "exchange": (tdist.exchange_mode() + " (bounds all-gathered, lists merged over NVLink peer memory)") if world > 1 else "none"},
             "dtype": "16-bit tensor-core operands (fp16 or bf16, chosen from the data), fp32 accumulate in TMEM, fp64-accumulated rerank",
@@ -1210,7 +1221,7 @@ def main():
     if args.topk != "none":
         try:
             tu, ti, tr, tk = (int(x) for x in args.topk.split("x"))
-            out["topk"] = bench_topk(tu, ti, tr, tk, args.topk_steps, 1, world, rank, hbm_peak, tf_peak, args.topk_user_sharded)
+            out["topk"] = bench_topk(tu, ti, tr, tk, args.topk_steps, 3, world, rank, hbm_peak, tf_peak, args.topk_user_sharded)
             parity["c5"] = out["topk"].get("parity_check")
         except Exception as e:  # keep the primary line alive
             import traceback
