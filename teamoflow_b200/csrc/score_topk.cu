@@ -112,6 +112,25 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Whole-warp forms: every lane of a CONVERGED warp executes them with warp-uniform operands, one elected lane issues.  Issued
+// from inside an `if (lane == 0)` branch the compiler has to move each operand into the uniform registers tcgen05 reads through
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and rebuild the descriptors with vector arithmetic: ~19 SASS instructions per MMA.
+__device__ __forceinline__ void tcgen05_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -764,13 +783,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues =====================
+    {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, a_phase = 0;
       // operand format bits of the instruction descriptor: a_format (bit 7) / b_format (bit 10): 1 = bf16, 0 = fp16
       const bool f16 = p.force_fmt >= 0 ? p.force_fmt == 1 : use_fp16(p.fmt_stats);
       const uint32_t idesc = f16 ? (kIdesc & ~((1u << 7) | (1u << 10))) : kIdesc;
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));  // + (byte offset >> 4): sub-tile / k-slice (no carry out of the 14-bit field)
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
       for (int ub = blockIdx.x; ub < p.n_ublocks; ub += gridDim.x) {
         mbar_wait(smem_u32(a_full), a_phase);
         a_phase ^= 1;
@@ -779,29 +800,30 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmapU, const __grid_consta
           long long t0 = now();
           mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);  // epilogue drained this accumulator
           w_tempty += now() - t0;
+          __syncwarp();
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.kb; ++kb) {
             t0 = now();
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             w_full += now() - t0;
+            __syncwarp();
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(sA + kb * A_SUB_BYTES);
-            const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+            const uint64_t a_desc = a_desc0 + (uint64_t)((kb * A_SUB_BYTES) >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((stage * B_STAGE_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              tcgen05_mma_f16(d_tmem, umma_desc_sw128(a_addr + k * UMMA_K * 2), umma_desc_sw128(b_addr + k * UMMA_K * 2), idesc,
-                              (uint32_t)((kb | k) != 0));
-            }
-            tcgen05_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tcgen05_mma_f16_elect(d_tmem, a_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), b_desc + (uint64_t)(k * (UMMA_K * 2 / 16)), idesc,
+                                    (uint32_t)((kb | k) != 0));
+            tcgen05_commit_elect(smem_u32(&empty_bar[stage]));  // frees the smem slot when these MMAs retire
             if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(smem_u32(&tfull[acc]));  // accumulator ready for the epilogue
+          tcgen05_commit_elect(smem_u32(&tfull[acc]));  // accumulator ready for the epilogue
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
-        tcgen05_commit(smem_u32(a_empty));  // A tile may be overwritten
-        if (PROF) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
+        tcgen05_commit_elect(smem_u32(a_empty));  // A tile may be overwritten
+        if (PROF && lane == 0) { atomicAdd(p.prof + 2, (unsigned long long)w_tempty); atomicAdd(p.prof + 3, (unsigned long long)w_full); }
       }
     }
   } else if (warp >= 4) {
