@@ -87,10 +87,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol bug traps instead of hanging the GPU
+// A wait may legitimately last a whole item sweep of the other warps (the TMA producer waits for the A tile of a user block to be
+// released: 7,813 tiles at 1M items, 230k at 30M), so the dead-lock guard is a TIME bound, checked every 2^20 polls -- the first
+// version trapped after 2^22 polls (~0.1 s), which a sweep over more than ~10M items exceeds.
+constexpr long long kWaitTimeoutCycles = 1ll << 39;  // ~4-5 minutes at 1.9 GHz
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 0xfffffu) == 0) {
+      const long long t = clock64();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kWaitTimeoutCycles) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {

@@ -56,12 +56,20 @@ __device__ __forceinline__ bool mbar_try_wait_h(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) { return mbar_try_wait_h<kSuspendHintNs>(bar, parity); }
-// bounded wait: a protocol bug traps instead of hanging the GPU
+// bounded wait: a protocol bug traps instead of hanging the GPU.  The bound is TIME (checked every 2^20 polls), not a poll count:
+// how long a poll takes depends on how the hardware honours the suspend hint, and a legitimate wait can be long.
+constexpr long long kWaitTimeoutCycles = 1ll << 39;  // ~4-5 minutes at 1.9 GHz
+__device__ __forceinline__ void wait_guard(uint32_t& spins, long long& t0) {
+  if ((++spins & 0xfffffu) == 0) {
+    const long long t = clock64();
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > kWaitTimeoutCycles) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) wait_guard(spins, t0);
 }
 // epilogue flavour: an explicit sleep between polls.  16 epilogue warps per SM poll for their accumulators; every poll is a
 // shared-memory access next to the tensor core's operand reads and the TMA writes, and the wake-up latency it buys is hidden
@@ -74,17 +82,17 @@ __device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
     mbar_wait(bar, parity);
   } else {
     uint32_t spins = 0;
+    long long t0 = 0;
     while (!mbar_try_wait_h<0>(bar, parity)) {
       __nanosleep(TMF_EPI_SLEEP_NS);
-      if (++spins > (1u << 24)) __trap();
+      wait_guard(spins, t0);
     }
   }
 }
 __device__ __forceinline__ void mbar_wait_ctrl(uint32_t bar, uint32_t parity) {  // producer / MMA-issuer flavour
   uint32_t spins = 0;
-  while (!mbar_try_wait_h<kSuspendHintCtrlNs>(bar, parity)) {
-    if (++spins > (1u << 25)) __trap();
-  }
+  long long t0 = 0;
+  while (!mbar_try_wait_h<kSuspendHintCtrlNs>(bar, parity)) wait_guard(spins, t0);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(

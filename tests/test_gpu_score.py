@@ -479,3 +479,41 @@ def test_gather_rate_aid_reads_every_row(ld):
     _abi.call("tmf_gather_rate", _abi.ptr(table), 1000, ld, _abi.ptr(idx), idx.numel(), _abi.ptr(out), out.numel())
     torch.cuda.synchronize()
     assert float(out.double().sum()) == float(table[idx.long()].double().sum())
+
+
+@pytest.mark.gpu
+def test_topk_long_item_sweep_does_not_trip_the_wait_guard():
+    """30M items: one user-block sweep lasts > 0.1 s, longer than the poll-count guard of the first mbarrier waits allowed
+    (the producer waits a whole sweep for the A tile to be released).  Checked against a chunked fp64 top-k + canonical rerank."""
+    from teamoflow_b200.mf._engine import new_storage
+    from teamoflow_b200.mf.matrix_factorization import score_topk
+    n_u, n_i, r, k = 64, 30_000_000, 8, 10
+    g = torch.Generator(device="cuda"); g.manual_seed(77)
+    U = new_storage(n_u, r); U[:, :r] = torch.randn(n_u, r, generator=g, device="cuda")
+    V = new_storage(n_i, r)
+    for a in range(0, n_i, 5_000_000):
+        V[a:a + 5_000_000, :r] = torch.randn(5_000_000, r, generator=g, device="cuda")
+    idx, sc = score_topk(U, V, r, k, False, 0)
+    torch.cuda.synchronize()
+    # candidates: top-40 per row by fp64 score over item chunks, then the oracle's canonical score and tie order
+    best_s = torch.full((n_u, 40), float("-inf"), dtype=torch.float64, device="cuda")
+    best_i = torch.zeros((n_u, 40), dtype=torch.int64, device="cuda")
+    Ud = U[:, :r].double()
+    for a in range(0, n_i, 2_000_000):
+        P = Ud @ V[a:a + 2_000_000, :r].double().T
+        s, i = torch.topk(P, 40, dim=1)
+        cs, ci = torch.cat([best_s, s], 1), torch.cat([best_i, i + a], 1)
+        best_s, sel = torch.topk(cs, 40, dim=1)
+        best_i = torch.gather(ci, 1, sel)
+        del P
+    Uh, cand = cpu(U[:, :r]), best_i.cpu().numpy()
+    Vc = cpu(V[best_i.reshape(-1), :r]).reshape(n_u, 40, r)
+    got_i, got_s = cpu(idx), cpu(sc)
+    for u in range(n_u):
+        c = cand[u]
+        order0 = np.argsort(c)
+        c, Vu = c[order0], Vc[u][order0]
+        s = o.canonical_pair_scores(Uh[u:u + 1], Vu, np.zeros(c.size, np.int64), np.arange(c.size))
+        order = np.lexsort((c, -s.astype(np.float64)))[:k]
+        assert np.array_equal(got_i[u], c[order].astype(np.int32)), u
+        assert np.array_equal(got_s[u], s[order]), u
