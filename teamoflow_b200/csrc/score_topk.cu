@@ -25,6 +25,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace tmf {
 
@@ -60,131 +61,7 @@ constexpr int MAX_KB = 4;                  // n_components <= 256
 constexpr float ACC_UNIT = 2.4e-7f;
 constexpr float NORM_SLACK = 1.0001f;  // rounding of the fp32 norm arithmetic itself
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// suspend-time hint: without it try_wait returns after ~30 cycles and the single-thread TMA / MMA waiters spin at full
-// issue rate (ncu: 550 M TRYWAITs per 17 ms), stealing issue slots from the epilogue warps of their SM sub-partition
-constexpr uint32_t kSuspendHintNs = 4000;
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps instead of hanging the GPU
-// A wait may legitimately last a whole item sweep of the other warps (the TMA producer waits for the A tile of a user block to be
-// released: 7,813 tiles at 1M items, 230k at 30M), so the dead-lock guard is a TIME bound, checked every 2^20 polls -- the first
-// version trapped after 2^22 polls (~0.1 s), which a sweep over more than ~10M items exceeds.
-constexpr long long kWaitTimeoutCycles = 1ll << 39;  // ~4-5 minutes at 1.9 GHz
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0xfffffu) == 0) {
-      const long long t = clock64();
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > kWaitTimeoutCycles) __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// Whole-warp forms: every lane of a CONVERGED warp executes them with warp-uniform operands, one elected lane issues.  Issued
-// from inside an `if (lane == 0)` branch the compiler has to move each operand into the uniform registers tcgen05 reads through
-// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and rebuild the descriptors with vector arithmetic: ~19 SASS instructions per MMA.
-__device__ __forceinline__ void tcgen05_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p, e;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait_for8(uint32_t (&r)[8]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// wait that also pins the loaded registers behind it (consumers cannot be scheduled above the wait)
-__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);  // start address
-  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset
-  d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-  return d;
-}
+// PTX wrappers (mbarrier, TMA, tcgen05, TMEM loads, descriptors): tc_common.cuh, shared with gemm_tc.cu
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -1456,33 +1333,10 @@ __global__ void row_error_kernel(const float* __restrict__ unorm_bf, const float
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
+// tensor maps: make_tmap_k64 (tc_common.cuh) -- K-major 16-bit [rows, k_pad], 128-byte swizzle, box = 64 x box_rows
 static int make_tmap(CUtensorMap* map, void* base, long long rows, int k_pad, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  TMF_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
-  cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k_pad * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  TMF_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)rc);
-  return TMF_OK;
+  static_assert(BK == 64, "make_tmap_k64 boxes are 64 elements wide");
+  return make_tmap_k64(map, base, rows, k_pad, box_rows);
 }
 
 struct TopkLayout {

@@ -22,40 +22,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // suspend-time hint: without it try_wait returns after ~30 cycles and the single-thread TMA / MMA waiters spin at full
 // issue rate (ncu: 550 M TRYWAITs per 17 ms), stealing issue slots from the epilogue warps of their SM sub-partition
-// Two flavours of waiting.  The single-thread TMA-producer / MMA-issuer waits sit on the tensor pipe's critical path (with one
-// CTA per SM nobody else keeps the pipe fed while they sleep): a short suspend hint.  The epilogue waits (32 lanes x 16 warps
-// per SM spinning for an accumulator) use a long one so their polling does not eat the issue slots of the working warps.
-#ifndef TMF_HINT_CTRL_NS
-#define TMF_HINT_CTRL_NS 4000
-#endif
-#ifndef TMF_HINT_EPI_NS
-#define TMF_HINT_EPI_NS 4000
-#endif
-constexpr uint32_t kSuspendHintNs = TMF_HINT_EPI_NS;
-constexpr uint32_t kSuspendHintCtrlNs = TMF_HINT_CTRL_NS;
-template <uint32_t HINT>
-__device__ __forceinline__ bool mbar_try_wait_h(uint32_t bar, uint32_t parity) {
+constexpr uint32_t kSuspendHintNs = 4000;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  if constexpr (HINT == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(HINT)
-        : "memory");
-  }
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(kSuspendHintNs)
+      : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) { return mbar_try_wait_h<kSuspendHintNs>(bar, parity); }
 // bounded wait: a protocol bug traps instead of hanging the GPU.  The bound is TIME (checked every 2^20 polls), not a poll count:
 // how long a poll takes depends on how the hardware honours the suspend hint, and a legitimate wait can be long.
 constexpr long long kWaitTimeoutCycles = 1ll << 39;  // ~4-5 minutes at 1.9 GHz
@@ -70,29 +48,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) wait_guard(spins, t0);
-}
-// epilogue flavour: an explicit sleep between polls.  16 epilogue warps per SM poll for their accumulators; every poll is a
-// shared-memory access next to the tensor core's operand reads and the TMA writes, and the wake-up latency it buys is hidden
-// by the four accumulators in flight.
-#ifndef TMF_EPI_SLEEP_NS
-#define TMF_EPI_SLEEP_NS 0
-#endif
-__device__ __forceinline__ void mbar_wait_epi(uint32_t bar, uint32_t parity) {
-  if constexpr (TMF_EPI_SLEEP_NS == 0) {
-    mbar_wait(bar, parity);
-  } else {
-    uint32_t spins = 0;
-    long long t0 = 0;
-    while (!mbar_try_wait_h<0>(bar, parity)) {
-      __nanosleep(TMF_EPI_SLEEP_NS);
-      wait_guard(spins, t0);
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait_ctrl(uint32_t bar, uint32_t parity) {  // producer / MMA-issuer flavour
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait_h<kSuspendHintCtrlNs>(bar, parity)) wait_guard(spins, t0);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(
@@ -112,6 +67,25 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// Whole-warp forms: every lane of a CONVERGED warp executes them with warp-uniform operands, one elected lane issues.  Issued
+// from inside an `if (lane == 0)` branch the compiler has to move each operand into the uniform registers tcgen05 reads through
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and rebuild the descriptors with vector arithmetic: ~19 SASS instructions per MMA.
+__device__ __forceinline__ void tcgen05_mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -171,88 +145,6 @@ __device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
                : "memory");
-}
-
-// ---- CTA pair (cta_group::2): two SMs of a cluster execute ONE MMA of M = 256 -- each CTA supplies its 128 rows of A and its
-// half of the B tile (N/2 rows) from its own shared memory and receives its 128 rows of D in its own TMEM -- so a B stage costs
-// each SM half the shared memory and half the L2 -> SM traffic per flop.  The leader (cluster rank 0) issues; its barriers
-// collect the TMA bytes of both CTAs (peer bit of the barrier address cleared) and the epilogue arrivals of both.
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: rank 0's copy of the same offset
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load into THIS CTA's shared memory whose bytes complete on the LEADER's barrier (same offset in rank 0's shared memory)
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar & kPeerBitMask)
-      : "memory");
-}
-// commit of the pair's MMAs: arrives on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void tcgen05_commit_cg2(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_f16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// ---- warp-uniform issue.  tcgen05.mma / tcgen05.commit take their descriptors from UNIFORM registers; when the issuing code runs
-// in one lane of a divergent branch every operand is first moved R -> UR (R2UR, ~25 cycles each, serialised): measured ~147
-// cycles of issue per MMA against 64 cycles of execution, i.e. the single issuing thread, not the tensor core, set the pace.
-// These forms are executed by the WHOLE warp (uniform control flow, uniform operands) and elect one lane only for the
-// instruction itself; elect.sync picks the same lane every time, so the commits track the MMAs of that lane.
-template <bool CG2>
-__device__ __forceinline__ void tcgen05_mma_f16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  if constexpr (CG2) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-template <bool CG2>
-__device__ __forceinline__ void tcgen05_commit_warp(uint32_t bar) {
-  if constexpr (CG2) {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
-        ::"r"(bar), "h"((uint16_t)3)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-        ::"r"(bar)
-        : "memory");
-  }
-}
-
-// arrive on the LEADER's barrier from either CTA of the pair
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (8-row groups 1024 B apart)
