@@ -85,8 +85,9 @@ __global__ void peer_barrier_kernel(PeerPtrs pads, int world, int rank, uint32_t
 constexpr int kMergeWarps = 4;
 
 __global__ void __launch_bounds__(kMergeWarps * 32)
-topk_merge_lists_kernel(PeerPtrs idx_in, PeerPtrs sc_in, int G, long long row_lo, long long n_rows, int k,
-                        PeerPtrs out_idx, PeerPtrs out_sc, int n_out) {
+topk_merge_lists_kernel(const __grid_constant__ PeerPtrs idx_in, const __grid_constant__ PeerPtrs sc_in, int G, long long row_lo,
+                        long long n_rows, int k, const __grid_constant__ PeerPtrs out_idx, const __grid_constant__ PeerPtrs out_sc,
+                        int n_out) {  // __grid_constant__: the pointer tables are indexed in parameter space, not copied to the stack
   extern __shared__ __align__(16) unsigned char smraw[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long lr = (long long)blockIdx.x * kMergeWarps + w;
@@ -95,13 +96,41 @@ topk_merge_lists_kernel(PeerPtrs idx_in, PeerPtrs sc_in, int G, long long row_lo
   const int n = G * k;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw) + (size_t)w * (n + k);
   unsigned long long* outk = keys + n;
-  for (int g = 0; g < G; ++g) {
-    const int* gi = reinterpret_cast<const int*>(idx_in.p[g]) + row * k;
-    const float* gs = reinterpret_cast<const float*>(sc_in.p[g]) + row * k;
-    for (int q = lane; q < k; q += 32) {
-      const int id = __ldcv(gi + q);   // peer data written by another GPU moments ago: never from a stale line
-      const float s = __ldcv(gs + q);
-      keys[g * k + q] = ((unsigned long long)f2key_desc(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)id);
+  auto pack = [](float sc, int id) {
+    return ((unsigned long long)f2key_desc(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)id);
+  };
+  const bool vec = (k & 3) == 0;  // rows of k entries start 16-byte aligned: 128-bit loads / stores over NVLink
+  if (vec) {
+    // the loads of ALL lists are issued before the first is consumed: one NVLink round trip per row instead of one per list
+    const int k4 = k >> 2;
+    for (int q0 = 0; q0 < k4; q0 += 32) {
+      const int q4 = q0 + lane;
+      constexpr int GB = 8;  // lists per batch (registers: 8 x (int4 + float4))
+      for (int g0 = 0; g0 < G; g0 += GB) {
+        int4 iv[GB];
+        float4 sv[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          if (g0 + j < G && q4 < k4) {  // peer data written by another GPU moments ago: never from a stale line
+            iv[j] = __ldcv(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(idx_in.p[g0 + j]) + row * k) + q4);
+            sv[j] = __ldcv(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sc_in.p[g0 + j]) + row * k) + q4);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+          if (g0 + j < G && q4 < k4) {
+            unsigned long long* dst = keys + (g0 + j) * k + 4 * q4;
+            dst[0] = pack(sv[j].x, iv[j].x); dst[1] = pack(sv[j].y, iv[j].y);
+            dst[2] = pack(sv[j].z, iv[j].z); dst[3] = pack(sv[j].w, iv[j].w);
+          }
+        }
+      }
+    }
+  } else {
+    for (int g = 0; g < G; ++g) {
+      const int* gi = reinterpret_cast<const int*>(idx_in.p[g]) + row * k;
+      const float* gs = reinterpret_cast<const float*>(sc_in.p[g]) + row * k;
+      for (int q = lane; q < k; q += 32) keys[g * k + q] = pack(__ldcv(gs + q), __ldcv(gi + q));
     }
   }
   __syncwarp();
@@ -123,13 +152,27 @@ topk_merge_lists_kernel(PeerPtrs idx_in, PeerPtrs sc_in, int G, long long row_lo
     if (rank < k) outk[rank] = key;
   }
   __syncwarp();
-  for (int d = 0; d < n_out; ++d) {
-    int* oi = reinterpret_cast<int*>(out_idx.p[d]) + row * k;
-    float* os = reinterpret_cast<float*>(out_sc.p[d]) + row * k;
-    for (int q = lane; q < k; q += 32) {
-      const unsigned long long key = outk[q];
-      oi[q] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
-      os[q] = key2f_desc((uint32_t)(key >> 32));
+  auto key_id = [](unsigned long long key) { return (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull)); };
+  auto key_sc = [](unsigned long long key) { return key2f_desc((uint32_t)(key >> 32)); };
+  if (vec) {
+    const int k4 = k >> 2;
+    for (int q4 = lane; q4 < k4; q4 += 32) {
+      const unsigned long long k0 = outk[4 * q4], k1 = outk[4 * q4 + 1], k2 = outk[4 * q4 + 2], k3 = outk[4 * q4 + 3];
+      const int4 iv = make_int4(key_id(k0), key_id(k1), key_id(k2), key_id(k3));
+      const float4 sv = make_float4(key_sc(k0), key_sc(k1), key_sc(k2), key_sc(k3));
+      for (int d = 0; d < n_out; ++d) {
+        reinterpret_cast<int4*>(reinterpret_cast<int*>(out_idx.p[d]) + row * k)[q4] = iv;
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out_sc.p[d]) + row * k)[q4] = sv;
+      }
+    }
+  } else {
+    for (int d = 0; d < n_out; ++d) {
+      int* oi = reinterpret_cast<int*>(out_idx.p[d]) + row * k;
+      float* os = reinterpret_cast<float*>(out_sc.p[d]) + row * k;
+      for (int q = lane; q < k; q += 32) {
+        oi[q] = key_id(outk[q]);
+        os[q] = key_sc(outk[q]);
+      }
     }
   }
 }
