@@ -12,8 +12,8 @@
 //
 // Structure (round 2 re-measured the alternatives, profiles/r02_summary.md): two CTAs per SM, each with its own TMA producer,
 // MMA-issuing thread, two 128-column TMEM accumulators and FOUR epilogue warps that own their rows outright -- list, queue,
-// histogram and threshold of a row are private to one lane, so the filter needs no atomics and no cross-warp hand-shakes.  The
-// epilogue is bound by instruction issue, not by latency: designs with 16 epilogue warps per SM on shared per-row state (one
+// histogram and threshold of a row are private to one lane, so the filter needs no atomics and no cross-warp hand-shakes.
+// Designs with 16 epilogue warps per SM on shared per-row state (one
 // CTA per SM, cta_group::2 pairs, two issuing threads) ran the bare MMA pipeline at the sustained tensor peak but spent more
 // instructions per score on the shared state and were 10 % slower end to end.
 #include <cuda.h>
